@@ -1,0 +1,243 @@
+/*
+ * avid_b200.h — C ABI of the B200-native AVID / AVID-CMA training hot path.
+ *
+ * The reference (facebookresearch/AVID-CMA) has no FFI layer: its hot path is a
+ * chain of ATen calls issued from Python (criterions/{nce,avid,avid_cma}.py,
+ * models/{video,audio,network_blocks,av_wrapper}.py).  Every entry point below
+ * replaces one such chain; the comment on each cites the reference lines it
+ * stands in for.  The Python modules in avid_cma_b200/{criterions,models} bind
+ * these through ctypes and are the only callers.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - sizes are explicit, tensors are dense row-major in the layout stated;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises, nothing
+ *     allocates (scratch comes in through `workspace`);
+ *   - return value: 0 = ok, otherwise an AVID_E* code; avid_last_error() holds
+ *     a human-readable message for the calling thread.
+ *   - activations of the encoders are channels-last: [N, T, H, W, C] fp32
+ *     (audio uses T = 1).  Convolution filters are [taps, Cin, Cout] fp32 where
+ *     taps = kT*kH*kW in (kt, kh, kw) order ("tap-major"); avid_filter_to_tapmajor
+ *     converts from / to the PyTorch [Cout, Cin, kT, kH, kW] parameter layout.
+ */
+#ifndef AVID_B200_H
+#define AVID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVID_OK            0
+#define AVID_EINVAL        1   /* bad argument (shape, null pointer, unsupported size) */
+#define AVID_EWORKSPACE    2   /* workspace too small */
+#define AVID_ECUDA         3   /* CUDA runtime error, see avid_last_error() */
+#define AVID_EUNSUPPORTED  4
+
+#define AVID_ABI_VERSION   1
+#define AVID_MAX_KEYS      8
+#define AVID_EMB_DIM       128 /* embedding width the criterion kernels are specialised for */
+
+int         avid_version(void);
+const char* avid_last_error(void);
+/* number of kernels launched by this library since load / since the last reset */
+uint64_t    avid_launch_count(void);
+void        avid_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* Criterion: memory bank + NCE                                               */
+/* ------------------------------------------------------------------------- */
+
+/* One score key of AVIDSimilarityMemoryBank.forward (criterions/avid.py:69-75) or
+ * AVIDSimilarityPositiveExpansion.forward (criterions/avid_cma.py:169-188).
+ *   ctx      0 = video embedding is the context, 1 = audio embedding
+ *   bank     0 = targets come from view1_mem (video bank), 1 = view2_mem (audio)
+ *   pos_mode 0 = positive is the instance's own row y[b] (P = 1)
+ *            1 = positives are positive_set[y[b], :] (P = pos_k)
+ *   num_neg  this key uses the first num_neg of the shared negatives
+ *   weight   contribution of the key's loss to the total (coeff / 2)            */
+typedef struct avid_nce_key {
+    int32_t ctx;
+    int32_t bank;
+    int32_t pos_mode;
+    int32_t num_neg;
+    float   weight;
+} avid_nce_key_t;
+
+typedef struct avid_nce_args {
+    /* (B, 128) un-normalised embeddings, as returned by the towers */
+    const float*   emb_video;
+    const float*   emb_audio;
+    const int64_t* y;              /* (B) instance indices */
+    const float*   bank_video;     /* rows [row_begin, row_end) of view1_mem, (row_end-row_begin, 128) */
+    const float*   bank_audio;     /* same rows of view2_mem */
+    int64_t        num_rows;       /* N: logical bank size */
+    int64_t        row_begin;      /* first row held by this process (0 when not sharded) */
+    int64_t        row_end;        /* one past the last row held (N when not sharded) */
+    int32_t        batch;          /* B: instances scored by this call */
+    int32_t        mean_batch;     /* divisor of the batch mean (nce.py:57); 0 = batch.  A sharded caller
+                                      scoring all W*B gathered instances passes the per-rank B here. */
+    int32_t        num_neg;        /* K: shared negatives per instance */
+    /* Negatives: either given (B, K) int64 (the reference's host-drawn indices,
+     * alias_method.py:64-71 + avid.py:84-85 already applied) or NULL: drawn in the
+     * kernel from Philox4x32-10 keyed by (seed, offset), uniform over the same support. */
+    const int64_t* neg_idx;
+    uint64_t       seed;
+    uint64_t       offset;
+    const int32_t* positive_set;   /* (N, pos_k) int32 sorted ascending per row, or NULL */
+    int32_t        pos_k;
+    int32_t        num_keys;
+    avid_nce_key_t keys[AVID_MAX_KEYS];
+    const float*   avg_exp_score;  /* device scalar Z (criterions/nce.py:21-36); must be > 0 */
+    float          temperature;    /* 0.07 in the reference (avid.py:32) */
+    /* outputs */
+    float*         loss_keys;      /* (num_keys) per-key NCE loss (mean over the batch) */
+    float*         loss_total;     /* (1) sum_k weight_k * loss_k */
+    float*         grad_video;     /* (B, 128) dL_total / d emb_video (through F.normalize) */
+    float*         grad_audio;     /* (B, 128) */
+    float*         scores;         /* optional (num_keys, B, 1 + pos_k + K): s for [self | positives | negatives]; unused slots untouched */
+    int64_t*       neg_idx_out;    /* optional (B, K): the negatives that were used */
+    /* Sharded mode (row_begin/row_end a strict sub-range): the kernel only scores rows it
+     * holds and leaves partial sums in grad_hat_* / loss_part for the caller to reduce;
+     * loss_keys / loss_total / grad_* are then produced by avid_nce_finalize.  */
+    float*         grad_hat_video; /* (B, 128) partial dL/d normalised video embedding; may be NULL when not sharded */
+    float*         grad_hat_audio; /* (B, 128) */
+    float*         loss_part;      /* (num_keys, B) per-instance loss terms (before the batch mean) */
+} avid_nce_args_t;
+
+size_t avid_nce_workspace_bytes(int32_t batch, int32_t num_neg, int32_t pos_k, int32_t num_keys);
+
+/* Fused replacement for: F.normalize (avid.py:52-53), positive/negative gathers
+ * (avid.py:57-62 / avid_cma.py:158-165,196-209), bmm/T scores (avid.py:65-75),
+ * NCECriterion.forward (nce.py:38-58) for every key, the coefficient mix
+ * (avid.py:216-233 / avid_cma.py:338-359) AND the backward of all of those
+ * w.r.t. the embeddings, in one pass over the gathered rows.                      */
+int avid_nce_forward_backward(const avid_nce_args_t* args_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Second half of the sharded protocol: given (all-reduced) grad_hat_* and loss_part,
+ * produce loss_keys, loss_total, grad_video, grad_audio.                         */
+int avid_nce_finalize(const avid_nce_args_t* args_host, void* stream);
+
+/* NCECriterion.compute_partition_function (nce.py:21-36) for the first batch:
+ * mean over (b, k < keys[key].num_neg) of exp(score) for one key -> out_mean (1).
+ * In sharded mode writes the partial SUM over held rows instead (caller divides). */
+int avid_nce_partition_mean(const avid_nce_args_t* args_host, int32_t key, float* out_mean, void* workspace, size_t workspace_bytes, void* stream);
+
+/* AVIDSimilarityMemoryBank.update_memory (avid.py:103-129) after the all-gather:
+ * for i < n: if y[i] in [row_begin,row_end): m = bank[y[i]]; m = mom*m + (1-mom)*normalize(emb[i]);
+ * bank[y[i]] = normalize(m), for both banks.  Duplicate y: one of the writers wins.  */
+int avid_bank_update(float* bank_video, float* bank_audio, int64_t row_begin, int64_t row_end,
+                     const float* emb_video, const float* emb_audio, const int64_t* y, int32_t n,
+                     float momentum_video, float momentum_audio, void* stream);
+
+/* In-place row-wise x / max(||x||_2, 1e-12) on (rows, 128): init_memory (avid.py:92,95). */
+int avid_rows_l2_normalize(float* x, int64_t rows, void* stream);
+
+/* sample_negatives on device (avid.py:82-86; avid_cma.py:200-207): the same Philox stream
+ * avid_nce_forward_backward uses when neg_idx == NULL, exposed for tests and statistics. */
+int avid_sample_negatives(const int64_t* y, int32_t batch, int32_t num_neg, int64_t num_rows,
+                          const int32_t* positive_set, int32_t pos_k,
+                          uint64_t seed, uint64_t offset, int64_t* neg_idx_out, void* stream);
+
+/* CMASampler.sample_instance (avid_cma.py:42-73), all queries of [q_begin, q_end):
+ * sim = combine(V V_q^T, A A_q^T) over all N candidate rows, top-(pos_k+1) by
+ * similarity, first hit dropped, remaining pos_k indices sorted ascending.
+ *   mode 0 consensus(min) 1 union(max) 2 video 3 audio
+ * cand_* are the candidate rows [cand_begin, cand_begin+num_cand) of the banks, q_* the
+ * query rows; a sharded caller passes each shard in turn with the same top_val/top_idx
+ * scratch (running top lists, (q_end-q_begin, 64) each) and calls avid_cma_topk_finish. */
+size_t avid_cma_topk_workspace_bytes(int64_t num_queries);
+int avid_cma_topk_begin(int64_t num_queries, void* workspace, size_t workspace_bytes, void* stream);
+int avid_cma_topk_scan(const float* q_video, const float* q_audio, int64_t num_queries,
+                       const float* cand_video, const float* cand_audio, int64_t cand_begin, int64_t num_cand,
+                       int32_t mode, int32_t pos_k, void* workspace, size_t workspace_bytes, void* stream);
+int avid_cma_topk_finish(int64_t num_queries, int32_t pos_k, int32_t* positive_set_out /* (num_queries, pos_k) */,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Encoders: (2+1)D / 2D convolution stacks, train-mode BatchNorm, pools, heads */
+/* ------------------------------------------------------------------------- */
+
+typedef struct avid_conv_shape {
+    int32_t n, ti, hi, wi, ci;      /* input  [n, ti, hi, wi, ci] */
+    int32_t to, ho, wo, co;         /* output [n, to, ho, wo, co] */
+    int32_t kt, kh, kw;             /* filter taps */
+    int32_t st, sh, sw;             /* strides  */
+    int32_t pt, ph, pw;             /* zero padding */
+} avid_conv_shape_t;
+
+/* math mode of the contraction */
+#define AVID_MATH_FP32    0   /* CUDA-core fp32 FMA (exact-parity mode)             */
+#define AVID_MATH_BF16X3  1   /* tcgen05 bf16 tensor cores, 3-term split (~fp32)    */
+#define AVID_MATH_BF16    2   /* tcgen05 bf16 tensor cores, single pass             */
+
+/* nn.Conv3d / nn.Conv2d forward without bias (network_blocks.py:18,20,35-49; video.py:20;
+ * audio.py:22): out = conv(in, filt) (+ addend when non-NULL: the residual sum of
+ * network_blocks.py:58-59).  filt is tap-major [taps, ci, co].                   */
+int avid_conv_forward(const avid_conv_shape_t* s_host, const float* in, const float* filt, const float* addend,
+                      float* out, int32_t math, void* stream);
+/* gradient w.r.t. the input: din = conv_transpose(dout, filt) (+ addend) */
+int avid_conv_dgrad(const avid_conv_shape_t* s_host, const float* dout, const float* filt, const float* addend,
+                    float* din, int32_t math, void* stream);
+/* gradient w.r.t. the filter, tap-major [taps, ci, co]; dfilt must be zeroed by the caller
+ * (split over pixels, accumulated with atomics) */
+int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const float* dout, float* dfilt,
+                    int32_t math, void* stream);
+
+/* [co, ci, taps] (PyTorch parameter layout) <-> [taps, ci, co] */
+int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, int32_t co, int32_t ci, int32_t taps, void* stream);
+int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int32_t ci, int32_t taps, void* stream);
+
+/* [n, c, thw] <-> [n, thw, c] */
+int avid_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int64_t thw, void* stream);
+int avid_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int64_t thw, void* stream);
+
+/* Train-mode BatchNorm{2d,3d} statistics (PyTorch defaults eps=1e-5, momentum=0.1):
+ * per-channel sum / sum-of-squares of x (rows, c) in fp64 (stats, (2, c) doubles, zeroed
+ * by the caller), then finalize -> scale = gamma*invstd, shift = beta - mean*scale,
+ * saved mean / invstd, running stats EMA with the unbiased variance.              */
+int avid_bn_stats(const float* x, int64_t rows, int32_t c, double* stats, void* stream);
+int avid_bn_finalize(const double* stats, int64_t rows, int32_t c, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* y = relu(x*scale + shift) */
+int avid_bn_relu_forward(const float* x, const float* scale, const float* shift, float* y,
+                         int64_t rows, int32_t c, void* stream);
+/* backward of y = relu(bn(x)): sums (2, c) doubles zeroed by caller: sum(g), sum(g*xhat), g = dy*(y>0) */
+int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, int64_t rows, int32_t c,
+                                 double* sums, void* stream);
+/* dx = gamma*invstd*(g - sum_g/rows - xhat*sum_gx/rows); dgamma = sum_gx; dbeta = sum_g */
+int avid_bn_relu_backward_apply(const float* x, const float* dy, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, const double* sums,
+                                int64_t rows, int32_t c, float* dx, float* dgamma, float* dbeta, void* stream);
+
+/* nn.MaxPool3d((1,3,3), stride (1,2,2), padding (0,1,1)) on [n*t, h, w, c] (video.py:23) */
+int avid_maxpool_1x3x3_forward(const float* x, float* y, int32_t nt, int32_t h, int32_t w, int32_t c,
+                               int32_t ho, int32_t wo, void* stream);
+/* dx zeroed by caller; routes dy to the first maximal element of each window (atomic add) */
+int avid_maxpool_1x3x3_backward(const float* x, const float* y, const float* dy, float* dx,
+                                int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream);
+
+/* nn.AdaptiveMaxPool{2d,3d}(1) (video.py:41, audio.py:31): x [n, thw, c] -> y [n, c], argmax [n, c] */
+int avid_global_maxpool_forward(const float* x, float* y, int32_t* argmax, int32_t n, int64_t thw, int32_t c, void* stream);
+/* dx zeroed by caller */
+int avid_global_maxpool_backward(const float* dy, const int32_t* argmax, float* dx, int32_t n, int64_t thw, int32_t c, void* stream);
+
+/* Head (av_wrapper.py:17-33): y = x W^T + b (optionally ReLU), W in PyTorch [out, in] layout */
+int avid_linear_forward(const float* x, const float* w, const float* b, float* y,
+                        int32_t rows, int32_t in_f, int32_t out_f, int32_t relu, void* stream);
+/* dy is overwritten with dy*(y>0) when relu != 0; dx may be NULL; dw/db are overwritten */
+int avid_linear_backward(const float* x, const float* w, const float* y, float* dy,
+                         float* dx, float* dw, float* db,
+                         int32_t rows, int32_t in_f, int32_t out_f, int32_t relu, void* stream);
+
+/* elementwise helpers used by the towers */
+int avid_add_inplace(float* a, const float* b, int64_t n, void* stream);   /* a += b */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVID_B200_H */
