@@ -1,0 +1,223 @@
+"""AVID criterion on the fused CUDA NCE kernel (reference: criterions/avid.py).
+
+Same constructor kwargs, forward signature, state_dict keys (`nce_average.view1_mem`,
+`nce_average.view2_mem`, `criterion.avg_exp_score`) and loss semantics as the reference;
+the ATen chain normalize -> gather -> bmm -> exp/log -> autograd is replaced by ONE pass of
+`avid_nce_forward_backward` over the gathered bank rows (forward scores, loss terms and the
+gradient w.r.t. the embeddings share the gather), and `update_memory` by `avid_bank_update`.
+"""
+import pprint
+
+import torch
+from torch import nn
+import torch.distributed as dist
+
+from .. import ops
+from ..utils.distributed_utils import _gather_from_all
+from .nce import NCECriterion
+
+__all__ = ['AVID']
+
+# key name -> (ctx, bank): 0 = video embedding / view1_mem, 1 = audio embedding / view2_mem
+_COMBO = {'v2a': (0, 1), 'a2v': (1, 0), 'v2v': (0, 0), 'a2a': (1, 1)}
+
+
+class _FusedNCE(torch.autograd.Function):
+    """loss_total, loss_keys = f(emb_v, emb_a); the kernel already produced d loss_total / d emb."""
+
+    @staticmethod
+    def forward(ctx, emb_v, emb_a, bank, y):
+        loss_total, loss_keys, grad_v, grad_a = bank._run_fused(emb_v.detach().contiguous().float(),
+                                                                emb_a.detach().contiguous().float(), y)
+        ctx.save_for_backward(grad_v, grad_a)
+        ctx.mark_non_differentiable(loss_keys)
+        return loss_total, loss_keys
+
+    @staticmethod
+    def backward(ctx, g_total, _g_keys):
+        grad_v, grad_a = ctx.saved_tensors
+        return g_total * grad_v, g_total * grad_a, None, None
+
+
+class AVIDSimilarityMemoryBank(nn.Module):
+    def __init__(self, memory_size, embedding_dim, xModal=True, wModal=False, num_negatives=1024, momentum=0.5, device=0):
+        super().__init__()
+        if embedding_dim != 128:
+            raise ValueError('the CUDA criterion kernels are specialised for embedding_dim == 128 (got %d)' % embedding_dim)
+        self.num_negatives = num_negatives
+        self.temperature = 0.07
+        if not isinstance(momentum, (list, tuple)):
+            momentum = [momentum] * 2
+        self.momentum = momentum
+        self.device = device
+        self.memory_size = memory_size
+        self.xModal = xModal
+        self.wModal = wModal
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank() if self.distributed else 0
+        # counter-based sampler state: (seed, offset) of the Philox stream shared by all ranks' kernels
+        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self._offset = 0
+        self._owner = None           # the AVID module (gives access to the NCECriterion and coefficients)
+        self._ws = None
+        self.init_memory(memory_size, embedding_dim)
+
+    # ---- reference API -------------------------------------------------------------------------
+    def init_memory(self, num_items, embedding_dim):
+        """avid.py:88-101: N(0,1) rows, L2-normalised, rank 0's copy broadcast to every rank."""
+        dev = torch.device('cuda', self.device) if isinstance(self.device, int) else torch.device(self.device)
+        for name in ('view1_mem', 'view2_mem'):
+            mem = torch.randn(num_items, embedding_dim, device=dev)
+            ops.rows_l2_normalize_(mem)
+            self.register_buffer(name, mem)
+        if self.distributed:
+            dist.broadcast(self.view1_mem, 0)
+            dist.broadcast(self.view2_mem, 0)
+            dist.barrier()
+
+    def sample_negatives(self, y, K):
+        """avid.py:82-86: (B,K) indices uniform over [0,N) minus {y_b}, drawn on the device (Philox4x32-10).
+
+        Tests inject the reference's host-drawn indices by replacing this method on the instance."""
+        idx = ops.sample_negatives(y, K, self.memory_size, self._seed, self._offset)
+        self._offset += y.shape[0] * K
+        return idx
+
+    def update_memory(self, video_emb, audio_emb, y):
+        """avid.py:103-129.  Takes the un-normalised embeddings: the kernel normalises them itself."""
+        if self.distributed:
+            video_emb = _gather_from_all(video_emb)
+            audio_emb = _gather_from_all(audio_emb)
+            y = _gather_from_all(y)
+        ops.bank_update(self.view1_mem, self.view2_mem, video_emb, audio_emb, y, float(self.momentum[0]), float(self.momentum[1]))
+
+    # ---- fused path ----------------------------------------------------------------------------
+    def keys(self):
+        """[(name, ctx, bank, pos_mode, num_neg)] in the insertion order of avid.py:69-75."""
+        K = int(self.num_negatives)
+        out = []
+        if self.xModal:
+            out += [('v2a',) + _COMBO['v2a'] + (0, K), ('a2v',) + _COMBO['a2v'] + (0, K)]
+        if self.wModal:
+            out += [('v2v',) + _COMBO['v2v'] + (0, K), ('a2a',) + _COMBO['a2a'] + (0, K)]
+        return out
+
+    def _positive_set(self):
+        return None
+
+    def _sampler_overridden(self):
+        return 'sample_negatives' in self.__dict__
+
+    def _draw(self, y):
+        """Returns (neg_idx or None, seed, offset): None means 'draw inside the kernel'."""
+        K = int(self.num_negatives)
+        if self._sampler_overridden():
+            return self.sample_negatives(y, K).to(device=y.device, dtype=torch.int64).contiguous(), 0, 0
+        off = self._offset
+        self._offset += y.shape[0] * K
+        return None, self._seed, off
+
+    def _run_fused(self, emb_v, emb_a, y):
+        owner = self._owner
+        crit = owner.criterion
+        keys = self.keys()
+        weights = owner._key_weights([k[0] for k in keys])
+        key_tuples = [(k[1], k[2], k[3], k[4], w) for k, w in zip(keys, weights)]
+        B, K = emb_v.shape[0], int(self.num_negatives)
+        pos = self._positive_set()
+        pos_k = pos.shape[1] if pos is not None else 0
+        if self._ws is None or self._ws_shape != (B, K, pos_k, len(keys)):
+            self._ws = ops.nce_workspace(B, K, pos_k, len(keys), emb_v.device)
+            self._ws_shape = (B, K, pos_k, len(keys))
+        y = y.to(device=emb_v.device, dtype=torch.int64).contiguous()
+        neg_idx, seed, offset = self._draw(y)
+        out = torch.empty(1 + len(keys) + 2 * B * 128, dtype=torch.float32, device=emb_v.device)
+        loss_total, loss_keys = out[0:1], out[1:1 + len(keys)]
+        grad_v = out[1 + len(keys):1 + len(keys) + B * 128].view(B, 128)
+        grad_a = out[1 + len(keys) + B * 128:].view(B, 128)
+        args = ops.make_nce_args(emb_v, emb_a, y, self.view1_mem, self.view2_mem, key_tuples, K, crit.avg_exp_score,
+                                 neg_idx=neg_idx, seed=seed, offset=offset, positive_set=pos, temperature=self.temperature,
+                                 loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a)
+        if not crit.z_ready():
+            # nce.py:21-36: Z <- mean exp(score) over the negatives of the first key of the first batch
+            # (mean of the per-rank means when distributed), frozen afterwards.
+            z = torch.empty(1, dtype=torch.float32, device=emb_v.device)
+            ops.nce_partition_mean(args, 0, z, self._ws)
+            if self.distributed:
+                dist.all_reduce(z)
+                z /= dist.get_world_size()
+            crit.avg_exp_score.copy_(z.reshape(()))
+            crit.mark_ready()
+        ops.nce_forward_backward(args, self._ws)
+        return loss_total.reshape(()), loss_keys, grad_v, grad_a
+
+    def forward(self, video_emb, audio_emb, y):
+        """Returns (loss_total, {key: loss}) -- the reference returns raw scores here (avid.py:47-80) and leaves
+        the loss to NCECriterion; the fused kernel produces both at once, then the bank is updated (avid.py:78)."""
+        loss_total, loss_keys = _FusedNCE.apply(video_emb, audio_emb, self, y)
+        with torch.no_grad():
+            self.update_memory(video_emb.detach().contiguous().float(), audio_emb.detach().contiguous().float(),
+                               y.to(device=video_emb.device, dtype=torch.int64).contiguous())
+        return loss_total, {k[0]: loss_keys[i] for i, k in enumerate(self.keys())}
+
+    def __repr__(self):
+        repr_dict = {
+            'name': self._get_name(),
+            'num_negatives': int(self.num_negatives),
+            'momentum': [float(self.momentum[0]), float(self.momentum[1])],
+            'view1_buffer_size': self.view1_mem.shape,
+            'view2_buffer_size': self.view2_mem.shape,
+        }
+        return pprint.pformat(repr_dict, indent=2)
+
+
+def _restore_bank_and_partition(module, checkpoint):
+    """avid.py:187-200 / avid_cma.py:308-319: warm-start the banks and Z from another run's checkpoint."""
+    ckp = torch.load(checkpoint, map_location='cpu', weights_only=False)['train_criterion']
+    state_dict = module.state_dict()
+    state_dict['nce_average.view1_mem'] = ckp['nce_average.view1_mem']
+    state_dict['nce_average.view2_mem'] = ckp['nce_average.view2_mem']
+    Z = torch.stack([ckp[k].reshape(()).float() for k in ckp if 'avg_exp_score' in k]).mean()
+    for k in state_dict:
+        if 'avg_exp_score' in k:
+            state_dict[k] = Z
+    module.load_state_dict(state_dict)
+
+
+class AVID(nn.Module):
+    def __init__(self, num_data, embedding_dim, num_negatives=4096, momentum=0.9, xModal_coeff=1., wModal_coeff=0.,
+                 checkpoint=None, device=0):
+        super().__init__()
+        self.nce_average = AVIDSimilarityMemoryBank(memory_size=num_data, embedding_dim=embedding_dim, num_negatives=num_negatives,
+                                                    momentum=momentum, xModal=xModal_coeff > 0., wModal=wModal_coeff > 0., device=device)
+        self.nce_average = self.nce_average.cuda(device)
+        object.__setattr__(self.nce_average, '_owner', self)
+        sum_coeff = xModal_coeff + wModal_coeff
+        self.xModal_coeff = xModal_coeff / sum_coeff
+        self.wModal_coeff = wModal_coeff / sum_coeff
+        self.criterion = NCECriterion(num_data).cuda(device)
+        if checkpoint is not None:
+            _restore_bank_and_partition(self, checkpoint)
+
+    def _key_weights(self, names):
+        # avid.py:216-233: each pair of directions is averaged, then mixed with the normalised coefficients
+        return [(self.xModal_coeff if n in ('v2a', 'a2v') else self.wModal_coeff) / 2. for n in names]
+
+    def forward(self, emb1, emb2, target):
+        """emb1: video embeddings (N, D); emb2: audio embeddings (N, D); target: instance labels (N)."""
+        total_loss, losses = self.nce_average(emb1, emb2, target)
+        tb_log = {}
+        zero = total_loss.new_zeros(())
+        xModal_loss, wModal_loss = zero, zero
+        for k, loss in losses.items():
+            if k in {'v2a', 'a2v'}:
+                xModal_loss = xModal_loss + loss / 2.
+            elif k in {'v2v', 'a2a'}:
+                wModal_loss = wModal_loss + loss / 2.
+            tb_log[f'Loss/{k}'] = loss
+        tb_log['Loss/xModal'] = xModal_loss
+        tb_log['Loss/wModal'] = wModal_loss
+        return total_loss, tb_log
+
+    def set_epoch(self, epoch):
+        pass

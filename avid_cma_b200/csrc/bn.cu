@@ -1,0 +1,216 @@
+// Train-mode BatchNorm{2d,3d} (+ReLU) on channels-last activations x[rows, c] (include/avid_b200.h).
+// PyTorch semantics of the reference's nn.BatchNorm layers (models/network_blocks.py:19-21,36-45,
+// models/video.py:21, models/audio.py:23): batch statistics with the biased variance, eps inside the
+// square root, running statistics updated with the unbiased variance.  Sums are accumulated in
+// fp64 so the statistics do not depend on the (atomic) summation order to fp32 precision.
+#include "common.cuh"
+
+namespace avid {
+
+// one thread = one float4 of channels, striding over rows; blockDim.x = 256
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int64_t rows, int c, int64_t rows_per_block, double* __restrict__ out) {
+    extern __shared__ double s_red[];   // [2][rpi][c]  (rpi = row groups per iteration)
+    const int c4 = c >> 2;
+    const int rpi = 256 / c4;                    // c4 <= 256 and divides 256 (c in 64..1024, power of two)
+    const int lane_c = threadIdx.x % c4, rg = threadIdx.x / c4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    float mu[4], is[4], ga[4], be[4];
+    if (BACKWARD) {
+        *reinterpret_cast<float4*>(mu) = reinterpret_cast<const float4*>(mean)[lane_c];
+        *reinterpret_cast<float4*>(is) = reinterpret_cast<const float4*>(invstd)[lane_c];
+        *reinterpret_cast<float4*>(ga) = reinterpret_cast<const float4*>(gamma)[lane_c];
+        *reinterpret_cast<float4*>(be) = reinterpret_cast<const float4*>(beta)[lane_c];
+    }
+    for (int64_t r = r0 + rg; r < r1; r += rpi) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * c) + lane_c);
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        if (!BACKWARD) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a0[j] += (double)xv[j];
+                a1[j] += (double)xv[j] * (double)xv[j];
+            }
+        } else {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * c) + lane_c);
+            const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (xv[j] - mu[j]) * is[j];
+                const float g = (xh * ga[j] + be[j]) > 0.f ? dv[j] : 0.f;   // relu'(bn(x))
+                a0[j] += (double)g;
+                a1[j] += (double)g * (double)xh;
+            }
+        }
+    }
+    // block reduction over the row groups, then one fp64 atomic per channel per block
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s_red[(size_t)rg * c + lane_c * 4 + j] = a0[j];
+        s_red[(size_t)(rpi + rg) * c + lane_c * 4 + j] = a1[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * c; i += 256) {
+        const int which = i / c, ch = i - which * c;
+        double t = 0.0;
+        for (int k = 0; k < rpi; ++k) t += s_red[(size_t)(which * rpi + k) * c + ch];
+        atomicAdd(out + i, t);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t rows, int c, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, float* mean, float* invstd, float* scale, float* shift) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const double n = (double)rows;
+    const double m = stats[ch] / n;
+    double var = stats[c + ch] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[ch] = (float)m;
+    invstd[ch] = is;
+    const float sc = gamma[ch] * is;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - (float)m * sc;
+    if (running_mean) {
+        const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_forward_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, float* __restrict__ y,
+                                                              int64_t n4, int c4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cc);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cc);
+        float4 o;
+        o.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+        o.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+        o.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+        o.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+        reinterpret_cast<float4*>(y)[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const double* __restrict__ sums, int64_t rows, int c,
+                                                                     float* __restrict__ dx, float* dgamma, float* dbeta) {
+    const int c4 = c >> 2;
+    const int64_t n4 = rows * c4;
+    const float inv_n = 1.0f / (float)rows;
+    if (blockIdx.x == 0)
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            if (dbeta) dbeta[ch] = (float)sums[ch];
+            if (dgamma) dgamma[ch] = (float)sums[c + ch];
+        }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + i);
+        const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = cc * 4 + j;
+            const float is = invstd[ch], ga = gamma[ch];
+            const float xh = (xv[j] - mean[ch]) * is;
+            const float g = (xh * ga + beta[ch]) > 0.f ? dv[j] : 0.f;
+            const float sg = (float)sums[ch] * inv_n, sgx = (float)sums[c + ch] * inv_n;
+            o[j] = ga * is * (g - sg - xh * sgx);
+        }
+        reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+static int check_bn_shape(int64_t rows, int c) {
+    AVID_REQUIRE(rows > 0, "bn: rows must be positive");
+    AVID_REQUIRE(c >= 4 && c <= 1024 && (c & (c - 1)) == 0, "bn: c=%d must be a power of two in [4,1024]", c);
+    return AVID_OK;
+}
+
+static unsigned ew_grid(int64_t n4) {
+    int64_t b = (n4 + 255) / 256;
+    const int64_t cap = 16 * kNumSMs;
+    return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+template <bool BACKWARD>
+static int launch_reduce(const float* x, const float* dy, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, int64_t rows, int c, double* out, cudaStream_t st) {
+    const int c4 = c >> 2, rpi = 256 / c4;
+    int64_t blocks = 8 * kNumSMs;
+    int64_t rpb = (rows + blocks - 1) / blocks;
+    const int64_t min_rpb = 4 * rpi;
+    if (rpb < min_rpb) rpb = min_rpb;
+    blocks = (rows + rpb - 1) / rpb;
+    const size_t smem = sizeof(double) * 2 * rpi * c;   // = 2 * 256 * 4 * 8 = 16 KB
+    bn_reduce_kernel<BACKWARD><<<(unsigned)blocks, 256, smem, st>>>(x, dy, mean, invstd, gamma, beta, rows, c, rpb, out);
+    return check_launch(BACKWARD ? "bn_reduce_kernel<bwd>" : "bn_reduce_kernel<fwd>");
+}
+
+}  // namespace avid
+
+using namespace avid;
+
+extern "C" {
+
+int avid_bn_stats(const float* x, int64_t rows, int32_t c, double* stats, void* stream) {
+    int rc = check_bn_shape(rows, c);
+    if (rc) return rc;
+    AVID_REQUIRE(x && stats, "bn_stats: NULL pointer");
+    return launch_reduce<false>(x, nullptr, nullptr, nullptr, nullptr, nullptr, rows, c, stats, static_cast<cudaStream_t>(stream));
+}
+
+int avid_bn_finalize(const double* stats, int64_t rows, int32_t c, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream) {
+    int rc = check_bn_shape(rows, c);
+    if (rc) return rc;
+    AVID_REQUIRE(stats && gamma && beta && mean && invstd && scale && shift, "bn_finalize: NULL pointer");
+    AVID_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running_mean / running_var must both be given or both NULL");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, rows, c, gamma, beta, eps, momentum,
+                                                                                       running_mean, running_var, mean, invstd, scale, shift);
+    return check_launch("bn_finalize_kernel");
+}
+
+int avid_bn_relu_forward(const float* x, const float* scale, const float* shift, float* y, int64_t rows, int32_t c, void* stream) {
+    int rc = check_bn_shape(rows, c);
+    if (rc) return rc;
+    AVID_REQUIRE(x && scale && shift && y, "bn_relu_forward: NULL pointer");
+    const int64_t n4 = rows * (c >> 2);
+    bn_relu_forward_kernel<<<ew_grid(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, scale, shift, y, n4, c >> 2);
+    return check_launch("bn_relu_forward_kernel");
+}
+
+int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, int64_t rows, int32_t c, double* sums, void* stream) {
+    int rc = check_bn_shape(rows, c);
+    if (rc) return rc;
+    AVID_REQUIRE(x && dy && mean && invstd && gamma && beta && sums, "bn_relu_backward_reduce: NULL pointer");
+    return launch_reduce<true>(x, dy, mean, invstd, gamma, beta, rows, c, sums, static_cast<cudaStream_t>(stream));
+}
+
+int avid_bn_relu_backward_apply(const float* x, const float* dy, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, const double* sums,
+                                int64_t rows, int32_t c, float* dx, float* dgamma, float* dbeta, void* stream) {
+    int rc = check_bn_shape(rows, c);
+    if (rc) return rc;
+    AVID_REQUIRE(x && dy && mean && invstd && gamma && beta && sums && dx, "bn_relu_backward_apply: NULL pointer");
+    bn_relu_backward_apply_kernel<<<ew_grid(rows * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, dy, mean, invstd, gamma, beta, sums, rows, c, dx, dgamma, dbeta);
+    return check_launch("bn_relu_backward_apply_kernel");
+}
+
+}  // extern "C"

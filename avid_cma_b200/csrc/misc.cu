@@ -1,0 +1,144 @@
+// Layout conversions, the fused Adam step and small elementwise helpers (include/avid_b200.h).
+#include "common.cuh"
+
+namespace avid {
+
+// [n, c, thw] -> [n, thw, cpad] (channels-last, zero-padded to cpad channels), c <= 4
+__global__ void __launch_bounds__(256) nchw_to_nhwc_small_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int c,
+                                                                 int64_t thw, int cpad) {
+    const int64_t total = (int64_t)n * thw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = i / thw, s = i - img * thw;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < c; ++ch) v[ch] = __ldg(in + (img * c + ch) * thw + s);
+        for (int q = 0; q < cpad; q += 4)
+            *reinterpret_cast<float4*>(out + i * cpad + q) = q == 0 ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// generic batched 2-D transpose through shared memory: in [b, rows, cols] -> out [b, cols, rows]
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int64_t cols) {
+    __shared__ float tile[32][33];
+    const int64_t b = blockIdx.z;
+    const float* src = in + (size_t)b * rows * cols;
+    float* dst = out + (size_t)b * rows * cols;
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8)
+        if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = src[(r0 + j) * cols + c0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+        if (c0 + j < cols && r0 + tx < rows) dst[(c0 + j) * rows + r0 + tx] = tile[tx][j];
+}
+
+// PyTorch filter [co, ci, taps] -> tap-major [taps, ci_pad, co] and its transpose [taps, co, ci_pad]
+__global__ void filter_to_tap_kernel(const float* __restrict__ w, float* __restrict__ w_tap, float* __restrict__ w_tap_t, int co, int ci,
+                                     int taps, int ci_pad) {
+    const int64_t total = (int64_t)taps * ci_pad * co;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int o = (int)(i % co);
+        int64_t r = i / co;
+        const int c = (int)(r % ci_pad), t = (int)(r / ci_pad);
+        const float v = c < ci ? __ldg(w + ((size_t)o * ci + c) * taps + t) : 0.f;
+        w_tap[i] = v;
+        if (w_tap_t) w_tap_t[((size_t)t * co + o) * ci_pad + c] = v;
+    }
+}
+
+// tap-major [taps, ci_pad, co] -> PyTorch [co, ci, taps]
+__global__ void filter_from_tap_kernel(const float* __restrict__ w_tap, float* __restrict__ w, int co, int ci, int taps, int ci_pad) {
+    const int64_t total = (int64_t)co * ci * taps;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps);
+        int64_t r = i / taps;
+        const int c = (int)(r % ci), o = (int)(r / ci);
+        w[i] = __ldg(w_tap + ((size_t)t * ci_pad + c) * co + o);
+    }
+}
+
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 x = reinterpret_cast<float4*>(a)[i];
+        const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        reinterpret_cast<float4*>(a)[i] = x;
+    }
+}
+
+// torch.optim.Adam (L2 weight decay folded into the gradient, no amsgrad) on flat fp32 buffers
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                                   float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        const float gi = fmaf(weight_decay, pi, g[i] * grad_scale);
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+static unsigned grid_for(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = 16 * kNumSMs;
+    return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace avid
+
+using namespace avid;
+
+extern "C" {
+
+int avid_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int64_t thw, int32_t c_pad, void* stream) {
+    AVID_REQUIRE(in && out && n > 0 && c > 0 && thw > 0 && c_pad >= c, "nchw_to_nhwc: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (c <= 4) {
+        AVID_REQUIRE(c_pad % 4 == 0, "nchw_to_nhwc: c_pad=%d must be a multiple of 4", c_pad);
+        nchw_to_nhwc_small_kernel<<<grid_for((int64_t)n * thw), 256, 0, st>>>(in, out, n, c, thw, c_pad);
+        return check_launch("nchw_to_nhwc_small_kernel");
+    }
+    AVID_REQUIRE(c_pad == c, "nchw_to_nhwc: channel padding is only supported for c <= 4");
+    AVID_REQUIRE((thw + 31) / 32 < 65536 && n < 65536, "nchw_to_nhwc: tensor too large");
+    transpose_kernel<<<dim3((unsigned)((thw + 31) / 32), (c + 31) / 32, n), 256, 0, st>>>(in, out, c, thw);
+    return check_launch("transpose_kernel");
+}
+
+int avid_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int64_t thw, void* stream) {
+    AVID_REQUIRE(in && out && n > 0 && c > 0 && thw > 0, "nhwc_to_nchw: bad arguments");
+    AVID_REQUIRE((thw + 31) / 32 < 65536 && n < 65536, "nhwc_to_nchw: tensor too large");
+    transpose_kernel<<<dim3((c + 31) / 32, (unsigned)((thw + 31) / 32), n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, thw, c);
+    return check_launch("transpose_kernel");
+}
+
+int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, float* w_tap_t, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream) {
+    AVID_REQUIRE(w_oihw && w_tap && co > 0 && ci > 0 && taps > 0 && ci_pad >= ci, "filter_to_tapmajor: bad arguments");
+    filter_to_tap_kernel<<<grid_for((int64_t)taps * ci_pad * co), 256, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, w_tap, w_tap_t, co, ci, taps, ci_pad);
+    return check_launch("filter_to_tap_kernel");
+}
+
+int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream) {
+    AVID_REQUIRE(w_oihw && w_tap && co > 0 && ci > 0 && taps > 0 && ci_pad >= ci, "filter_from_tapmajor: bad arguments");
+    filter_from_tap_kernel<<<grid_for((int64_t)taps * ci * co), 256, 0, static_cast<cudaStream_t>(stream)>>>(w_tap, w_oihw, co, ci, taps, ci_pad);
+    return check_launch("filter_from_tap_kernel");
+}
+
+int avid_add_inplace(float* a, const float* b, int64_t n, void* stream) {
+    AVID_REQUIRE(a && b && n > 0 && n % 4 == 0, "add_inplace: n=%lld must be a positive multiple of 4", (long long)n);
+    add_inplace_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n / 4);
+    return check_launch("add_inplace_kernel");
+}
+
+int avid_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+    AVID_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step > 0, "adam_step: bad arguments");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                            weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+    return check_launch("adam_kernel");
+}
+
+}  // extern "C"

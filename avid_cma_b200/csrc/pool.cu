@@ -1,0 +1,133 @@
+// Pooling layers of the towers on channels-last activations (include/avid_b200.h):
+// nn.MaxPool3d((1,3,3),(1,2,2),(0,1,1)) of the video stem (models/video.py:23) and the global
+// nn.AdaptiveMaxPool{2d,3d}(1) (models/video.py:41, models/audio.py:31).  Bandwidth-bound: one
+// float4 of channels per thread, every global access a coalesced run of channels.
+#include <math.h>
+#include "common.cuh"
+
+namespace avid {
+
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int nt, int h, int w,
+                                                          int c4, int ho, int wo) {
+    const int64_t total = (int64_t)nt * ho * wo * c4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c4);
+        int64_t r = i / c4;
+        const int ow = (int)(r % wo);  r /= wo;
+        const int oh = (int)(r % ho);
+        const int64_t img = r / ho;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh) {
+            const int ih = oh * 2 - 1 + dh;
+            if (ih < 0 || ih >= h) continue;
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+                const int iw = ow * 2 - 1 + dw;
+                if (iw < 0 || iw >= w) continue;
+                m = max4(m, __ldg(reinterpret_cast<const float4*>(x) + ((img * h + ih) * w + iw) * c4 + cc));
+            }
+        }
+        reinterpret_cast<float4*>(y)[i] = m;
+    }
+}
+
+// gradient goes to the first maximal element of the window in (h, w) scan order, as ATen does
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          const float* __restrict__ dy, float* __restrict__ dx, int nt, int h, int w,
+                                                          int c, int ho, int wo) {
+    const int64_t total = (int64_t)nt * ho * wo * c;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        int64_t r = i / c;
+        const int ow = (int)(r % wo);  r /= wo;
+        const int oh = (int)(r % ho);
+        const int64_t img = r / ho;
+        const float g = dy[i];
+        if (g == 0.f) continue;
+        const float m = y[i];
+        bool done = false;
+        for (int dh = 0; dh < 3 && !done; ++dh) {
+            const int ih = oh * 2 - 1 + dh;
+            if (ih < 0 || ih >= h) continue;
+            for (int dw = 0; dw < 3 && !done; ++dw) {
+                const int iw = ow * 2 - 1 + dw;
+                if (iw < 0 || iw >= w) continue;
+                const int64_t off = ((img * h + ih) * w + iw) * c + ch;
+                if (x[off] == m) {
+                    atomicAdd(dx + off, g);
+                    done = true;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) global_maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int* __restrict__ argmax,
+                                                                 int n, int64_t thw, int c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    const int img = i / c, ch = i - img * c;
+    const float* p = x + (size_t)img * thw * c + ch;
+    float m = -INFINITY;
+    int am = 0;
+    for (int64_t s = 0; s < thw; ++s) {
+        const float v = __ldg(p + s * c);
+        if (v > m) { m = v; am = (int)s; }
+    }
+    y[i] = m;
+    if (argmax) argmax[i] = am;
+}
+
+__global__ void __launch_bounds__(128) global_maxpool_bwd_kernel(const float* __restrict__ dy, const int* __restrict__ argmax,
+                                                                 float* __restrict__ dx, int n, int64_t thw, int c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    const int img = i / c, ch = i - img * c;
+    dx[((size_t)img * thw + argmax[i]) * c + ch] = dy[i];
+}
+
+static unsigned grid_for(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = 16 * kNumSMs;
+    return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace avid
+
+using namespace avid;
+
+extern "C" {
+
+int avid_maxpool_1x3x3_forward(const float* x, float* y, int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream) {
+    AVID_REQUIRE(x && y && nt > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool_forward: bad arguments");
+    AVID_REQUIRE(ho == (h + 2 - 3) / 2 + 1 && wo == (w + 2 - 3) / 2 + 1, "maxpool_forward: output extent mismatch");
+    maxpool_fwd_kernel<<<grid_for((int64_t)nt * ho * wo * (c / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, nt, h, w, c / 4, ho, wo);
+    return check_launch("maxpool_fwd_kernel");
+}
+
+int avid_maxpool_1x3x3_backward(const float* x, const float* y, const float* dy, float* dx,
+                                int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream) {
+    AVID_REQUIRE(x && y && dy && dx && nt > 0 && h > 0 && w > 0 && c > 0, "maxpool_backward: bad arguments");
+    AVID_REQUIRE(ho == (h + 2 - 3) / 2 + 1 && wo == (w + 2 - 3) / 2 + 1, "maxpool_backward: output extent mismatch");
+    maxpool_bwd_kernel<<<grid_for((int64_t)nt * ho * wo * c), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, dy, dx, nt, h, w, c, ho, wo);
+    return check_launch("maxpool_bwd_kernel");
+}
+
+int avid_global_maxpool_forward(const float* x, float* y, int32_t* argmax, int32_t n, int64_t thw, int32_t c, void* stream) {
+    AVID_REQUIRE(x && y && n > 0 && thw > 0 && c > 0, "global_maxpool_forward: bad arguments");
+    global_maxpool_fwd_kernel<<<(n * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, y, argmax, n, thw, c);
+    return check_launch("global_maxpool_fwd_kernel");
+}
+
+int avid_global_maxpool_backward(const float* dy, const int32_t* argmax, float* dx, int32_t n, int64_t thw, int32_t c, void* stream) {
+    AVID_REQUIRE(dy && argmax && dx && n > 0 && thw > 0 && c > 0, "global_maxpool_backward: bad arguments");
+    global_maxpool_bwd_kernel<<<(n * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(dy, argmax, dx, n, thw, c);
+    return check_launch("global_maxpool_bwd_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+"""Tensor-level wrappers over the C ABI: validate torch CUDA tensors, pass raw pointers + the current stream.
+
+PyTorch is plumbing here (device memory and streams); every function below launches only kernels of
+libavid_b200.so.  All tensors must be contiguous CUDA tensors on the current device.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape, NceArgs, check
+
+MATH_FP32, MATH_BF16X3, MATH_BF16 = _lib.MATH_FP32, _lib.MATH_BF16X3, _lib.MATH_BF16
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32, optional=False):
+    if t is None:
+        if optional:
+            return None
+        raise ValueError("tensor is None")
+    if not t.is_cuda:
+        raise RuntimeError("avid_cma_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+# ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream around each hot kernel
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """[(family, algorithmic work (FLOP or bytes), milliseconds)] for every instrumented launch since profile_begin()."""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    return [(name, work, e0.elapsed_time(e1)) for name, work, e0, e1 in rec]
+
+
+def _t0():
+    if _prof is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _t1(e0, name, work):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _prof.append((name, work, e0, e1))
+
+
+def _conv_flops(s, ci_real=None):
+    return 2.0 * s.n * s.to * s.ho * s.wo * s.kt * s.kh * s.kw * (ci_real or s.ci) * s.co
+
+
+def launch_count():
+    return int(_lib.lib().avid_launch_count())
+
+
+def reset_launch_count():
+    _lib.lib().avid_reset_launch_count()
+
+
+# ------------------------------------------------------------------ criterion
+
+def nce_workspace(batch, num_neg, pos_k, num_keys, device):
+    n = int(_lib.lib().avid_nce_workspace_bytes(batch, num_neg, max(pos_k, 0), num_keys))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows=None, row_begin=0, row_end=None,
+                  neg_idx=None, seed=0, offset=0, positive_set=None, mean_batch=0, temperature=0.07,
+                  loss_keys=None, loss_total=None, grad_v=None, grad_a=None, scores=None, neg_idx_out=None,
+                  grad_hat_v=None, grad_hat_a=None, loss_part=None):
+    """keys: sequence of (ctx, bank, pos_mode, num_neg, weight)."""
+    a = NceArgs()
+    a.emb_video, a.emb_audio, a.y = _p(emb_v), _p(emb_a), _p(y, torch.int64)
+    a.bank_video, a.bank_audio = _p(bank_v), _p(bank_a)
+    a.num_rows = bank_v.shape[0] if num_rows is None else num_rows
+    a.row_begin = row_begin
+    a.row_end = a.num_rows if row_end is None else row_end
+    if bank_v.shape[0] != a.row_end - a.row_begin or bank_a.shape != bank_v.shape or bank_v.shape[1] != 128:
+        raise ValueError("bank shapes do not match the row range / embedding width 128")
+    if emb_v.shape != emb_a.shape or emb_v.shape[1] != 128 or y.shape[0] != emb_v.shape[0]:
+        raise ValueError("embeddings must be (B,128) and y (B,)")
+    a.batch, a.mean_batch, a.num_neg = emb_v.shape[0], mean_batch, num_neg
+    if neg_idx is not None and tuple(neg_idx.shape) != (a.batch, num_neg):
+        raise ValueError("neg_idx must be (B,K)")
+    a.neg_idx = _p(neg_idx, torch.int64, optional=True)
+    a.seed, a.offset = seed, offset
+    a.positive_set = _p(positive_set, torch.int32, optional=True)
+    a.pos_k = positive_set.shape[1] if positive_set is not None else 0
+    a.num_keys = len(keys)
+    for i, (ctx, bank, pos_mode, kn, w) in enumerate(keys):
+        a.keys[i].ctx, a.keys[i].bank, a.keys[i].pos_mode, a.keys[i].num_neg, a.keys[i].weight = ctx, bank, pos_mode, kn, w
+    a.avg_exp_score = _p(Z, optional=True)
+    a.temperature = temperature
+    a.loss_keys, a.loss_total = _p(loss_keys, optional=True), _p(loss_total, optional=True)
+    a.grad_video, a.grad_audio = _p(grad_v, optional=True), _p(grad_a, optional=True)
+    a.scores = _p(scores, optional=True)
+    a.neg_idx_out = _p(neg_idx_out, torch.int64, optional=True)
+    a.grad_hat_video, a.grad_hat_audio = _p(grad_hat_v, optional=True), _p(grad_hat_a, optional=True)
+    a.loss_part = _p(loss_part, optional=True)
+    return a
+
+
+def nce_forward_backward(args, workspace):
+    e0 = _t0()
+    nb = len({args.keys[i].bank for i in range(args.num_keys)})
+    check(_lib.lib().avid_nce_forward_backward(C.byref(args), _p(workspace, torch.uint8), workspace.numel(), _stream()))
+    _t1(e0, "nce_fused", float(nb * args.batch * (args.num_neg + 1 + args.pos_k) * 512))   # bytes: SURVEY.md §8d
+
+
+def nce_finalize(args, workspace):
+    check(_lib.lib().avid_nce_finalize(C.byref(args), _p(workspace, torch.uint8), workspace.numel(), _stream()))
+
+
+def nce_partition_mean(args, key, out, workspace):
+    check(_lib.lib().avid_nce_partition_mean(C.byref(args), key, _p(out), _p(workspace, torch.uint8), workspace.numel(), _stream()))
+
+
+def bank_update(bank_v, bank_a, emb_v, emb_a, y, mom_v, mom_a, row_begin=0, row_end=None):
+    row_end = row_begin + bank_v.shape[0] if row_end is None else row_end
+    check(_lib.lib().avid_bank_update(_p(bank_v), _p(bank_a), row_begin, row_end, _p(emb_v), _p(emb_a), _p(y, torch.int64),
+                                      y.shape[0], float(mom_v), float(mom_a), _stream()))
+
+
+def rows_l2_normalize_(x):
+    check(_lib.lib().avid_rows_l2_normalize(_p(x), x.shape[0], _stream()))
+    return x
+
+
+def sample_negatives(y, num_neg, num_rows, seed, offset, positive_set=None):
+    out = torch.empty(y.shape[0], num_neg, dtype=torch.int64, device=y.device)
+    check(_lib.lib().avid_sample_negatives(_p(y, torch.int64), y.shape[0], num_neg, num_rows, _p(positive_set, torch.int32, optional=True),
+                                           positive_set.shape[1] if positive_set is not None else 0, seed, offset, _p(out, torch.int64), _stream()))
+    return out
+
+
+CMA_MODES = {"consensus": 0, "union": 1, "video": 2, "audio": 3}
+
+
+def cma_topk(q_video, q_audio, cand_shards, pos_k, mode="consensus"):
+    """cand_shards: iterable of (cand_video, cand_audio, cand_begin).  Returns (Q, pos_k) int32 sorted positives."""
+    if mode not in CMA_MODES:
+        raise ValueError(mode)
+    L = _lib.lib()
+    nq = q_video.shape[0]
+    ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(nq)), dtype=torch.uint8, device=q_video.device)
+    wp, wn = _p(ws, torch.uint8), ws.numel()
+    check(L.avid_cma_topk_begin(nq, wp, wn, _stream()))
+    for cv, ca, begin in cand_shards:
+        check(L.avid_cma_topk_scan(_p(q_video), _p(q_audio), nq, _p(cv), _p(ca), begin, cv.shape[0], CMA_MODES[mode], pos_k, wp, wn, _stream()))
+    out = torch.empty(nq, pos_k, dtype=torch.int32, device=q_video.device)
+    check(L.avid_cma_topk_finish(nq, pos_k, _p(out, torch.int32), wp, wn, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ encoders
+
+def conv_shape(n, ti, hi, wi, ci, co, kernel, stride, padding):
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = padding
+    to, ho, wo = (ti + 2 * pt - kt) // st + 1, (hi + 2 * ph - kh) // sh + 1, (wi + 2 * pw - kw) // sw + 1
+    return ConvShape(n, ti, hi, wi, ci, to, ho, wo, co, kt, kh, kw, st, sh, sw, pt, ph, pw)
+
+
+def conv_forward(s, x, w_tap, addend=None, out=None, math=MATH_FP32, ci_real=None):
+    if out is None:
+        out = torch.empty(s.n, s.to, s.ho, s.wo, s.co, dtype=torch.float32, device=x.device)
+    assert x.numel() == s.n * s.ti * s.hi * s.wi * s.ci and w_tap.numel() >= s.kt * s.kh * s.kw * s.ci * s.co
+    e0 = _t0()
+    check(_lib.lib().avid_conv_forward(C.byref(s), _p(x), _p(w_tap), _p(addend, optional=True), _p(out), math, _stream()))
+    _t1(e0, "conv_forward", _conv_flops(s, ci_real))
+    return out
+
+
+def conv_dgrad(s, dout, w_tap_t, addend=None, out=None, math=MATH_FP32):
+    if out is None:
+        out = torch.empty(s.n, s.ti, s.hi, s.wi, s.ci, dtype=torch.float32, device=dout.device)
+    assert dout.numel() == s.n * s.to * s.ho * s.wo * s.co
+    e0 = _t0()
+    check(_lib.lib().avid_conv_dgrad(C.byref(s), _p(dout), _p(w_tap_t), _p(addend, optional=True), _p(out), math, _stream()))
+    _t1(e0, "conv_dgrad", _conv_flops(s))
+    return out
+
+
+def conv_wgrad(s, x, dout, math=MATH_FP32, ci_real=None):
+    dw = torch.zeros(s.kt * s.kh * s.kw, s.ci, s.co, dtype=torch.float32, device=x.device)
+    e0 = _t0()
+    check(_lib.lib().avid_conv_wgrad(C.byref(s), _p(x), _p(dout), _p(dw), math, _stream()))
+    _t1(e0, "conv_wgrad", _conv_flops(s, ci_real))
+    return dw
+
+
+def filter_to_tapmajor(w, ci_pad=None, transpose=True):
+    """PyTorch conv weight (co, ci, *k) -> ([taps, ci_pad, co], [taps, co, ci_pad] or None)."""
+    co, ci = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    ci_pad = ci if ci_pad is None else ci_pad
+    w_tap = torch.empty(taps, ci_pad, co, dtype=torch.float32, device=w.device)
+    w_tap_t = torch.empty(taps, co, ci_pad, dtype=torch.float32, device=w.device) if transpose else None
+    check(_lib.lib().avid_filter_to_tapmajor(_p(w), _p(w_tap), _p(w_tap_t, optional=True), co, ci, taps, ci_pad, _stream()))
+    return w_tap, w_tap_t
+
+
+def filter_from_tapmajor(dw_tap, like):
+    co, ci = like.shape[0], like.shape[1]
+    taps, ci_pad = dw_tap.shape[0], dw_tap.shape[1]
+    out = torch.empty_like(like)
+    check(_lib.lib().avid_filter_from_tapmajor(_p(dw_tap), _p(out), co, ci, taps, ci_pad, _stream()))
+    return out
+
+
+def nchw_to_nhwc(x, c_pad=None):
+    """(n, c, *spatial) -> (n, *spatial, c_pad)."""
+    n, c = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:])
+    thw = x[0, 0].numel()
+    c_pad = c if c_pad is None else c_pad
+    out = torch.empty((n,) + sp + (c_pad,), dtype=torch.float32, device=x.device)
+    check(_lib.lib().avid_nchw_to_nhwc(_p(x), _p(out), n, c, thw, c_pad, _stream()))
+    return out
+
+
+def nhwc_to_nchw(x):
+    """(n, *spatial, c) -> (n, c, *spatial)."""
+    n, c = x.shape[0], x.shape[-1]
+    sp = tuple(x.shape[1:-1])
+    out = torch.empty((n, c) + sp, dtype=torch.float32, device=x.device)
+    check(_lib.lib().avid_nhwc_to_nchw(_p(x), _p(out), n, c, x[0, ..., 0].numel(), _stream()))
+    return out
+
+
+class BNState:
+    """Per-call buffers of one train-mode BatchNorm: statistics, saved mean/invstd, folded scale/shift."""
+    __slots__ = ("stats", "mean", "invstd", "scale", "shift")
+
+    def __init__(self, c, device):
+        self.stats = torch.zeros(2, c, dtype=torch.float64, device=device)
+        buf = torch.empty(4, c, dtype=torch.float32, device=device)
+        self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
+
+
+def bn_train_stats(x, gamma, beta, running_mean, running_var, eps=BN_EPS, momentum=BN_MOMENTUM):
+    """x (..., c) channels-last.  Computes batch statistics, updates running stats, returns BNState."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    s = BNState(c, x.device)
+    L = _lib.lib()
+    check(L.avid_bn_stats(_p(x), rows, c, _p(s.stats, torch.float64), _stream()))
+    check(L.avid_bn_finalize(_p(s.stats, torch.float64), rows, c, _p(gamma), _p(beta), eps, momentum,
+                             _p(running_mean, optional=True), _p(running_var, optional=True),
+                             _p(s.mean), _p(s.invstd), _p(s.scale), _p(s.shift), _stream()))
+    return s
+
+
+def bn_relu_forward(x, scale, shift, out=None):
+    c = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().avid_bn_relu_forward(_p(x), _p(scale), _p(shift), _p(out), x.numel() // c, c, _stream()))
+    return out
+
+
+def bn_relu_backward(x, dy, s, gamma, beta, dx=None):
+    """Backward of y = relu(bn_train(x)).  Returns (dx, dgamma, dbeta)."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    sums = torch.zeros(2, c, dtype=torch.float64, device=x.device)
+    if dx is None:
+        dx = torch.empty_like(x)
+    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+    L = _lib.lib()
+    check(L.avid_bn_relu_backward_reduce(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), rows, c, _p(sums, torch.float64), _stream()))
+    check(L.avid_bn_relu_backward_apply(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), _p(sums, torch.float64), rows, c,
+                                        _p(dx), _p(dgamma), _p(dbeta), _stream()))
+    return dx, dgamma, dbeta
+
+
+def maxpool_1x3x3_forward(x):
+    """x (n, t, h, w, c) -> (n, t, ho, wo, c)."""
+    n, t, h, w, c = x.shape
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    y = torch.empty(n, t, ho, wo, c, dtype=torch.float32, device=x.device)
+    check(_lib.lib().avid_maxpool_1x3x3_forward(_p(x), _p(y), n * t, h, w, c, ho, wo, _stream()))
+    return y
+
+
+def maxpool_1x3x3_backward(x, y, dy):
+    n, t, h, w, c = x.shape
+    dx = torch.zeros_like(x)
+    check(_lib.lib().avid_maxpool_1x3x3_backward(_p(x), _p(y), _p(dy), _p(dx), n * t, h, w, c, y.shape[2], y.shape[3], _stream()))
+    return dx
+
+
+def global_maxpool_forward(x):
+    """x (n, ..., c) -> (y (n, c), argmax (n, c) int32)."""
+    n, c = x.shape[0], x.shape[-1]
+    thw = x.numel() // (n * c)
+    y = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    am = torch.empty(n, c, dtype=torch.int32, device=x.device)
+    check(_lib.lib().avid_global_maxpool_forward(_p(x), _p(y), _p(am, torch.int32), n, thw, c, _stream()))
+    return y, am
+
+
+def global_maxpool_backward(dy, argmax, shape):
+    dx = torch.zeros(shape, dtype=torch.float32, device=dy.device)
+    n, c = dy.shape
+    check(_lib.lib().avid_global_maxpool_backward(_p(dy), _p(argmax, torch.int32), _p(dx), n, dx.numel() // (n * c), c, _stream()))
+    return dx
+
+
+def linear_forward(x, w, b, relu):
+    rows, in_f = x.shape
+    out_f = w.shape[0]
+    y = torch.empty(rows, out_f, dtype=torch.float32, device=x.device)
+    check(_lib.lib().avid_linear_forward(_p(x), _p(w), _p(b, optional=True), _p(y), rows, in_f, out_f, int(relu), _stream()))
+    return y
+
+
+def linear_backward(x, w, y, dy, relu, need_dx=True):
+    """dy is modified in place when relu.  Returns (dx or None, dw, db)."""
+    rows, in_f = x.shape
+    out_f = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dw, db = torch.empty_like(w), torch.empty(out_f, dtype=torch.float32, device=x.device)
+    check(_lib.lib().avid_linear_backward(_p(x), _p(w), _p(y, optional=True), _p(dy), _p(dx, optional=True), _p(dw), _p(db),
+                                          rows, in_f, out_f, int(relu), _stream()))
+    return dx, dw, db
+
+
+def add_(a, b):
+    check(_lib.lib().avid_add_inplace(_p(a), _p(b), a.numel(), _stream()))
+    return a
+
+
+def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    check(_lib.lib().avid_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), step, lr, betas[0], betas[1], eps,
+                                    weight_decay, grad_scale, _stream()))

@@ -1,0 +1,31 @@
+"""Adam on the libavid_b200 kernel: the reference builds torch.optim.Adam(lr, weight_decay, betas)
+(utils/main_utils.py:250-256); this optimizer has the same update rule and state_dict layout
+(`exp_avg`, `exp_avg_sq`, `step` per parameter) but applies it with avid_adam_step."""
+import torch
+
+from . import ops
+
+
+class Adam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st['step'] += 1
+                ops.adam_step_(p.data, p.grad.contiguous(), st['exp_avg'], st['exp_avg_sq'], st['step'], group['lr'],
+                               group['betas'], group['eps'], group['weight_decay'], grad_scale)
+        return loss

@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""Headline benchmark: AVID training clips/sec (video+audio pair) on N B200s (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = the reference's run_phase body (main-avid.py:155-184): forward of both towers, AVID criterion
+(fused gather + NCE + bank update), backward, Adam.  Workload = BASELINE.json configs[1]: Cross-N1024 AVID,
+240k-entry memory bank, batch 64/GPU of 8x3x224x224 clips + 1x200x257 spectrograms, synthetic data, random-init
+weights.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "AVID training clips/sec (video+audio pair)"
+UNIT = "clips/s"
+BANK_ROWS = 240000
+NUM_NEG = 1024
+FWD_GFLOP_PER_CLIP = 27.134       # SURVEY.md §8d (conv + linear, 2*MAC) at 8x3x224x224 + 1x200x257
+STEP_GFLOP_PER_CLIP = 75.66
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--spec", type=int, nargs=2, default=[200, 257])
+    ap.add_argument("--bank", type=int, default=BANK_ROWS)
+    ap.add_argument("--negatives", type=int, default=NUM_NEG)
+    ap.add_argument("--math", default=os.environ.get("AVID_MATH", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_of(a, n_gpus):
+    return {"workload": "Cross-N1024 AVID, 240k-entry memory bank (Kinetics-shape), batch=64/GPU 8x3x224x224 + 1x200x257",
+            "global_batch": a.batch * n_gpus, "batch_per_gpu": a.batch, "clip": [3, a.frames, a.size, a.size], "spectrogram": [1] + list(a.spec),
+            "bank_rows": a.bank, "num_negatives": a.negatives, "optimizer": "adam lr 2e-4 wd 1e-5",
+            "parallelism": f"dp{n_gpus}", "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(a, steps, warmup, batch):
+    """The reference's CPU path (oracle port: torch-CPU restatement of towers + criterion + Adam) on this box's host cores."""
+    from oracle import synth
+    from oracle.step import OracleTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr = OracleTrainer(a.bank, num_negatives=a.negatives, seed=0)
+    g = torch.Generator().manual_seed(0)
+    video = torch.randn(batch, 3, a.frames, a.size, a.size, generator=g)
+    audio = torch.randn(batch, 1, a.spec[0], a.spec[1], generator=g)
+    for i in range(warmup):
+        tr.step(video, audio, synth.instance_ids(batch, a.bank, seed=i))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tr.step(video, audio, synth.instance_ids(batch, a.bank, seed=100 + i))
+    dt = time.perf_counter() - t0
+    return {"value": batch * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} full training steps (fwd + AVID criterion + bwd + Adam) of {batch} clips at the workload's clip/spectrogram shape, "
+                      f"bank {a.bank}, K={a.negatives}, torch-CPU oracle port of the reference, {cores} threads, after {warmup} warm-up"}, dt / steps
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, sec = cpu_reference(a, a.steps, a.warmup, a.cpu_sample_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(a, a.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch.distributed as dist
+    from avid_cma_b200 import models, ops, optim
+    from avid_cma_b200.criterions import AVID
+    from avid_cma_b200.models import _tower
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["AVID_MATH"] = a.math
+
+    torch.manual_seed(0)
+    model = models.av_wrapper('R2Plus1D', {'depth': 18}, 'Conv2D', {'depth': 10}, proj_dim=[512, 512, 128]).to(dev).train()
+    crit = AVID(num_data=a.bank, embedding_dim=model.out_dim, num_negatives=a.negatives, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=local)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
+
+    B = a.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    nbuf = 2
+    host = [(torch.randn(B, 3, a.frames, a.size, a.size, generator=g).pin_memory(), torch.randn(B, 1, a.spec[0], a.spec[1], generator=g).pin_memory())
+            for _ in range(nbuf)]
+    resident = [(v.to(dev), s.to(dev)) for v, s in host]
+    perm = torch.randperm(a.bank, generator=torch.Generator().manual_seed(7))
+    total_steps = 2 * (a.warmup + a.steps) + 4
+    ys_host = [perm[(i * world + rank) * B % (a.bank - B):][:B].contiguous().pin_memory() for i in range(total_steps)]
+    ys_dev = [y.to(dev) for y in ys_host]
+
+    def step(video, audio, y):
+        ve, ae = net(video, audio)
+        loss, _ = crit(ve, ae, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it = 0
+    for _ in range(a.warmup):
+        step(*resident[it % nbuf], ys_dev[it]); it += 1
+    # ---- timed region 1: inputs resident in HBM ----
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.reset_launch_count()
+    ops.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step(*resident[it % nbuf], ys_dev[it]); it += 1
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count()
+    prof = ops.profile_end()
+    clocks = sampler.summary()
+
+    # ---- timed region 2: end to end, host buffers -> H2D each step, loss.item() each step ----
+    for _ in range(min(2, a.warmup)):
+        v, s = host[it % nbuf]
+        float(step(v.to(dev, non_blocking=True), s.to(dev, non_blocking=True), ys_host[it].to(dev, non_blocking=True))); it += 1
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(a.steps):
+        v, s = host[it % nbuf]
+        loss = step(v.to(dev, non_blocking=True), s.to(dev, non_blocking=True), ys_host[it].to(dev, non_blocking=True)); it += 1
+        last_loss = loss.item()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0]) + ys_host[0].numel() * 8
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clips = B * world * a.steps
+    # roofline of the dominant kernel family, from CUDA events recorded around every launch of the timed region
+    fam = {}
+    for name, work, dur in prof:
+        f = fam.setdefault(name, [0.0, 0.0, 0])
+        f[0] += work; f[1] += dur; f[2] += 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline, families = None, {}
+    for name, (work, dur, cnt) in fam.items():
+        rate = work / (dur * 1e-3) if dur > 0 else 0.0
+        families[name] = {"launches": cnt, "ms_per_step": dur / a.steps, "share_of_step": dur / ms}
+        families[name]["GB/s" if name.startswith("nce") else "TFLOP/s"] = rate / (1e9 if name.startswith("nce") else 1e12)
+    if fam:
+        top = max((n for n in fam if n.startswith("conv")), key=lambda n: fam[n][1])
+        work, dur, cnt = fam[top]
+        ach = work / (dur * 1e-3) / 1e12
+        roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
+                    "launches_timed": cnt, "avg_launch_ms": dur / cnt, "families": families}
+
+    line = {"metric": METRIC, "value": clips / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (3-term split, f32 accumulate)", "bf16": "bf16"}[a.math], "data": "synthetic",
+            "config": config_of(a, world), "clocks": clocks,
+            "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches, "roofline": roofline, "last_loss": last_loss,
+            "step_tflops": clips * STEP_GFLOP_PER_CLIP * 1e9 / (ms * 1e-3) / 1e12 / world}
+    if world == 1 and not a.no_cpu_baseline:
+        cb, _ = cpu_reference(a, 2, 1, a.cpu_sample_batch)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

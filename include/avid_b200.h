@@ -118,7 +118,7 @@ int avid_nce_forward_backward(const avid_nce_args_t* args_host, void* workspace,
 
 /* Second half of the sharded protocol: given (all-reduced) grad_hat_* and loss_part,
  * produce loss_keys, loss_total, grad_video, grad_audio.                         */
-int avid_nce_finalize(const avid_nce_args_t* args_host, void* stream);
+int avid_nce_finalize(const avid_nce_args_t* args_host, void* workspace, size_t workspace_bytes, void* stream);
 
 /* NCECriterion.compute_partition_function (nce.py:21-36) for the first batch:
  * mean over (b, k < keys[key].num_neg) of exp(score) for one key -> out_mean (1).
@@ -178,20 +178,24 @@ typedef struct avid_conv_shape {
  * network_blocks.py:58-59).  filt is tap-major [taps, ci, co].                   */
 int avid_conv_forward(const avid_conv_shape_t* s_host, const float* in, const float* filt, const float* addend,
                       float* out, int32_t math, void* stream);
-/* gradient w.r.t. the input: din = conv_transpose(dout, filt) (+ addend) */
-int avid_conv_dgrad(const avid_conv_shape_t* s_host, const float* dout, const float* filt, const float* addend,
+/* gradient w.r.t. the input: din = conv_transpose(dout, filt) (+ addend); filt_t is the transposed
+ * tap-major filter [taps, co, ci] written by avid_filter_to_tapmajor */
+int avid_conv_dgrad(const avid_conv_shape_t* s_host, const float* dout, const float* filt_t, const float* addend,
                     float* din, int32_t math, void* stream);
 /* gradient w.r.t. the filter, tap-major [taps, ci, co]; dfilt must be zeroed by the caller
  * (split over pixels, accumulated with atomics) */
 int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const float* dout, float* dfilt,
                     int32_t math, void* stream);
 
-/* [co, ci, taps] (PyTorch parameter layout) <-> [taps, ci, co] */
-int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, int32_t co, int32_t ci, int32_t taps, void* stream);
-int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int32_t ci, int32_t taps, void* stream);
+/* PyTorch parameter layout [co, ci, taps] -> tap-major [taps, ci_pad, co] (channels ci..ci_pad-1 zero) and,
+ * when w_tap_t != NULL, its transpose [taps, co, ci_pad] (the filter operand of avid_conv_dgrad). */
+int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, float* w_tap_t, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream);
+/* tap-major [taps, ci_pad, co] (a filter gradient) -> PyTorch layout [co, ci, taps] */
+int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream);
 
-/* [n, c, thw] <-> [n, thw, c] */
-int avid_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int64_t thw, void* stream);
+/* [n, c, thw] -> [n, thw, c_pad] (c_pad > c only for c <= 4: the 3-channel clip / 1-channel spectrogram)
+ * and back [n, thw, c] -> [n, c, thw] */
+int avid_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int64_t thw, int32_t c_pad, void* stream);
 int avid_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int64_t thw, void* stream);
 
 /* Train-mode BatchNorm{2d,3d} statistics (PyTorch defaults eps=1e-5, momentum=0.1):
@@ -236,6 +240,12 @@ int avid_linear_backward(const float* x, const float* w, const float* y, float* 
 
 /* elementwise helpers used by the towers */
 int avid_add_inplace(float* a, const float* b, int64_t n, void* stream);   /* a += b */
+
+/* torch.optim.Adam.step (utils/main_utils.py:250-256: lr, betas, weight_decay as L2 added to the gradient)
+ * on flat fp32 buffers; `step` counts from 1; the gradient is multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce). */
+int avid_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,74 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads and exports every symbol the header declares;
+argument validation reports errors without touching a GPU; the Python layer refuses CPU tensors (no fallback)."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from avid_cma_b200 import _lib, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/avid_b200.h but not exported"
+    assert set(declared) == set(_lib._SIGNATURES), "ctypes signatures out of sync with the header"
+    assert lib.avid_version() == 1
+
+
+def test_struct_layout_matches_header(lib):
+    # avid_nce_key_t: 4 x int32 + float; avid_conv_shape_t: 18 x int32
+    assert C.sizeof(_lib.NceKey) == 20
+    assert C.sizeof(_lib.ConvShape) == 72
+    assert _lib.NceArgs.keys.offset % 4 == 0 and C.sizeof(_lib.NceArgs) % 8 == 0
+
+
+def test_workspace_queries_are_host_only(lib):
+    assert lib.avid_nce_workspace_bytes(64, 1024, 0, 2) > 64 * 128 * 4 * 2
+    assert lib.avid_nce_workspace_bytes(0, 1024, 0, 2) == 0
+    assert lib.avid_cma_topk_workspace_bytes(1000) == 1000 * 64 * 8
+
+
+def test_invalid_arguments_report_einval(lib):
+    rc = lib.avid_bank_update(None, None, 0, 10, None, None, None, 4, 0.5, 0.5, None)
+    assert rc == 1 and b"NULL" in lib.avid_last_error()
+    s = _lib.ConvShape(1, 1, 8, 8, 3, 1, 8, 8, 64, 1, 3, 3, 1, 1, 1, 0, 1, 1)   # ci = 3 is not a padded channel count
+    rc = lib.avid_conv_forward(C.byref(s), C.c_void_p(16), C.c_void_p(16), None, C.c_void_p(16), 0, None)
+    assert rc == 1 and b"ci=3" in lib.avid_last_error()
+    s = _lib.ConvShape(1, 1, 8, 8, 4, 1, 8, 8, 64, 1, 3, 3, 1, 1, 1, 0, 1, 1)
+    rc = lib.avid_conv_forward(C.byref(s), C.c_void_p(16), C.c_void_p(16), None, C.c_void_p(16), 7, None)
+    assert rc == 4   # unknown math mode -> AVID_EUNSUPPORTED, before any launch
+
+
+def test_ops_refuse_cpu_tensors():
+    from avid_cma_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.rows_l2_normalize_(torch.zeros(4, 128))
+    from avid_cma_b200.models import R2Plus1D
+    with pytest.raises(RuntimeError, match="CUDA"):
+        R2Plus1D(depth=10)(torch.zeros(1, 3, 2, 16, 16))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(os.path.dirname(_lib.LIB_PATH), "no_such_lib.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_model_state_dict_matches_reference_layout():
+    from avid_cma_b200 import models
+    from oracle import towers
+    m = models.av_wrapper('R2Plus1D', {'depth': 18}, 'Conv2D', {'depth': 10}, proj_dim=[512, 512, 128])
+    sd, ref = m.state_dict(), towers.state_dict_template()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
+    assert m.out_dim == 128 and m.video_model.out_dim == 512 and m.audio_model.out_dim == 512
