@@ -13,11 +13,13 @@ import torch.nn as nn
 from .. import ops
 
 
-def _triple(v):
+def _triple(v, fill=1):
+    """(t, h, w) view of a Conv2d / Conv3d hyper-parameter; `fill` is the value of the missing t entry
+    (1 for kernel_size / stride, 0 for padding)."""
     if isinstance(v, int):
-        return (1, v, v)
+        return (fill, v, v)
     v = tuple(v)
-    return v if len(v) == 3 else (1,) + v
+    return v if len(v) == 3 else (fill,) + v
 
 
 def pad_channels(c):
@@ -35,7 +37,7 @@ class ConvBNReLU:
     @staticmethod
     def forward(x, conv, bn, training, math, addend=None):
         n, t, h, w, ci = x.shape
-        k, s, p = _triple(conv.kernel_size), _triple(conv.stride), _triple(conv.padding)
+        k, s, p = _triple(conv.kernel_size), _triple(conv.stride), _triple(conv.padding, 0)
         shape = ops.conv_shape(n, t, h, w, ci, conv.out_channels, k, s, p)
         w_tap, w_tap_t = ops.filter_to_tapmajor(conv.weight.detach(), ci_pad=ci)
         z = ops.conv_forward(shape, x, w_tap, addend=addend, math=math, ci_real=conv.in_channels)
@@ -116,7 +118,7 @@ class BasicR2P1DBlock(nn.Module):
         if self.res:
             n, t, h, w, ci = x.shape
             rc = self.res_conv
-            rshape = ops.conv_shape(n, t, h, w, ci, rc.out_channels, _triple(rc.kernel_size), _triple(rc.stride), _triple(rc.padding))
+            rshape = ops.conv_shape(n, t, h, w, ci, rc.out_channels, _triple(rc.kernel_size), _triple(rc.stride), _triple(rc.padding, 0))
             rw, rw_t = ops.filter_to_tapmajor(rc.weight.detach(), ci_pad=ci)
             r = ops.conv_forward(rshape, x, rw, math=math)
             sres = (rshape, rw_t)

@@ -167,6 +167,21 @@ def step_case(tag="config1", B=4, N=64, K=1024, size=112, spec=(100, 129), seed=
     for n in ("video_model.conv1.1", "video_model.conv5x.1.out_bn", "audio_model.block2.bn1"):
         out["rm::" + n] = np_(msd[n + ".running_mean"])
         out["rv::" + n] = np_(msd[n + ".running_var"])
+    # fp64 re-computation with the oracle (pinned against the reference above): separates "reference fp32 rounding"
+    # from "our error" -- with train-mode BN at batch 4 the early-layer gradients of two fp32 runs differ by ~4e-3.
+    from oracle import criterion as oc, towers
+    sd64 = synth.fill_state_dict(towers.state_dict_template(), seed=seed)
+    for k in towers.param_keys(sd64):
+        sd64[k] = sd64[k].double().requires_grad_(True)
+    ve64, ae64 = towers.av_forward(video.double(), audio.double(), sd64, training=True)
+    bank64 = [synth.bank(N, seed=seed, tag=t) for t in ("bank_v", "bank_a")]
+    tot64, _, _ = oc.criterion_forward(ve64, ae64, y, bank64[0], bank64[1], idx, oc.avid_keys(K))
+    tot64.backward()
+    out["fp64::video_emb"], out["fp64::audio_emb"], out["fp64::total"] = np_(ve64), np_(ae64), np_(tot64)
+    out["fp64::grad_norms"] = np.asarray([float(sd64[n].grad.norm()) for n in names])
+    for k in list(out):
+        if k.startswith("grad::"):
+            out["fp64::" + k] = np_(sd64[k[6:]].grad)
     np.savez_compressed(os.path.join(HERE, f"step_{tag}.npz"), **out)
     print("step", tag, "loss", float(loss), "Z", float(out["Z"]))
 
