@@ -1,0 +1,328 @@
+// tcgen05 implicit-GEMM convolution for the encoders (include/avid_b200.h, avid_conv_*_tc).
+//
+// forward / stride-1 input gradient:  D[m, n] = sum_{tap, c} A[pix(m, tap), c] * B[tap][n][c]
+//   * no im2col buffer: the A tile (128 output pixels x 64 channels of one filter tap) is fetched by ONE
+//     TMA im2col-mode load straight from the channels-last bf16 activation tensor; zero padding, conv
+//     stride and the wrap from one row / frame / clip to the next are done by the TMA unit.
+//   * B tile (BN output channels x 64 input channels of the tap, K-major) by a tiled TMA load.
+//   * both land in 128-byte-swizzled shared memory and feed tcgen05.mma (M=128, N=BN, K=16, bf16 in,
+//     fp32 accumulate in TMEM) issued by a single thread; an mbarrier ring (TMA -> MMA -> TMA) of
+//     kStages stages keeps the tensor pipe fed.
+//   * "bf16x3" mode: operands are split as x = hi + lo (two bf16 planes); the kernel accumulates
+//     hi*hi + hi*lo + lo*hi, i.e. ~16 significand bits per operand -- this is the mode that meets the
+//     1e-3 parity bar through 40+ train-mode BatchNorms (SURVEY.md §7 "Precision").  "bf16" mode
+//     accumulates hi*hi only.
+//   * epilogue: 4 warps read the accumulator with tcgen05.ld (one output pixel per thread), add the
+//     optional residual and store fp32 rows.
+//
+// filter gradient: D[ci, co] = sum_m X[pix(m, tap), ci] * dZ[m, co] per tap, reduction over pixels:
+//   both operands are MN-major (the reduction index is the row index of the channels-last tensors);
+//   X tiles by im2col TMA, dZ tiles by tiled TMA, split over pixel ranges, fp32 atomics into dW.
+#include <mutex>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace avid {
+
+const TensorMapApi& tensor_map_api() {
+    static TensorMapApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn)
+            api.tiled = reinterpret_cast<TensorMapApi::EncodeTiled>(fn);
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess && fn)
+            api.im2col = reinterpret_cast<TensorMapApi::EncodeIm2col>(fn);
+        api.ok = api.tiled && api.im2col;
+    });
+    return api;
+}
+
+using namespace tc;
+
+constexpr int kBM = 128;        // output pixels per CTA (UMMA M)
+constexpr int kBK = 64;         // channels per k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int kTcThreads = 192; // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
+
+struct TcConvParams {
+    int M;                          // destination pixels
+    int td, hd, wd, cd;             // destination extents / channels (GEMM N total)
+    int cs;                         // source channels (GEMM K per tap)
+    int kt, kh, kw;                 // filter taps
+    int st, sh, sw;                 // traversal strides (forward conv stride; 1 for dgrad)
+    int pt, ph, pw;                 // padding in SOURCE coordinates (dgrad: k-1-p)
+    int flip;                       // dgrad: filter tap (kt-1-a, kh-1-b, kw-1-c) multiplies source offset (a, b, c)
+    int x3;                         // 1: hi/lo planes, 3 MMAs per k-step; 0: hi only
+};
+
+template <int BN>
+struct TcSmem {
+    static constexpr int kABytes = kBM * kBK * 2;   // 16 KB
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kStages = BN <= 64 ? 4 : 3;
+    static constexpr int kBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcConvParams p,
+               const float* __restrict__ addend, float* __restrict__ out) {
+    using S = TcSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+    uint64_t* empty_bar = full_bar + S::kStages;
+    uint64_t* accum_bar = empty_bar + S::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    const int cblocks = p.cs / kBK;
+    const int taps = p.kt * p.kh * p.kw;
+    const int nkb = taps * cblocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a_hi);
+        prefetch_tensormap(&map_b_hi);
+        if (p.x3) {
+            prefetch_tensormap(&map_a_lo);
+            prefetch_tensormap(&map_b_lo);
+        }
+        for (int s = 0; s < S::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int m = m0;
+        const int w_o = m % p.wd;  m /= p.wd;
+        const int h_o = m % p.hd;  m /= p.hd;
+        const int t_o = m % p.td;
+        const int n_i = m / p.td;
+        const int bw = w_o * p.sw - p.pw, bh = h_o * p.sh - p.ph, bt = t_o * p.st - p.pt;   // base pixel (tap 0) in source coordinates
+        const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
+        int stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kBK;
+            const int a = tap / (p.kh * p.kw), r = tap - a * p.kh * p.kw;
+            const int b = r / p.kw, c = r - b * p.kw;
+            const int ftap = p.flip ? ((p.kt - 1 - a) * p.kh + (p.kh - 1 - b)) * p.kw + (p.kw - 1 - c) : tap;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * S::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], tx);
+            tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, (uint16_t)c, (uint16_t)b, (uint16_t)a);
+            tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
+            if (p.x3) {
+                tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, (uint16_t)c, (uint16_t)b, (uint16_t)a);
+                tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
+            }
+            if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+        int stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+            const uint32_t sb = sa + 2 * S::kABytes;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+                // K-major SW128 tiles: 8-row groups are 1024 bytes apart; a K=16 slice is 32 bytes into the swizzle row
+                const uint64_t a_hi = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t b_hi = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
+                if (p.x3) {
+                    const uint64_t a_lo = make_smem_desc_sw128(sa + S::kABytes + k * 32, 16, 1024);
+                    const uint64_t b_lo = make_smem_desc_sw128(sb + S::kBBytes + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+                    umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+                }
+            }
+            umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs have read it
+            if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accum_bar);                 // accumulator complete
+    } else if (warp >= 2) {
+        // ===== epilogue: TMEM -> registers -> global (one output pixel per thread) =====
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;
+        const size_t row = (size_t)m * p.cd + n0;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, r);
+            tmem_ld_wait();
+            if (m < p.M) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                           __uint_as_float(r[4 * v + 3]));
+                    if (addend) {
+                        const float4 ad = __ldg(reinterpret_cast<const float4*>(addend + row + j * 32) + v);
+                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                    }
+                    reinterpret_cast<float4*>(out + row + j * 32)[v] = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+// fp32 -> (bf16 hi, bf16 lo) planes: hi = rn(x), lo = rn(x - hi)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                         int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2bfloat16_rn(f[j]);
+            l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+        }
+        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+        if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static int encode_im2col(CUtensorMap* map, const void* base, int n, int t, int h, int w, int c, const int lower[3], const int upper[3],
+                         const int stride[3], int pixels) {
+    const TensorMapApi& api = tensor_map_api();
+    if (!api.ok) { set_error("conv_tc: cuTensorMapEncode* driver entry points unavailable"); return AVID_ECUDA; }
+    cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2, (cuuint64_t)t * h * w * c * 2};
+    cuuint32_t estr[5] = {1, (cuuint32_t)stride[0], (cuuint32_t)stride[1], (cuuint32_t)stride[2], 1};
+    CUresult r = api.im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, lower, upper, kBK, (cuuint32_t)pixels,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeIm2col failed (%d)", (int)r); return AVID_ECUDA; }
+    // driver <= 13.1 mis-encodes im2col maps of tensors smaller than 128 KiB (same work-around as CUTLASS)
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (size_t)n * t * h * w * c * 2 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+    return AVID_OK;
+}
+
+static int encode_tiled_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    const TensorMapApi& api = tensor_map_api();
+    if (!api.ok) { set_error("conv_tc: cuTensorMapEncode* driver entry points unavailable"); return AVID_ECUDA; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = api.tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return AVID_ECUDA; }
+    return AVID_OK;
+}
+
+template <int BN>
+static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const float* addend, float* out, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kBytes);
+        if (e != cudaSuccess) { set_error("conv_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        configured = true;
+    }
+    dim3 grid((p.M + kBM - 1) / kBM, p.cd / BN);
+    conv_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out);
+    return check_launch("conv_tc_kernel");
+}
+
+// dgrad == 0: out[n,to,ho,wo,co] = conv(in, filt);  a_* = input planes [n,ti,hi,wi,ci], b_* = filter planes [taps][co][ci]
+// dgrad == 1: out[n,ti,hi,wi,ci] = conv_transpose(dout, filt), stride 1 only; a_* = dout planes, b_* = filter planes [taps][ci][co]
+int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                const float* addend, float* out, cudaStream_t st) {
+    AVID_REQUIRE(s && a_hi && b_hi && out, "conv_tc: NULL pointer");
+    AVID_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "conv_tc: give both lo planes (bf16x3) or neither (bf16)");
+    TcConvParams p;
+    int sn, stt, shh, sww;   // source tensor extents
+    if (!dgrad) {
+        p.td = s->to; p.hd = s->ho; p.wd = s->wo; p.cd = s->co; p.cs = s->ci;
+        sn = s->n; stt = s->ti; shh = s->hi; sww = s->wi;
+        p.st = s->st; p.sh = s->sh; p.sw = s->sw;
+        p.pt = s->pt; p.ph = s->ph; p.pw = s->pw;
+        p.flip = 0;
+    } else {
+        AVID_REQUIRE(s->st == 1 && s->sh == 1 && s->sw == 1, "conv_tc: the tensor-core input gradient supports stride 1 only");
+        p.td = s->ti; p.hd = s->hi; p.wd = s->wi; p.cd = s->ci; p.cs = s->co;
+        sn = s->n; stt = s->to; shh = s->ho; sww = s->wo;
+        p.st = p.sh = p.sw = 1;
+        p.pt = s->kt - 1 - s->pt; p.ph = s->kh - 1 - s->ph; p.pw = s->kw - 1 - s->pw;
+        p.flip = 1;
+    }
+    p.kt = s->kt; p.kh = s->kh; p.kw = s->kw;
+    p.x3 = a_lo != nullptr;
+    AVID_REQUIRE(p.cs % kBK == 0, "conv_tc: source channels (%d) must be a multiple of 64", p.cs);
+    AVID_REQUIRE(p.cd % 64 == 0, "conv_tc: destination channels (%d) must be a multiple of 64", p.cd);
+    AVID_REQUIRE(p.pt >= 0 && p.ph >= 0 && p.pw >= 0 && p.pt < 16 && p.ph < 16 && p.pw < 16, "conv_tc: padding out of range");
+    const int64_t M = (int64_t)s->n * p.td * p.hd * p.wd;
+    AVID_REQUIRE(M > 0 && M < ((int64_t)1 << 31) - 256, "conv_tc: bad pixel count");
+    p.M = (int)M;
+    const int lower[3] = {-p.pw, -p.ph, -p.pt};
+    const int upper[3] = {p.pw - (p.kw - 1), p.ph - (p.kh - 1), p.pt - (p.kt - 1)};
+    const int stride[3] = {p.sw, p.sh, p.st};
+    // the im2col box must walk exactly the destination extents
+    AVID_REQUIRE((sww + upper[0] - lower[0] - 1) / stride[0] + 1 == p.wd && (shh + upper[1] - lower[1] - 1) / stride[1] + 1 == p.hd &&
+                 (stt + upper[2] - lower[2] - 1) / stride[2] + 1 == p.td, "conv_tc: geometry mismatch");
+    const int bn = p.cd % 128 == 0 ? 128 : 64;
+    const int taps = p.kt * p.kh * p.kw;
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = encode_im2col(&maps[0], a_hi, sn, stt, shh, sww, p.cs, lower, upper, stride, kBM))) return rc;
+    if ((rc = encode_tiled_2d(&maps[2], b_hi, (uint64_t)taps * p.cd, p.cs, bn, kBK))) return rc;
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+    if (p.x3) {
+        if ((rc = encode_im2col(&maps[1], a_lo, sn, stt, shh, sww, p.cs, lower, upper, stride, kBM))) return rc;
+        if ((rc = encode_tiled_2d(&maps[3], b_lo, (uint64_t)taps * p.cd, p.cs, bn, kBK))) return rc;
+    }
+    return bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, st) : launch_conv_tc<64>(maps, p, addend, out, st);
+}
+
+}  // namespace avid
+
+using namespace avid;
+
+extern "C" {
+
+int avid_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+    AVID_REQUIRE(x && hi && n > 0 && n % 4 == 0, "split_bf16: n=%lld must be a positive multiple of 4", (long long)n);
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n / 4);
+    return check_launch("split_bf16_kernel");
+}
+
+int avid_conv_forward_tc(const avid_conv_shape_t* s, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
+                         const float* addend, float* out, void* stream) {
+    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, out, static_cast<cudaStream_t>(stream));
+}
+
+int avid_conv_dgrad_tc(const avid_conv_shape_t* s, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
+                       const float* addend, float* din, void* stream) {
+    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, din, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

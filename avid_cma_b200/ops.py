@@ -212,6 +212,36 @@ def conv_wgrad(s, x, dout, math=MATH_FP32, ci_real=None):
     return dw
 
 
+def split_bf16(x, need_lo=True):
+    """fp32 tensor -> (hi, lo) bf16 planes with x ~= hi + lo (lo is None when need_lo is False)."""
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if need_lo else None
+    check(_lib.lib().avid_split_bf16(_p(x), _p(hi, torch.bfloat16), _p(lo, torch.bfloat16, optional=True), x.numel(), _stream()))
+    return hi, lo
+
+
+def conv_forward_tc(s, x_hi, x_lo, w_hi, w_lo, addend=None, out=None, ci_real=None):
+    """tcgen05 forward conv; x_* planes [n,t,h,w,ci] bf16, w_* planes [taps,co,ci] bf16 (lo planes None -> single-pass bf16)."""
+    if out is None:
+        out = torch.empty(s.n, s.to, s.ho, s.wo, s.co, dtype=torch.float32, device=x_hi.device)
+    e0 = _t0()
+    check(_lib.lib().avid_conv_forward_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
+                                          _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out), _stream()))
+    _t1(e0, "conv_forward_tc", _conv_flops(s, ci_real))
+    return out
+
+
+def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None):
+    """tcgen05 input gradient (stride 1); d_* planes [n,to,ho,wo,co] bf16, w_* planes [taps,ci,co] bf16."""
+    if out is None:
+        out = torch.empty(s.n, s.ti, s.hi, s.wi, s.ci, dtype=torch.float32, device=d_hi.device)
+    e0 = _t0()
+    check(_lib.lib().avid_conv_dgrad_tc(C.byref(s), _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
+                                        _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out), _stream()))
+    _t1(e0, "conv_dgrad_tc", _conv_flops(s))
+    return out
+
+
 def filter_to_tapmajor(w, ci_pad=None, transpose=True):
     """PyTorch conv weight (co, ci, *k) -> ([taps, ci_pad, co], [taps, co, ci_pad] or None)."""
     co, ci = w.shape[0], w.shape[1]

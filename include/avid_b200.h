@@ -187,6 +187,20 @@ int avid_conv_dgrad(const avid_conv_shape_t* s_host, const float* dout, const fl
 int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const float* dout, float* dfilt,
                     int32_t math, void* stream);
 
+/* ---- tensor-core (tcgen05) convolutions ------------------------------------------------------------
+ * Operands are bf16 planes of the channels-last tensors: x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+ * (avid_split_bf16).  With both planes the kernel accumulates hi*hi + hi*lo + lo*hi in fp32 ("bf16x3",
+ * AVID_MATH_BF16X3, ~16 significand bits per operand); with lo == NULL it is a plain bf16 product
+ * (AVID_MATH_BF16).  Activations are fetched by TMA im2col-mode loads, filters by tiled TMA loads.
+ * Channel counts must be multiples of 64 (every layer of both towers except the two stems).
+ *   forward: in planes [n,ti,hi,wi,ci], filter planes K-major [taps][co][ci] (the w_tap_t layout)
+ *   dgrad  : dout planes [n,to,ho,wo,co], filter planes [taps][ci][co] (the w_tap layout), stride 1 only  */
+int avid_split_bf16(const float* x, void* hi, void* lo /* may be NULL */, int64_t n, void* stream);
+int avid_conv_forward_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
+                         const float* addend, float* out, void* stream);
+int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
+                       const float* addend, float* din, void* stream);
+
 /* PyTorch parameter layout [co, ci, taps] -> tap-major [taps, ci_pad, co] (channels ci..ci_pad-1 zero) and,
  * when w_tap_t != NULL, its transpose [taps, co, ci_pad] (the filter operand of avid_conv_dgrad). */
 int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, float* w_tap_t, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream);

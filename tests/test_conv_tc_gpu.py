@@ -1,0 +1,65 @@
+"""GPU parity of the tcgen05 convolutions (TMA im2col + UMMA) against torch fp64: bf16x3 (hi/lo split, ~fp32 accuracy)
+and single-pass bf16."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# (n, ci, co, (t,h,w), kernel, stride, padding)
+TC_CASES = [
+    (2, 64, 64, (3, 9, 11), (1, 3, 3), (1, 1, 1), (0, 1, 1)),      # spatial, ragged pixel count, rows wrap inside a tile
+    (2, 64, 64, (4, 5, 7), (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # temporal
+    (2, 64, 128, (4, 10, 10), (1, 3, 3), (1, 2, 2), (0, 1, 1)),    # strided spatial (stage entry)
+    (2, 128, 128, (4, 5, 5), (3, 1, 1), (2, 1, 1), (1, 0, 0)),     # strided temporal
+    (2, 64, 128, (4, 10, 10), (1, 1, 1), (2, 2, 2), (0, 0, 0)),    # residual 1x1x1 s2
+    (1, 256, 512, (1, 7, 9), (1, 3, 3), (1, 1, 1), (0, 1, 1)),     # audio block4-like (2-D)
+    (3, 128, 256, (2, 14, 14), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 512, 512, (1, 4, 4), (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # conv5x temporal at config-1 size (T = 1)
+    (4, 64, 64, (8, 28, 28), (1, 3, 3), (1, 1, 1), (0, 1, 1)),     # config-1 conv2x spatial: 196 tiles
+]
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("x3", [True, False], ids=["bf16x3", "bf16"])
+@pytest.mark.parametrize("case", TC_CASES, ids=[f"c{i}" for i in range(len(TC_CASES))])
+def test_conv_tc_forward_and_dgrad(case, x3):
+    from avid_cma_b200 import ops
+    n, ci, co, (t, h, w), k, s, p = case
+    g = torch.Generator().manual_seed(hash(case) % 2 ** 31)
+    x = torch.randn(n, ci, t, h, w, generator=g)
+    wt = torch.randn(co, ci, *k, generator=g) / (ci * k[0] * k[1] * k[2]) ** 0.5
+    xd, wd = x.double().requires_grad_(True), wt.double()
+    ref = F.conv3d(xd, wd, stride=s, padding=p)
+    dout = torch.randn(ref.shape, generator=g)
+    addend = torch.randn(ref.shape, generator=g)
+    ref.backward(dout.double())
+    tol = 3e-5 if x3 else 1e-2
+    xc = ops.nchw_to_nhwc(x.to(DEV))
+    w_tap, w_tap_t = ops.filter_to_tapmajor(wt.to(DEV))
+    shape = ops.conv_shape(n, t, h, w, ci, co, k, s, p)
+    x_hi, x_lo = ops.split_bf16(xc, x3)
+    wf_hi, wf_lo = ops.split_bf16(w_tap_t, x3)            # forward: [taps, co, ci]
+    out = ops.conv_forward_tc(shape, x_hi, x_lo, wf_hi, wf_lo)
+    torch.cuda.synchronize()
+    assert _rel(ops.nhwc_to_nchw(out), ref) < tol
+    add_c = ops.nchw_to_nhwc(addend.to(DEV))
+    out2 = ops.conv_forward_tc(shape, x_hi, x_lo, wf_hi, wf_lo, addend=add_c)
+    assert _rel(ops.nhwc_to_nchw(out2), ref + addend.double()) < tol
+    if s == (1, 1, 1):
+        d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
+        wd_hi, wd_lo = ops.split_bf16(w_tap, x3)          # dgrad: [taps, ci, co]
+        din = ops.conv_dgrad_tc(shape, d_hi, d_lo, wd_hi, wd_lo)
+        assert _rel(ops.nhwc_to_nchw(din), xd.grad) < tol
+
+
+def test_split_bf16_reconstructs_16_bits():
+    from avid_cma_b200 import ops
+    x = torch.randn(4096, device=DEV) * 3
+    hi, lo = ops.split_bf16(x)
+    assert float(((hi.float() + lo.float()) - x).abs().max() / x.abs().max()) < 2 ** -15
