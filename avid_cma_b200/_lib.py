@@ -63,6 +63,7 @@ _SIGNATURES = {
     "avid_split_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
     "avid_conv_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P]),
     "avid_conv_dgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P]),
+    "avid_conv_wgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P]),
     "avid_filter_to_tapmajor": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "avid_filter_from_tapmajor": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "avid_nchw_to_nhwc": (C.c_int, [_P, _P, _I, _I, _L, _I, _P]),

@@ -188,6 +188,169 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
+// ---- filter gradient ---------------------------------------------------------------------------------
+// dW[tap][ci][co] = sum_m X[pix(m, tap), ci] * dZ[m, co].  GEMM rows = 128 = two "groups" (tap, 64-channel block)
+// of the flattened (taps x ci/64) index space, columns = BN output channels, reduction = destination pixels in
+// k-blocks of 64.  Both operands are MN-major SW128 tiles [64 pixels][64 channels] (8 KB, exactly what one TMA
+// box delivers): groups of 64 channels are 8 KB apart (LBO), groups of 8 pixels 1 KB apart (SBO), a K = 16 step
+// advances 2 KB.
+constexpr int kWgKB = 64;                    // pixels per k-block
+constexpr int kSubTile = kWgKB * 64 * 2;     // 8 KB: [64 pixels][64 channels] bf16
+
+struct TcWgradParams {
+    int M;                  // destination pixels (rows of dZ)
+    int td, hd, wd;         // destination extents
+    int cs, cd;             // ci, co
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int groups;             // taps * cs / 64
+    int kb_per_split;       // k-blocks per split
+    int x3;
+};
+
+template <int BN>
+struct TcWgSmem {
+    static constexpr int kABytes = 2 * kSubTile;            // two (tap, 64-channel) groups
+    static constexpr int kBBytes = (BN / 64) * kSubTile;
+    static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
+    static constexpr int kStages = BN <= 64 ? 4 : (BN <= 128 ? 3 : 2);
+    static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, const TcWgradParams p,
+                float* __restrict__ dfilt) {
+    using S = TcWgSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+    uint64_t* empty_bar = full_bar + S::kStages;
+    uint64_t* accum_bar = empty_bar + S::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g0 = blockIdx.x * 2;                       // first (tap, channel-block) group of this CTA
+    const int n0 = blockIdx.y * BN;
+    const int cblocks = p.cs / 64;
+    const int total_kb = (p.M + kWgKB - 1) / kWgKB;
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int nkb = min(p.kb_per_split, total_kb - kb0);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x_hi);
+        prefetch_tensormap(&map_d_hi);
+        for (int s = 0; s < S::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int gtap[2], gc0[2], ga[2], gb[2], gc[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int g = min(g0 + i, p.groups - 1);     // an odd tail group is loaded twice and not stored
+            gtap[i] = g / cblocks;
+            gc0[i] = (g - gtap[i] * cblocks) * 64;
+            ga[i] = gtap[i] / (p.kh * p.kw);
+            const int r = gtap[i] - ga[i] * p.kh * p.kw;
+            gb[i] = r / p.kw;
+            gc[i] = r - gb[i] * p.kw;
+        }
+        const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
+        int stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            int m = (kb0 + kb) * kWgKB;
+            const int w_o = m % p.wd;  m /= p.wd;
+            const int h_o = m % p.hd;  m /= p.hd;
+            const int t_o = m % p.td;
+            const int n_i = m / p.td;
+            const int bw = w_o * p.sw - p.pw, bh = h_o * p.sh - p.ph, bt = t_o * p.st - p.pt;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * S::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], tx);
+            const int planes = p.x3 ? 2 : 1;
+            for (int pl = 0; pl < planes; ++pl) {
+                const CUtensorMap* mx = pl ? &map_x_lo : &map_x_hi;
+                const CUtensorMap* md = pl ? &map_d_lo : &map_d_hi;
+                uint8_t* a = st + pl * (S::kABytes + S::kBBytes);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    tma_load_im2col_5d(a + i * kSubTile, mx, &full_bar[stage], gc0[i], bw, bh, bt, n_i, (uint16_t)gc[i], (uint16_t)gb[i], (uint16_t)ga[i]);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_2d(a + S::kABytes + j * kSubTile, md, &full_bar[stage], n0 + j * 64, (kb0 + kb) * kWgKB);
+            }
+            if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        int stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_hi_s = smem_u32(smem + stage * S::kStageBytes);
+            const uint32_t b_hi_s = a_hi_s + S::kABytes;
+            const uint32_t a_lo_s = a_hi_s + S::kABytes + S::kBBytes;
+            const uint32_t b_lo_s = a_lo_s + S::kABytes;
+#pragma unroll
+            for (int k = 0; k < kWgKB / 16; ++k) {
+                const uint64_t a_hi = make_smem_desc_sw128(a_hi_s + k * 2048, kSubTile, 1024);
+                const uint64_t b_hi = make_smem_desc_sw128(b_hi_s + k * 2048, kSubTile, 1024);
+                umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
+                if (p.x3) {
+                    const uint64_t a_lo = make_smem_desc_sw128(a_lo_s + k * 2048, kSubTile, 1024);
+                    const uint64_t b_lo = make_smem_desc_sw128(b_lo_s + k * 2048, kSubTile, 1024);
+                    umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+                    umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+                }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accum_bar);
+    } else if (warp >= 2 && nkb > 0) {
+        // ===== epilogue: accumulator row = (group, channel) -> fp32 atomics into dW[tap][ci][co] =====
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = q * 32 + lane;              // 0..127
+        const int g = g0 + (row >> 6);
+        const bool valid = g < p.groups;
+        const int tap = g / cblocks, ci = (g - tap * cblocks) * 64 + (row & 63);
+        float* dst = dfilt + ((size_t)tap * p.cs + ci) * p.cd + n0;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    red_add_v4(dst + j * 32 + 4 * v, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                               __uint_as_float(r[4 * v + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
 // fp32 -> (bf16 hi, bf16 lo) planes: hi = rn(x), lo = rn(x - hi)
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                          int64_t n4) {
@@ -301,11 +464,72 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     return bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, st) : launch_conv_tc<64>(maps, p, addend, out, st);
 }
 
+template <int BN>
+static int launch_wgrad_tc(const CUtensorMap* maps, const TcWgradParams& p, int splits, float* dfilt, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWgSmem<BN>::kBytes);
+        if (e != cudaSuccess) { set_error("wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        configured = true;
+    }
+    dim3 grid((p.groups + 1) / 2, p.cd / BN, splits);
+    wgrad_tc_kernel<BN><<<grid, kTcThreads, TcWgSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, dfilt);
+    return check_launch("wgrad_tc_kernel");
+}
+
+// dfilt[taps][ci][co] += sum over pixels; x_* planes [n,ti,hi,wi,ci], d_* planes [n,to,ho,wo,co]; dfilt zeroed by the caller
+int wgrad_tc_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, const void* d_hi, const void* d_lo, float* dfilt, cudaStream_t st) {
+    AVID_REQUIRE(s && x_hi && d_hi && dfilt, "wgrad_tc: NULL pointer");
+    AVID_REQUIRE((x_lo == nullptr) == (d_lo == nullptr), "wgrad_tc: give both lo planes (bf16x3) or neither (bf16)");
+    AVID_REQUIRE(s->ci % 64 == 0 && s->co % 64 == 0, "wgrad_tc: ci (%d) and co (%d) must be multiples of 64", s->ci, s->co);
+    TcWgradParams p;
+    p.td = s->to; p.hd = s->ho; p.wd = s->wo;
+    p.cs = s->ci; p.cd = s->co;
+    p.kt = s->kt; p.kh = s->kh; p.kw = s->kw;
+    p.st = s->st; p.sh = s->sh; p.sw = s->sw;
+    p.pt = s->pt; p.ph = s->ph; p.pw = s->pw;
+    p.x3 = x_lo != nullptr;
+    const int64_t M = (int64_t)s->n * s->to * s->ho * s->wo;
+    AVID_REQUIRE(M > 0 && M < ((int64_t)1 << 31) - 256, "wgrad_tc: bad pixel count");
+    p.M = (int)M;
+    const int taps = s->kt * s->kh * s->kw;
+    p.groups = taps * (s->ci / 64);
+    const int bn = s->co % 256 == 0 ? 256 : (s->co % 128 == 0 ? 128 : 64);
+    const int tiles = ((p.groups + 1) / 2) * (s->co / bn);
+    const int total_kb = (p.M + kWgKB - 1) / kWgKB;
+    int splits = (2 * kNumSMs + tiles - 1) / tiles;
+    if (splits > (total_kb + 3) / 4) splits = (total_kb + 3) / 4;     // at least 4 k-blocks per CTA
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    const int lower[3] = {-s->pw, -s->ph, -s->pt};
+    const int upper[3] = {s->pw - (s->kw - 1), s->ph - (s->kh - 1), s->pt - (s->kt - 1)};
+    const int stride[3] = {s->sw, s->sh, s->st};
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = encode_im2col(&maps[0], x_hi, s->n, s->ti, s->hi, s->wi, s->ci, lower, upper, stride, kWgKB))) return rc;
+    if ((rc = encode_tiled_2d(&maps[2], d_hi, (uint64_t)M, s->co, kWgKB, 64))) return rc;
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+    if (p.x3) {
+        if ((rc = encode_im2col(&maps[1], x_lo, s->n, s->ti, s->hi, s->wi, s->ci, lower, upper, stride, kWgKB))) return rc;
+        if ((rc = encode_tiled_2d(&maps[3], d_lo, (uint64_t)M, s->co, kWgKB, 64))) return rc;
+    }
+    if (bn == 256) return launch_wgrad_tc<256>(maps, p, splits, dfilt, st);
+    if (bn == 128) return launch_wgrad_tc<128>(maps, p, splits, dfilt, st);
+    return launch_wgrad_tc<64>(maps, p, splits, dfilt, st);
+}
+
 }  // namespace avid
 
 using namespace avid;
 
 extern "C" {
+
+int avid_conv_wgrad_tc(const avid_conv_shape_t* s, const void* in_hi, const void* in_lo, const void* dout_hi, const void* dout_lo,
+                       float* dfilt, void* stream) {
+    return wgrad_tc_run(s, in_hi, in_lo, dout_hi, dout_lo, dfilt, static_cast<cudaStream_t>(stream));
+}
 
 int avid_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
     AVID_REQUIRE(x && hi && n > 0 && n % 4 == 0, "split_bf16: n=%lld must be a positive multiple of 4", (long long)n);

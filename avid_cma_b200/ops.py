@@ -242,6 +242,16 @@ def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None):
     return out
 
 
+def conv_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo, ci_real=None):
+    """tcgen05 filter gradient; returns fp32 tap-major [taps, ci, co]."""
+    dw = torch.zeros(s.kt * s.kh * s.kw, s.ci, s.co, dtype=torch.float32, device=x_hi.device)
+    e0 = _t0()
+    check(_lib.lib().avid_conv_wgrad_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), _p(d_hi, torch.bfloat16),
+                                        _p(d_lo, torch.bfloat16, optional=True), _p(dw), _stream()))
+    _t1(e0, "conv_wgrad_tc", _conv_flops(s, ci_real))
+    return dw
+
+
 def filter_to_tapmajor(w, ci_pad=None, transpose=True):
     """PyTorch conv weight (co, ci, *k) -> ([taps, ci_pad, co], [taps, co, ci_pad] or None)."""
     co, ci = w.shape[0], w.shape[1]

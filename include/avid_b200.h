@@ -200,6 +200,10 @@ int avid_conv_forward_tc(const avid_conv_shape_t* s_host, const void* in_hi, con
                          const float* addend, float* out, void* stream);
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
                        const float* addend, float* din, void* stream);
+/*   wgrad  : in planes [n,ti,hi,wi,ci], dout planes [n,to,ho,wo,co] -> dfilt fp32 tap-major [taps][ci][co], zeroed by the
+ *            caller (split over pixels, accumulated with fp32 vector atomics); any stride                               */
+int avid_conv_wgrad_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* dout_hi, const void* dout_lo,
+                       float* dfilt, void* stream);
 
 /* PyTorch parameter layout [co, ci, taps] -> tap-major [taps, ci_pad, co] (channels ci..ci_pad-1 zero) and,
  * when w_tap_t != NULL, its transpose [taps, co, ci_pad] (the filter operand of avid_conv_dgrad). */

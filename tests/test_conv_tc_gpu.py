@@ -34,7 +34,7 @@ def test_conv_tc_forward_and_dgrad(case, x3):
     g = torch.Generator().manual_seed(hash(case) % 2 ** 31)
     x = torch.randn(n, ci, t, h, w, generator=g)
     wt = torch.randn(co, ci, *k, generator=g) / (ci * k[0] * k[1] * k[2]) ** 0.5
-    xd, wd = x.double().requires_grad_(True), wt.double()
+    xd, wd = x.double().requires_grad_(True), wt.double().requires_grad_(True)
     ref = F.conv3d(xd, wd, stride=s, padding=p)
     dout = torch.randn(ref.shape, generator=g)
     addend = torch.randn(ref.shape, generator=g)
@@ -51,8 +51,10 @@ def test_conv_tc_forward_and_dgrad(case, x3):
     add_c = ops.nchw_to_nhwc(addend.to(DEV))
     out2 = ops.conv_forward_tc(shape, x_hi, x_lo, wf_hi, wf_lo, addend=add_c)
     assert _rel(ops.nhwc_to_nchw(out2), ref + addend.double()) < tol
+    d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
+    dw = ops.filter_from_tapmajor(ops.conv_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo), wt.to(DEV))
+    assert _rel(dw, wd.grad) < tol
     if s == (1, 1, 1):
-        d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
         wd_hi, wd_lo = ops.split_bf16(w_tap, x3)          # dgrad: [taps, ci, co]
         din = ops.conv_dgrad_tc(shape, d_hi, d_lo, wd_hi, wd_lo)
         assert _rel(ops.nhwc_to_nchw(din), xd.grad) < tol
