@@ -3,6 +3,7 @@
 // models/video.py:21, models/audio.py:23): batch statistics with the biased variance, eps inside the
 // square root, running statistics updated with the unbiased variance.  Sums are accumulated in
 // fp64 so the statistics do not depend on the (atomic) summation order to fp32 precision.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace avid {
@@ -85,8 +86,21 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t row
     }
 }
 
+// hi = bf16(v), lo = bf16(v - hi): the operand planes of the tcgen05 convolutions
+__device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i, const float (&f)[4]) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(f[j]);
+        l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+    }
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+}
+
 __global__ void __launch_bounds__(256) bn_relu_forward_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, float* __restrict__ y,
+                                                              __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
                                                               int64_t n4, int c4) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const int cc = (int)(i % c4);
@@ -98,7 +112,11 @@ __global__ void __launch_bounds__(256) bn_relu_forward_kernel(const float* __res
         o.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
         o.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
         o.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
-        reinterpret_cast<float4*>(y)[i] = o;
+        if (y) reinterpret_cast<float4*>(y)[i] = o;
+        if (y_hi) {
+            const float f[4] = {o.x, o.y, o.z, o.w};
+            store_planes(y_hi, y_lo, i, f);
+        }
     }
 }
 
@@ -106,7 +124,8 @@ __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float
                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      const double* __restrict__ sums, int64_t rows, int c,
-                                                                     float* __restrict__ dx, float* dgamma, float* dbeta) {
+                                                                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
+                                                                     __nv_bfloat16* __restrict__ dx_lo, float* dgamma, float* dbeta) {
     const int c4 = c >> 2;
     const int64_t n4 = rows * c4;
     const float inv_n = 1.0f / (float)rows;
@@ -130,7 +149,8 @@ __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float
             const float sg = (float)sums[ch] * inv_n, sgx = (float)sums[c + ch] * inv_n;
             o[j] = ga * is * (g - sg - xh * sgx);
         }
-        reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dx) reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dx_hi) store_planes(dx_hi, dx_lo, i, o);
     }
 }
 
@@ -185,13 +205,21 @@ int avid_bn_finalize(const double* stats, int64_t rows, int32_t c, const float* 
     return check_launch("bn_finalize_kernel");
 }
 
-int avid_bn_relu_forward(const float* x, const float* scale, const float* shift, float* y, int64_t rows, int32_t c, void* stream) {
+int avid_bn_relu_forward_ex(const float* x, const float* scale, const float* shift, float* y, void* y_hi, void* y_lo,
+                            int64_t rows, int32_t c, void* stream) {
     int rc = check_bn_shape(rows, c);
     if (rc) return rc;
-    AVID_REQUIRE(x && scale && shift && y, "bn_relu_forward: NULL pointer");
+    AVID_REQUIRE(x && scale && shift && (y || y_hi), "bn_relu_forward: NULL pointer");
+    AVID_REQUIRE(y_hi || !y_lo, "bn_relu_forward: a lo plane needs the hi plane");
     const int64_t n4 = rows * (c >> 2);
-    bn_relu_forward_kernel<<<ew_grid(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, scale, shift, y, n4, c >> 2);
+    bn_relu_forward_kernel<<<ew_grid(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, scale, shift, y, static_cast<__nv_bfloat16*>(y_hi),
+                                                                                      static_cast<__nv_bfloat16*>(y_lo), n4, c >> 2);
     return check_launch("bn_relu_forward_kernel");
+}
+
+int avid_bn_relu_forward(const float* x, const float* scale, const float* shift, float* y, int64_t rows, int32_t c, void* stream) {
+    AVID_REQUIRE(y, "bn_relu_forward: NULL pointer");
+    return avid_bn_relu_forward_ex(x, scale, shift, y, nullptr, nullptr, rows, c, stream);
 }
 
 int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
@@ -202,15 +230,23 @@ int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* m
     return launch_reduce<true>(x, dy, mean, invstd, gamma, beta, rows, c, sums, static_cast<cudaStream_t>(stream));
 }
 
+int avid_bn_relu_backward_apply_ex(const float* x, const float* dy, const float* mean, const float* invstd,
+                                   const float* gamma, const float* beta, const double* sums,
+                                   int64_t rows, int32_t c, float* dx, void* dx_hi, void* dx_lo, float* dgamma, float* dbeta, void* stream) {
+    int rc = check_bn_shape(rows, c);
+    if (rc) return rc;
+    AVID_REQUIRE(x && dy && mean && invstd && gamma && beta && sums && (dx || dx_hi), "bn_relu_backward_apply: NULL pointer");
+    AVID_REQUIRE(dx_hi || !dx_lo, "bn_relu_backward_apply: a lo plane needs the hi plane");
+    bn_relu_backward_apply_kernel<<<ew_grid(rows * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, dy, mean, invstd, gamma, beta, sums, rows, c, dx, static_cast<__nv_bfloat16*>(dx_hi), static_cast<__nv_bfloat16*>(dx_lo), dgamma, dbeta);
+    return check_launch("bn_relu_backward_apply_kernel");
+}
+
 int avid_bn_relu_backward_apply(const float* x, const float* dy, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, const double* sums,
                                 int64_t rows, int32_t c, float* dx, float* dgamma, float* dbeta, void* stream) {
-    int rc = check_bn_shape(rows, c);
-    if (rc) return rc;
-    AVID_REQUIRE(x && dy && mean && invstd && gamma && beta && sums && dx, "bn_relu_backward_apply: NULL pointer");
-    bn_relu_backward_apply_kernel<<<ew_grid(rows * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, dy, mean, invstd, gamma, beta, sums, rows, c, dx, dgamma, dbeta);
-    return check_launch("bn_relu_backward_apply_kernel");
+    AVID_REQUIRE(dx, "bn_relu_backward_apply: NULL pointer");
+    return avid_bn_relu_backward_apply_ex(x, dy, mean, invstd, gamma, beta, sums, rows, c, dx, nullptr, nullptr, dgamma, dbeta, stream);
 }
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 import torch.nn as nn
 
 from .. import ops
+from ..ops import Act
 from .network_blocks import Basic2DBlock, ConvBNReLU, pad_channels
 from ._tower import TowerMixin
 
@@ -27,20 +28,20 @@ class Conv2D(TowerMixin, nn.Module):
         self.out_dim = 512
 
     def _fwd(self, x, training, math, taps=None):
-        xc = ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])).unsqueeze(1)   # (B, 1, T, F, 4): a 2-D layer is t == 1
-        h, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, math)
+        xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])).unsqueeze(1))   # (B, 1, T, F, 4): a 2-D layer is t == 1
+        h, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)  # Cin = 1: CUDA-core kernel
         saved_blocks = []
         for blk, tag in zip((self.block1, self.block2, self.block3, self.block4), ('conv2x', 'conv3x', 'conv4x', 'conv5x')):
             h, sb = blk._fwd(h, training, math)
             saved_blocks.append((blk, sb))
             if taps is not None:
-                taps[tag] = h
-        pooled, argmax = ops.global_maxpool_forward(h)
+                taps[tag] = h.f32
+        pooled, argmax = ops.global_maxpool_forward(h.f32)
         return pooled, (s_stem, saved_blocks, argmax, tuple(h.shape))
 
     def _bwd(self, dpooled, saved, grads, math):
         s_stem, saved_blocks, argmax, hshape = saved
         d = ops.global_maxpool_backward(dpooled, argmax, hshape)
         for blk, sb in reversed(saved_blocks):
-            d = blk._bwd(d, sb, grads, math)
-        ConvBNReLU.backward(d, s_stem, grads, math, need_dx=False)
+            d = blk._bwd(d, sb, grads)
+        ConvBNReLU.backward(d, s_stem, grads, need_dx=False)

@@ -6,11 +6,17 @@ a seeded construction reproduces the reference's weights), but their own forward
 All arithmetic is done by libavid_b200.so on channels-last activations [n, t, h, w, c]; a 2-D layer is
 the t == 1 case.  Backward is hand-written (no autograd graph inside a tower): every block returns
 the tensors its backward needs in a `saved` record.
+
+Math modes (ops.MATH_*): FP32 runs the CUDA-core implicit-GEMM kernels; BF16X3 / BF16 run every layer
+whose channel counts are multiples of 64 (all but the two stems) on the tcgen05 kernels, with
+activations and gradients handed from layer to layer as bf16 (hi, lo) planes written by the
+BatchNorm+ReLU kernels.  The strided input gradients (9 layers) use the fp32 kernel in every mode.
 """
 import torch
 import torch.nn as nn
 
 from .. import ops
+from ..ops import Act
 
 
 def _triple(v, fill=1):
@@ -31,36 +37,81 @@ def pad_channels(c):
     return (c + 15) // 16 * 16
 
 
+class ConvOp:
+    """One convolution of a step: geometry + the filter in every layout / precision its kernels read."""
+
+    def __init__(self, conv, x_shape, math):
+        n, t, h, w, ci = x_shape
+        self.conv = conv
+        self.k, self.s, self.p = _triple(conv.kernel_size), _triple(conv.stride), _triple(conv.padding, 0)
+        self.shape = ops.conv_shape(n, t, h, w, ci, conv.out_channels, self.k, self.s, self.p)
+        self.tc = math != ops.MATH_FP32 and ci % 64 == 0 and conv.out_channels % 64 == 0
+        self.x3 = math == ops.MATH_BF16X3
+        self.unit_stride = self.s == (1, 1, 1)
+        self.ci_real = conv.in_channels
+        w_tap, w_tap_t = ops.filter_to_tapmajor(conv.weight.detach(), ci_pad=ci)
+        self.w_tap, self.w_tap_t = w_tap, w_tap_t          # fp32 [taps, ci, co] / [taps, co, ci]
+        if self.tc:
+            self.wf_hi, self.wf_lo = ops.split_bf16(w_tap_t, self.x3)           # forward operand, K-major in ci
+            if self.unit_stride:
+                self.wd_hi, self.wd_lo = ops.split_bf16(w_tap, self.x3)         # dgrad operand, K-major in co
+                self.w_tap = self.w_tap_t = None
+
+    def forward(self, x, addend=None):
+        if self.tc:
+            x.ensure_planes(self.x3)
+            return ops.conv_forward_tc(self.shape, x.hi, x.lo, self.wf_hi, self.wf_lo, addend=addend, ci_real=self.ci_real)
+        return ops.conv_forward(self.shape, x.f32, self.w_tap, addend=addend, ci_real=self.ci_real)
+
+    def needs_f32_dz(self):
+        return not self.tc or not self.unit_stride
+
+    def wgrad(self, x, dz):
+        if self.tc:
+            dw = ops.conv_wgrad_tc(self.shape, x.hi, x.lo, dz.hi, dz.lo, ci_real=self.ci_real)
+        else:
+            dw = ops.conv_wgrad(self.shape, x.f32, dz.f32, ci_real=self.ci_real)
+        return ops.filter_from_tapmajor(dw, self.conv.weight)
+
+    def dgrad(self, dz, addend=None):
+        if self.tc and self.unit_stride:
+            return ops.conv_dgrad_tc(self.shape, dz.hi, dz.lo, self.wd_hi, self.wd_lo, addend=addend)
+        return ops.conv_dgrad(self.shape, dz.f32, self.w_tap_t, addend=addend)
+
+
 class ConvBNReLU:
     """conv -> train/eval BatchNorm -> ReLU, with an optional residual addend fused into the conv epilogue."""
 
     @staticmethod
-    def forward(x, conv, bn, training, math, addend=None):
-        n, t, h, w, ci = x.shape
-        k, s, p = _triple(conv.kernel_size), _triple(conv.stride), _triple(conv.padding, 0)
-        shape = ops.conv_shape(n, t, h, w, ci, conv.out_channels, k, s, p)
-        w_tap, w_tap_t = ops.filter_to_tapmajor(conv.weight.detach(), ci_pad=ci)
-        z = ops.conv_forward(shape, x, w_tap, addend=addend, math=math, ci_real=conv.in_channels)
+    def forward(x, conv, bn, training, math, addend=None, out_f32=False):
+        """x: Act.  Returns (y: Act, saved).  In the tensor-core modes y carries the bf16 planes the next
+        convolution reads (plus fp32 when `out_f32`: block outputs feed residual adds and pools)."""
+        op = ConvOp(conv, x.shape, math)
+        z = op.forward(x, addend)
         if training:
             st = ops.bn_train_stats(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bn.momentum)
             bn.num_batches_tracked += 1
         else:
-            st = ops.BNState(conv.out_channels, x.device)
+            st = ops.BNState(conv.out_channels, z.device)
             st.invstd.copy_(torch.rsqrt(bn.running_var + bn.eps))
             st.mean.copy_(bn.running_mean)
             st.scale.copy_(bn.weight.detach() * st.invstd)
             st.shift.copy_(bn.bias.detach() - bn.running_mean * st.scale)
-        y = ops.bn_relu_forward(z, st.scale, st.shift)
-        return y, (shape, x, w_tap_t, z, st, conv, bn)
+        planes = math != ops.MATH_FP32
+        y = ops.bn_relu_forward_act(z, st.scale, st.shift, want_f32=out_f32 or not planes, want_planes=planes, x3=math == ops.MATH_BF16X3)
+        return y, (op, x, z, st, bn)
 
     @staticmethod
-    def backward(dy, saved, grads, math, need_dx=True, dx_addend=None):
-        """Returns (dx or None, dz) where dz is the gradient at the conv output (after the residual sum)."""
-        shape, x, w_tap_t, z, st, conv, bn = saved
-        dz, dgamma, dbeta = ops.bn_relu_backward(z, dy, st, bn.weight.detach(), bn.bias.detach())
+    def backward(dy, saved, grads, need_dx=True, dx_addend=None, dz_f32=False):
+        """dy: fp32 gradient at the ReLU output.  Returns (dx fp32 or None, dz: Act at the conv output, i.e. after
+        the residual sum)."""
+        op, x, z, st, bn = saved
+        want_f32 = dz_f32 or not op.tc or (need_dx and op.needs_f32_dz())
+        dz, dgamma, dbeta = ops.bn_relu_backward_act(z, dy, st, bn.weight.detach(), bn.bias.detach(), want_f32=want_f32,
+                                                     want_planes=op.tc, x3=op.x3)
         grads[bn.weight], grads[bn.bias] = dgamma, dbeta
-        grads[conv.weight] = ops.filter_from_tapmajor(ops.conv_wgrad(shape, x, dz, math=math, ci_real=conv.in_channels), conv.weight)
-        dx = ops.conv_dgrad(shape, dz, w_tap_t, addend=dx_addend, math=math) if need_dx else None
+        grads[op.conv.weight] = op.wgrad(x, dz)
+        dx = op.dgrad(dz, addend=dx_addend) if need_dx else None
         return dx, dz
 
 
@@ -77,13 +128,13 @@ class Basic2DBlock(nn.Module):
 
     def _fwd(self, x, training, math):
         y1, s1 = ConvBNReLU.forward(x, self.conv1, self.bn1, training, math)
-        y2, s2 = ConvBNReLU.forward(y1, self.conv2, self.bn2, training, math)
+        y2, s2 = ConvBNReLU.forward(y1, self.conv2, self.bn2, training, math, out_f32=True)
         return y2, (s1, s2)
 
-    def _bwd(self, dy, saved, grads, math, need_dx=True):
+    def _bwd(self, dy, saved, grads, need_dx=True):
         s1, s2 = saved
-        d1, _ = ConvBNReLU.backward(dy, s2, grads, math)
-        dx, _ = ConvBNReLU.backward(d1, s1, grads, math, need_dx=need_dx)
+        d1, _ = ConvBNReLU.backward(dy, s2, grads)
+        dx, _ = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx)
         return dx
 
 
@@ -111,33 +162,30 @@ class BasicR2P1DBlock(nn.Module):
             self.res = False
 
     def _fwd(self, x, training, math):
+        """x: Act carrying fp32 (the identity residual) and, in tensor-core modes, planes."""
         y1, s1 = ConvBNReLU.forward(x, self.spt_conv1, self.spt_bn1, training, math)
         y2, s2 = ConvBNReLU.forward(y1, self.tmp_conv1, self.tmp_bn1, training, math)
         y3, s3 = ConvBNReLU.forward(y2, self.spt_conv2, self.spt_bn2, training, math)
-        sres = None
+        rop = None
         if self.res:
-            n, t, h, w, ci = x.shape
-            rc = self.res_conv
-            rshape = ops.conv_shape(n, t, h, w, ci, rc.out_channels, _triple(rc.kernel_size), _triple(rc.stride), _triple(rc.padding, 0))
-            rw, rw_t = ops.filter_to_tapmajor(rc.weight.detach(), ci_pad=ci)
-            r = ops.conv_forward(rshape, x, rw, math=math)
-            sres = (rshape, rw_t)
+            rop = ConvOp(self.res_conv, x.shape, math)
+            r = rop.forward(x)
         else:
-            r = x
+            r = x.f32
         # x_main + x_res is formed in the epilogue of tmp_conv2, then out_bn + ReLU (network_blocks.py:58-59)
-        y4, s4 = ConvBNReLU.forward(y3, self.tmp_conv2, self.out_bn, training, math, addend=r)
-        return y4, (s1, s2, s3, s4, sres, x)
+        y4, s4 = ConvBNReLU.forward(y3, self.tmp_conv2, self.out_bn, training, math, addend=r, out_f32=True)
+        return y4, (s1, s2, s3, s4, rop, x)
 
-    def _bwd(self, dy, saved, grads, math, need_dx=True):
-        s1, s2, s3, s4, sres, x = saved
-        d3, d_sum = ConvBNReLU.backward(dy, s4, grads, math)
-        d2, _ = ConvBNReLU.backward(d3, s3, grads, math)
-        d1, _ = ConvBNReLU.backward(d2, s2, grads, math)
+    def _bwd(self, dy, saved, grads, need_dx=True):
+        s1, s2, s3, s4, rop, x = saved
+        # d_sum (gradient at x_main + x_res) flows to tmp_conv2 and to the residual branch
+        d3, d_sum = ConvBNReLU.backward(dy, s4, grads, dz_f32=(not self.res) or rop.needs_f32_dz())
+        d2, _ = ConvBNReLU.backward(d3, s3, grads)
+        d1, _ = ConvBNReLU.backward(d2, s2, grads)
         if self.res:
-            rshape, rw_t = sres
-            grads[self.res_conv.weight] = ops.filter_from_tapmajor(ops.conv_wgrad(rshape, x, d_sum, math=math), self.res_conv.weight)
-            d_res = ops.conv_dgrad(rshape, d_sum, rw_t, math=math) if need_dx else None
+            grads[self.res_conv.weight] = rop.wgrad(x, d_sum)
+            d_res = rop.dgrad(d_sum) if need_dx else None
         else:
-            d_res = d_sum
-        dx, _ = ConvBNReLU.backward(d1, s1, grads, math, need_dx=need_dx, dx_addend=d_res)
+            d_res = d_sum.f32
+        dx, _ = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx, dx_addend=d_res)
         return dx

@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..ops import Act
 from .network_blocks import BasicR2P1DBlock, ConvBNReLU, pad_channels
 from ._tower import TowerFunction, TowerMixin
 
@@ -47,26 +48,27 @@ class R2Plus1D(TowerMixin, nn.Module):
 
     def _fwd(self, x, training, math, taps=None):
         """x (B,3,T,H,W) -> pooled (B,512); saved record for _bwd.  `taps` collects channels-last stage outputs."""
-        xc = ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1]))
-        y, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, math)
+        xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])))
+        ya, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)   # Cin = 3: CUDA-core kernel
+        y = ya.f32
         p = ops.maxpool_1x3x3_forward(y)
         if taps is not None:
             taps['conv1'] = p
         saved_blocks = []
-        h = p
+        h = Act(p)
         for name, blocks in self._stages():
             for blk in blocks:
                 h, sb = blk._fwd(h, training, math)
                 saved_blocks.append((blk, sb))
             if taps is not None:
-                taps[name] = h
-        pooled, argmax = ops.global_maxpool_forward(h)
+                taps[name] = h.f32
+        pooled, argmax = ops.global_maxpool_forward(h.f32)
         return pooled, (s_stem, y, p, saved_blocks, argmax, tuple(h.shape))
 
     def _bwd(self, dpooled, saved, grads, math):
         s_stem, y, p, saved_blocks, argmax, hshape = saved
         d = ops.global_maxpool_backward(dpooled, argmax, hshape)
         for blk, sb in reversed(saved_blocks):
-            d = blk._bwd(d, sb, grads, math)
+            d = blk._bwd(d, sb, grads)
         dy = ops.maxpool_1x3x3_backward(y, p, d)
-        ConvBNReLU.backward(dy, s_stem, grads, math, need_dx=False)
+        ConvBNReLU.backward(dy, s_stem, grads, need_dx=False)

@@ -314,6 +314,28 @@ def bn_train_stats(x, gamma, beta, running_mean, running_var, eps=BN_EPS, moment
     return s
 
 
+class Act:
+    """A channels-last activation in the representations the kernels consume: fp32 and / or the bf16
+    planes (hi, lo) with x ~= hi + lo that feed the tcgen05 convolutions."""
+    __slots__ = ("f32", "hi", "lo")
+
+    def __init__(self, f32=None, hi=None, lo=None):
+        self.f32, self.hi, self.lo = f32, hi, lo
+
+    @property
+    def shape(self):
+        return (self.f32 if self.f32 is not None else self.hi).shape
+
+    @property
+    def device(self):
+        return (self.f32 if self.f32 is not None else self.hi).device
+
+    def ensure_planes(self, x3):
+        if self.hi is None or (x3 and self.lo is None):
+            self.hi, self.lo = split_bf16(self.f32, x3)
+        return self
+
+
 def bn_relu_forward(x, scale, shift, out=None):
     c = x.shape[-1]
     if out is None:
@@ -322,19 +344,39 @@ def bn_relu_forward(x, scale, shift, out=None):
     return out
 
 
+def bn_relu_forward_act(x, scale, shift, want_f32, want_planes, x3):
+    """relu(x * scale + shift) as an Act with the requested representations, in one pass over x."""
+    c = x.shape[-1]
+    y = torch.empty_like(x) if want_f32 else None
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes else None
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes and x3 else None
+    check(_lib.lib().avid_bn_relu_forward_ex(_p(x), _p(scale), _p(shift), _p(y, optional=True), _p(hi, torch.bfloat16, optional=True),
+                                             _p(lo, torch.bfloat16, optional=True), x.numel() // c, c, _stream()))
+    return Act(y, hi, lo)
+
+
 def bn_relu_backward(x, dy, s, gamma, beta, dx=None):
     """Backward of y = relu(bn_train(x)).  Returns (dx, dgamma, dbeta)."""
+    act, dgamma, dbeta = bn_relu_backward_act(x, dy, s, gamma, beta, True, False, False, dx=dx)
+    return act.f32, dgamma, dbeta
+
+
+def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=None):
+    """Backward of y = relu(bn_train(x)); the gradient w.r.t. x as an Act (fp32 and / or bf16 planes)."""
     c = x.shape[-1]
     rows = x.numel() // c
     sums = torch.zeros(2, c, dtype=torch.float64, device=x.device)
-    if dx is None:
+    if want_f32 and dx is None:
         dx = torch.empty_like(x)
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes else None
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes and x3 else None
     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
     L = _lib.lib()
     check(L.avid_bn_relu_backward_reduce(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), rows, c, _p(sums, torch.float64), _stream()))
-    check(L.avid_bn_relu_backward_apply(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), _p(sums, torch.float64), rows, c,
-                                        _p(dx), _p(dgamma), _p(dbeta), _stream()))
-    return dx, dgamma, dbeta
+    check(L.avid_bn_relu_backward_apply_ex(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), _p(sums, torch.float64), rows, c,
+                                           _p(dx, optional=True), _p(hi, torch.bfloat16, optional=True), _p(lo, torch.bfloat16, optional=True),
+                                           _p(dgamma), _p(dbeta), _stream()))
+    return Act(dx if want_f32 else None, hi, lo), dgamma, dbeta
 
 
 def maxpool_1x3x3_forward(x):

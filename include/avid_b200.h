@@ -227,6 +227,9 @@ int avid_bn_finalize(const double* stats, int64_t rows, int32_t c, const float* 
 /* y = relu(x*scale + shift) */
 int avid_bn_relu_forward(const float* x, const float* scale, const float* shift, float* y,
                          int64_t rows, int32_t c, void* stream);
+/* same, writing any of: fp32 y, bf16 planes y_hi / y_lo (y = hi + lo, the operands of the tcgen05 convolutions) */
+int avid_bn_relu_forward_ex(const float* x, const float* scale, const float* shift, float* y, void* y_hi, void* y_lo,
+                            int64_t rows, int32_t c, void* stream);
 /* backward of y = relu(bn(x)): sums (2, c) doubles zeroed by caller: sum(g), sum(g*xhat), g = dy*(y>0) */
 int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* mean, const float* invstd,
                                  const float* gamma, const float* beta, int64_t rows, int32_t c,
@@ -235,6 +238,10 @@ int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* m
 int avid_bn_relu_backward_apply(const float* x, const float* dy, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, const double* sums,
                                 int64_t rows, int32_t c, float* dx, float* dgamma, float* dbeta, void* stream);
+
+int avid_bn_relu_backward_apply_ex(const float* x, const float* dy, const float* mean, const float* invstd,
+                                   const float* gamma, const float* beta, const double* sums,
+                                   int64_t rows, int32_t c, float* dx, void* dx_hi, void* dx_lo, float* dgamma, float* dbeta, void* stream);
 
 /* nn.MaxPool3d((1,3,3), stride (1,2,2), padding (0,1,1)) on [n*t, h, w, c] (video.py:23) */
 int avid_maxpool_1x3x3_forward(const float* x, float* y, int32_t nt, int32_t h, int32_t w, int32_t c,

@@ -165,21 +165,24 @@ def test_adam_step_matches_torch():
         _close(p, ref, 1e-5, 1e-7)
 
 
-def _load_model(seed=0):
+def _load_model(seed=0, math="fp32"):
     from avid_cma_b200 import models
+    from avid_cma_b200.models._tower import _MATH
     model = models.av_wrapper('R2Plus1D', {'depth': 18}, 'Conv2D', {'depth': 10}, proj_dim=[512, 512, 128])
     model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=seed))
+    model.video_model.math = model.audio_model.math = _MATH[math]
     return model.to(DEV).train()
 
 
-def test_training_step_config1_matches_reference_golden(golden):
+@pytest.mark.parametrize("math", ["fp32", "bf16x3"])
+def test_training_step_config1_matches_reference_golden(golden, math):
     """BASELINE config 1: batch 4, 8x3x112x112 + 1x100x129, bank 64, K = 1024, injected negatives: embeddings, loss,
     every parameter-gradient norm, selected gradients, BN running stats and updated bank rows vs the imported reference."""
     from avid_cma_b200.criterions import AVID
     g = golden("step_config1")
     B, N, K, size, seed = int(g["B"]), int(g["N"]), int(g["K"]), int(g["size"]), int(g["seed"])
     spec = g["spec"].tolist()
-    model = _load_model(seed)
+    model = _load_model(seed, math)
     crit = AVID(num_data=N, embedding_dim=128, num_negatives=K, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=0)
     crit.nce_average.view1_mem.copy_(synth.bank(N, seed=seed, tag="bank_v"))
     crit.nce_average.view2_mem.copy_(synth.bank(N, seed=seed, tag="bank_a"))
@@ -210,7 +213,7 @@ def test_training_step_config1_matches_reference_golden(golden):
             # from the fp64 result there, so the bar is "no further from fp64 than 2x the reference's own rounding"
             truth = torch.from_numpy(g["fp64::" + k])
             ref_err = _rel(torch.from_numpy(g[k]), truth)
-            assert _rel(params[k[6:]].grad, truth) < max(1e-3, 2 * ref_err), (k, ref_err)
+            assert _rel(params[k[6:]].grad, truth) < max(1e-3, (2 if math == "fp32" else 8) * ref_err), (k, ref_err)
         elif k.startswith("grad_slice::"):
             want = torch.from_numpy(g[k])
             assert _rel(params[k[12:]].grad[:want.shape[0]], want) < 1e-2, k
@@ -221,6 +224,30 @@ def test_training_step_config1_matches_reference_golden(golden):
     assert int(sd["video_model.conv1.1.num_batches_tracked"]) == 1
     assert _rel(crit.nce_average.view1_mem[y.to(DEV)], torch.from_numpy(g["rows_v"])) < tol
     assert _rel(crit.nce_average.view2_mem[y.to(DEV)], torch.from_numpy(g["rows_a"])) < tol
+
+
+def test_training_step_config1_bf16_single_pass(golden):
+    """The documented fast mode (one bf16 MMA per product): exercised end to end; with train-mode BN at batch 4 it is
+    NOT expected to meet the 1e-3 parity bar (SURVEY.md §7 measured 5.5e-2 for bf16 autocast on the reference itself)."""
+    from avid_cma_b200.criterions import AVID
+    g = golden("step_config1")
+    B, N, K, size, seed = int(g["B"]), int(g["N"]), int(g["K"]), int(g["size"]), int(g["seed"])
+    spec = g["spec"].tolist()
+    model = _load_model(seed, "bf16")
+    crit = AVID(num_data=N, embedding_dim=128, num_negatives=K, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=0)
+    crit.nce_average.view1_mem.copy_(synth.bank(N, seed=seed, tag="bank_v"))
+    crit.nce_average.view2_mem.copy_(synth.bank(N, seed=seed, tag="bank_a"))
+    y = torch.from_numpy(g["y"])
+    idx = synth.negatives(y, K, N, seed).to(DEV)
+    crit.nce_average.sample_negatives = lambda y_, K_: idx
+    ve, ae = model(synth.clips(B, 8, size, seed).to(DEV), synth.spectrograms(B, spec[0], spec[1], seed).to(DEV))
+    loss, _ = crit(ve, ae, y.to(DEV))
+    loss.backward()
+    ev, ea = _rel(ve, torch.from_numpy(g["video_emb"])), _rel(ae, torch.from_numpy(g["audio_emb"]))
+    print("bf16 single-pass embedding errors", ev, ea)
+    assert ev < 0.25 and ea < 0.1
+    assert abs(float(loss) - float(g["total"])) < 0.05 * float(g["total"])
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
 
 
 def test_towers_eval_mode_and_return_embs():
