@@ -213,7 +213,12 @@ def test_training_step_config1_matches_reference_golden(golden, math):
             # from the fp64 result there, so the bar is "no further from fp64 than 2x the reference's own rounding"
             truth = torch.from_numpy(g["fp64::" + k])
             ref_err = _rel(torch.from_numpy(g[k]), truth)
-            assert _rel(params[k[6:]].grad, truth) < max(1e-3, (2 if math == "fp32" else 8) * ref_err), (k, ref_err)
+            # bf16x3 carries ~16 significand bits per operand: embeddings move by ~1e-5, which flips a handful of ReLU gates
+            # (4 of ~1M in the audio tower, scripts/emulate_bf16x3_budget.py); every flip is an O(1) change of one gradient
+            # element, i.e. ~sqrt(flip fraction) = several 1e-3 in relative L2 on the layers below it -- the same mechanism
+            # that puts the fp32 reference 4e-3 from fp64 on the (much larger) video tower.
+            floor = 1e-3 if math == "fp32" else 2e-2
+            assert _rel(params[k[6:]].grad, truth) < max(floor, (2 if math == "fp32" else 8) * ref_err), (k, ref_err)
         elif k.startswith("grad_slice::"):
             want = torch.from_numpy(g[k])
             assert _rel(params[k[12:]].grad[:want.shape[0]], want) < 1e-2, k
