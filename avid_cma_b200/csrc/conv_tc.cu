@@ -46,15 +46,21 @@ constexpr int kBM = 128;        // output pixels per CTA (UMMA M)
 constexpr int kBK = 64;         // channels per k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int kTcThreads = 192; // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
 
+constexpr int kMaxTaps = 32;
+
 struct TcConvParams {
-    int M;                          // destination pixels
-    int td, hd, wd, cd;             // destination extents / channels (GEMM N total)
+    int M;                          // destination pixels of this launch, enumerated ((n * tq + t) * hq + h) * wq + w
+    int tq, hq, wq;                 // extents of that enumeration (the whole output, or one stride-parity class of a strided dgrad)
+    int cd;                         // destination channels (GEMM N total)
     int cs;                         // source channels (GEMM K per tap)
-    int kt, kh, kw;                 // filter taps
-    int st, sh, sw;                 // traversal strides (forward conv stride; 1 for dgrad)
-    int pt, ph, pw;                 // padding in SOURCE coordinates (dgrad: k-1-p)
-    int flip;                       // dgrad: filter tap (kt-1-a, kh-1-b, kw-1-c) multiplies source offset (a, b, c)
+    int st, sh, sw;                 // source traversal strides (forward conv stride; 1 for dgrad)
+    int bt, bh, bw;                 // source coordinate read by tap offset 0 for destination pixel 0 (forward: -padding)
+    int ntaps;
+    uint32_t taps[kMaxTaps];        // off_w | off_h << 8 | off_t << 16 | filter tap << 24 (offsets relative to bt/bh/bw)
     int x3;                         // 1: hi/lo planes, 3 MMAs per k-step; 0: hi only
+    // destination addressing: enumerated pixel (n, t, h, w) -> ((n * Td + t * ot + rt) * Hd + h * oh + rh) * Wd + w * ow + rw
+    int strided_out;
+    int Td, Hd, Wd, ot, oh, ow, rt, rh, rw;
 };
 
 template <int BN>
@@ -82,8 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
     const int cblocks = p.cs / kBK;
-    const int taps = p.kt * p.kh * p.kw;
-    const int nkb = taps * cblocks;
+    const int nkb = p.ntaps * cblocks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a_hi);
@@ -108,25 +113,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         int m = m0;
-        const int w_o = m % p.wd;  m /= p.wd;
-        const int h_o = m % p.hd;  m /= p.hd;
-        const int t_o = m % p.td;
-        const int n_i = m / p.td;
-        const int bw = w_o * p.sw - p.pw, bh = h_o * p.sh - p.ph, bt = t_o * p.st - p.pt;   // base pixel (tap 0) in source coordinates
+        const int w_o = m % p.wq;  m /= p.wq;
+        const int h_o = m % p.hq;  m /= p.hq;
+        const int t_o = m % p.tq;
+        const int n_i = m / p.tq;
+        const int bw = w_o * p.sw + p.bw, bh = h_o * p.sh + p.bh, bt = t_o * p.st + p.bt;   // source pixel read by tap offset 0
         const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
         int stage = 0, phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kBK;
-            const int a = tap / (p.kh * p.kw), r = tap - a * p.kh * p.kw;
-            const int b = r / p.kw, c = r - b * p.kw;
-            const int ftap = p.flip ? ((p.kt - 1 - a) * p.kh + (p.kh - 1 - b)) * p.kw + (p.kw - 1 - c) : tap;
+            const uint32_t tp = p.taps[tap];
+            const uint16_t c = tp & 0xFF, b = (tp >> 8) & 0xFF, a = (tp >> 16) & 0xFF;
+            const int ftap = tp >> 24;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * S::kStageBytes;
             mbar_expect_tx(&full_bar[stage], tx);
-            tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, (uint16_t)c, (uint16_t)b, (uint16_t)a);
+            tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
             tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
             if (p.x3) {
-                tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, (uint16_t)c, (uint16_t)b, (uint16_t)a);
+                tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
                 tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
             }
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }
@@ -163,7 +168,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tc_fence_after();
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = m0 + q * 32 + lane;
-        const size_t row = (size_t)m * p.cd + n0;
+        size_t pix = (size_t)m;
+        if (p.strided_out) {            // one stride-parity class of a strided input gradient: scatter rows to their pixels
+            int r = m;
+            const int w_o = r % p.wq;  r /= p.wq;
+            const int h_o = r % p.hq;  r /= p.hq;
+            const int t_o = r % p.tq;
+            const int n_i = r / p.tq;
+            pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
+        }
+        const size_t row = pix * p.cd + n0;
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) {
             uint32_t r[32];
@@ -413,55 +427,129 @@ static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const 
     return check_launch("conv_tc_kernel");
 }
 
+// One dimension of one launch: which destination coordinates it enumerates, which source coordinates / filter taps they read.
+struct DimPlan {
+    int cnt = 0;            // enumerated destination coordinates
+    int base = 0;           // source coordinate of tap offset 0 for destination coordinate 0 (== im2col lower corner)
+    int upper = 0;          // im2col upper corner
+    int trav = 1;           // source traversal stride
+    int ntap = 0;
+    int off[8], ftap[8];    // source offset (>= 0, relative to base) and filter tap index
+    int ostride = 1, r = 0; // destination coordinate = enumerated * ostride + r
+};
+
+// forward: destination = conv output, source = input
+static DimPlan plan_forward(int dst, int k, int s, int pad) {
+    DimPlan d;
+    d.cnt = dst;  d.base = -pad;  d.upper = pad - (k - 1);  d.trav = s;  d.ntap = k;
+    for (int j = 0; j < k; ++j) { d.off[j] = j;  d.ftap[j] = j; }
+    return d;
+}
+// input gradient, destination coordinates i = q * s + r:  din[i] = sum_b dout[(i + pad - b) / s] w[b] over the taps b with
+// (i + pad - b) divisible by s, i.e. a stride-1 correlation of dout with the taps of residue class r
+static DimPlan plan_dgrad(int dst, int src, int k, int s, int pad, int r) {
+    DimPlan d;
+    d.ostride = s;  d.r = r;  d.trav = 1;
+    d.cnt = r < dst ? (dst - r + s - 1) / s : 0;
+    int lo = 1 << 30;
+    for (int b = 0; b < k; ++b) {
+        const int x = r + pad - b;
+        if (((x % s) + s) % s != 0) continue;
+        const int off = (x - (((x % s) + s) % s)) / s;      // exact: x divisible by s
+        d.off[d.ntap] = off;  d.ftap[d.ntap] = b;  ++d.ntap;
+        if (off < lo) lo = off;
+    }
+    if (d.ntap == 0) return d;
+    for (int j = 0; j < d.ntap; ++j) d.off[j] -= lo;
+    d.base = lo;
+    d.upper = lo + d.cnt - src;
+    return d;
+}
+
 // dgrad == 0: out[n,to,ho,wo,co] = conv(in, filt);  a_* = input planes [n,ti,hi,wi,ci], b_* = filter planes [taps][co][ci]
-// dgrad == 1: out[n,ti,hi,wi,ci] = conv_transpose(dout, filt), stride 1 only; a_* = dout planes, b_* = filter planes [taps][ci][co]
+// dgrad == 1: out[n,ti,hi,wi,ci] = conv_transpose(dout, filt); a_* = dout planes, b_* = filter planes [taps][ci][co].  A strided
+//             input gradient is one launch per stride-parity class (st * sh * sw of them), each a stride-1 correlation.
 int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                 const float* addend, float* out, cudaStream_t st) {
     AVID_REQUIRE(s && a_hi && b_hi && out, "conv_tc: NULL pointer");
     AVID_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "conv_tc: give both lo planes (bf16x3) or neither (bf16)");
-    TcConvParams p;
-    int sn, stt, shh, sww;   // source tensor extents
-    if (!dgrad) {
-        p.td = s->to; p.hd = s->ho; p.wd = s->wo; p.cd = s->co; p.cs = s->ci;
-        sn = s->n; stt = s->ti; shh = s->hi; sww = s->wi;
-        p.st = s->st; p.sh = s->sh; p.sw = s->sw;
-        p.pt = s->pt; p.ph = s->ph; p.pw = s->pw;
-        p.flip = 0;
-    } else {
-        AVID_REQUIRE(s->st == 1 && s->sh == 1 && s->sw == 1, "conv_tc: the tensor-core input gradient supports stride 1 only");
-        p.td = s->ti; p.hd = s->hi; p.wd = s->wi; p.cd = s->ci; p.cs = s->co;
-        sn = s->n; stt = s->to; shh = s->ho; sww = s->wo;
-        p.st = p.sh = p.sw = 1;
-        p.pt = s->kt - 1 - s->pt; p.ph = s->kh - 1 - s->ph; p.pw = s->kw - 1 - s->pw;
-        p.flip = 1;
-    }
-    p.kt = s->kt; p.kh = s->kh; p.kw = s->kw;
-    p.x3 = a_lo != nullptr;
-    AVID_REQUIRE(p.cs % kBK == 0, "conv_tc: source channels (%d) must be a multiple of 64", p.cs);
-    AVID_REQUIRE(p.cd % 64 == 0, "conv_tc: destination channels (%d) must be a multiple of 64", p.cd);
-    AVID_REQUIRE(p.pt >= 0 && p.ph >= 0 && p.pw >= 0 && p.pt < 16 && p.ph < 16 && p.pw < 16, "conv_tc: padding out of range");
-    const int64_t M = (int64_t)s->n * p.td * p.hd * p.wd;
-    AVID_REQUIRE(M > 0 && M < ((int64_t)1 << 31) - 256, "conv_tc: bad pixel count");
-    p.M = (int)M;
-    const int lower[3] = {-p.pw, -p.ph, -p.pt};
-    const int upper[3] = {p.pw - (p.kw - 1), p.ph - (p.kh - 1), p.pt - (p.kt - 1)};
-    const int stride[3] = {p.sw, p.sh, p.st};
-    // the im2col box must walk exactly the destination extents
-    AVID_REQUIRE((sww + upper[0] - lower[0] - 1) / stride[0] + 1 == p.wd && (shh + upper[1] - lower[1] - 1) / stride[1] + 1 == p.hd &&
-                 (stt + upper[2] - lower[2] - 1) / stride[2] + 1 == p.td, "conv_tc: geometry mismatch");
-    const int bn = p.cd % 128 == 0 ? 128 : 64;
-    const int taps = p.kt * p.kh * p.kw;
-    CUtensorMap maps[4];
+    AVID_REQUIRE(s->kt >= 1 && s->kh >= 1 && s->kw >= 1 && s->kt <= 8 && s->kh <= 8 && s->kw <= 8 && s->kt * s->kh * s->kw <= kMaxTaps,
+                 "conv_tc: filter %dx%dx%d not supported (at most 8 per dimension, %d taps)", s->kt, s->kh, s->kw, kMaxTaps);
+    AVID_REQUIRE(s->st >= 1 && s->sh >= 1 && s->sw >= 1, "conv_tc: bad stride");
+    const int cs = dgrad ? s->co : s->ci, cd = dgrad ? s->ci : s->co;
+    AVID_REQUIRE(cs % kBK == 0, "conv_tc: source channels (%d) must be a multiple of 64", cs);
+    AVID_REQUIRE(cd % 64 == 0, "conv_tc: destination channels (%d) must be a multiple of 64", cd);
+    const int src[3] = {dgrad ? s->wo : s->wi, dgrad ? s->ho : s->hi, dgrad ? s->to : s->ti};   // (w, h, t) order, like the tensor map
+    const int dst[3] = {dgrad ? s->wi : s->wo, dgrad ? s->hi : s->ho, dgrad ? s->ti : s->to};
+    const int kk[3] = {s->kw, s->kh, s->kt}, ss[3] = {s->sw, s->sh, s->st}, pp[3] = {s->pw, s->ph, s->pt};
+    const int64_t dst_pixels = (int64_t)s->n * dst[0] * dst[1] * dst[2];
+    AVID_REQUIRE(dst_pixels > 0 && dst_pixels < ((int64_t)1 << 31) - 256, "conv_tc: bad pixel count");
+    const int bn = cd % 128 == 0 ? 128 : 64;
+    const int taps_total = s->kt * s->kh * s->kw;
+    const bool x3 = a_lo != nullptr;
     int rc;
-    if ((rc = encode_im2col(&maps[0], a_hi, sn, stt, shh, sww, p.cs, lower, upper, stride, kBM))) return rc;
-    if ((rc = encode_tiled_2d(&maps[2], b_hi, (uint64_t)taps * p.cd, p.cs, bn, kBK))) return rc;
-    maps[1] = maps[0];
-    maps[3] = maps[2];
-    if (p.x3) {
-        if ((rc = encode_im2col(&maps[1], a_lo, sn, stt, shh, sww, p.cs, lower, upper, stride, kBM))) return rc;
-        if ((rc = encode_tiled_2d(&maps[3], b_lo, (uint64_t)taps * p.cd, p.cs, bn, kBK))) return rc;
+    CUtensorMap map_b[2];
+    if ((rc = encode_tiled_2d(&map_b[0], b_hi, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
+    map_b[1] = map_b[0];
+    if (x3 && (rc = encode_tiled_2d(&map_b[1], b_lo, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
+
+    const int classes[3] = {dgrad ? ss[0] : 1, dgrad ? ss[1] : 1, dgrad ? ss[2] : 1};
+    // classes whose residue meets no filter tap (filter smaller than the stride) receive no gradient: zero fill first
+    bool any_empty = false;
+    if (dgrad)
+        for (int d = 0; d < 3; ++d)
+            for (int r = 0; r < classes[d]; ++r) any_empty |= plan_dgrad(dst[d], src[d], kk[d], ss[d], pp[d], r).ntap == 0;
+    if (any_empty) {
+        AVID_REQUIRE(addend == nullptr, "conv_tc: an addend is not supported when the filter is smaller than the stride");
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)dst_pixels * cd * sizeof(float), st);
+        if (e != cudaSuccess) { set_error("conv_tc: memset: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
     }
-    return bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, st) : launch_conv_tc<64>(maps, p, addend, out, st);
+    for (int rt = 0; rt < classes[2]; ++rt)
+        for (int rh = 0; rh < classes[1]; ++rh)
+            for (int rw = 0; rw < classes[0]; ++rw) {
+                const int rr[3] = {rw, rh, rt};
+                DimPlan d[3];
+                bool empty = false;
+                for (int i = 0; i < 3; ++i) {
+                    d[i] = dgrad ? plan_dgrad(dst[i], src[i], kk[i], ss[i], pp[i], rr[i]) : plan_forward(dst[i], kk[i], ss[i], pp[i]);
+                    empty |= d[i].ntap == 0 || d[i].cnt == 0;
+                }
+                if (empty) continue;
+                TcConvParams p;
+                p.wq = d[0].cnt;  p.hq = d[1].cnt;  p.tq = d[2].cnt;
+                p.M = s->n * p.tq * p.hq * p.wq;
+                p.cd = cd;  p.cs = cs;
+                p.sw = d[0].trav;  p.sh = d[1].trav;  p.st = d[2].trav;
+                p.bw = d[0].base;  p.bh = d[1].base;  p.bt = d[2].base;
+                p.ntaps = 0;
+                for (int a = 0; a < d[2].ntap; ++a)
+                    for (int b = 0; b < d[1].ntap; ++b)
+                        for (int c = 0; c < d[0].ntap; ++c) {
+                            const uint32_t ftap = (uint32_t)((d[2].ftap[a] * s->kh + d[1].ftap[b]) * s->kw + d[0].ftap[c]);
+                            p.taps[p.ntaps++] = (uint32_t)d[0].off[c] | ((uint32_t)d[1].off[b] << 8) | ((uint32_t)d[2].off[a] << 16) | (ftap << 24);
+                        }
+                p.x3 = x3;
+                p.strided_out = dgrad && (ss[0] > 1 || ss[1] > 1 || ss[2] > 1);
+                p.Wd = dst[0];  p.Hd = dst[1];  p.Td = dst[2];
+                p.ow = d[0].ostride;  p.oh = d[1].ostride;  p.ot = d[2].ostride;
+                p.rw = d[0].r;  p.rh = d[1].r;  p.rt = d[2].r;
+                const int lower[3] = {d[0].base, d[1].base, d[2].base};
+                const int upper[3] = {d[0].upper, d[1].upper, d[2].upper};
+                const int stride[3] = {d[0].trav, d[1].trav, d[2].trav};
+                for (int i = 0; i < 3; ++i)
+                    AVID_REQUIRE(lower[i] >= -16 && lower[i] <= 15 && upper[i] >= -16 && upper[i] <= 15 &&
+                                     (src[i] + upper[i] - lower[i] - 1) / stride[i] + 1 == d[i].cnt,
+                                 "conv_tc: geometry not expressible as an im2col box (dim %d: lower %d upper %d)", i, lower[i], upper[i]);
+                CUtensorMap maps[4];
+                if ((rc = encode_im2col(&maps[0], a_hi, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
+                maps[1] = maps[0];
+                if (x3 && (rc = encode_im2col(&maps[1], a_lo, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
+                maps[2] = map_b[0];
+                maps[3] = map_b[1];
+                rc = bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, st) : launch_conv_tc<64>(maps, p, addend, out, st);
+                if (rc) return rc;
+            }
+    return AVID_OK;
 }
 
 template <int BN>

@@ -10,7 +10,7 @@ the tensors its backward needs in a `saved` record.
 Math modes (ops.MATH_*): FP32 runs the CUDA-core implicit-GEMM kernels; BF16X3 / BF16 run every layer
 whose channel counts are multiples of 64 (all but the two stems) on the tcgen05 kernels, with
 activations and gradients handed from layer to layer as bf16 (hi, lo) planes written by the
-BatchNorm+ReLU kernels.  The strided input gradients (9 layers) use the fp32 kernel in every mode.
+BatchNorm+ReLU kernels.  Strided input gradients run as one tcgen05 launch per stride-parity class.
 """
 import torch
 import torch.nn as nn
@@ -53,9 +53,8 @@ class ConvOp:
         self.w_tap, self.w_tap_t = w_tap, w_tap_t          # fp32 [taps, ci, co] / [taps, co, ci]
         if self.tc:
             self.wf_hi, self.wf_lo = ops.split_bf16(w_tap_t, self.x3)           # forward operand, K-major in ci
-            if self.unit_stride:
-                self.wd_hi, self.wd_lo = ops.split_bf16(w_tap, self.x3)         # dgrad operand, K-major in co
-                self.w_tap = self.w_tap_t = None
+            self.wd_hi, self.wd_lo = ops.split_bf16(w_tap, self.x3)             # dgrad operand, K-major in co
+            self.w_tap = self.w_tap_t = None
 
     def forward(self, x, addend=None):
         if self.tc:
@@ -64,7 +63,7 @@ class ConvOp:
         return ops.conv_forward(self.shape, x.f32, self.w_tap, addend=addend, ci_real=self.ci_real)
 
     def needs_f32_dz(self):
-        return not self.tc or not self.unit_stride
+        return not self.tc
 
     def wgrad(self, x, dz):
         if self.tc:
@@ -74,7 +73,7 @@ class ConvOp:
         return ops.filter_from_tapmajor(dw, self.conv.weight)
 
     def dgrad(self, dz, addend=None):
-        if self.tc and self.unit_stride:
+        if self.tc:
             return ops.conv_dgrad_tc(self.shape, dz.hi, dz.lo, self.wd_hi, self.wd_lo, addend=addend)
         return ops.conv_dgrad(self.shape, dz.f32, self.w_tap_t, addend=addend)
 

@@ -232,7 +232,7 @@ def conv_forward_tc(s, x_hi, x_lo, w_hi, w_lo, addend=None, out=None, ci_real=No
 
 
 def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None):
-    """tcgen05 input gradient (stride 1); d_* planes [n,to,ho,wo,co] bf16, w_* planes [taps,ci,co] bf16."""
+    """tcgen05 input gradient (any stride); d_* planes [n,to,ho,wo,co] bf16, w_* planes [taps,ci,co] bf16."""
     if out is None:
         out = torch.empty(s.n, s.ti, s.hi, s.wi, s.ci, dtype=torch.float32, device=d_hi.device)
     e0 = _t0()

@@ -194,7 +194,8 @@ int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const floa
  * (AVID_MATH_BF16).  Activations are fetched by TMA im2col-mode loads, filters by tiled TMA loads.
  * Channel counts must be multiples of 64 (every layer of both towers except the two stems).
  *   forward: in planes [n,ti,hi,wi,ci], filter planes K-major [taps][co][ci] (the w_tap_t layout)
- *   dgrad  : dout planes [n,to,ho,wo,co], filter planes [taps][ci][co] (the w_tap layout), stride 1 only  */
+ *   dgrad  : dout planes [n,to,ho,wo,co], filter planes [taps][ci][co] (the w_tap layout); a strided gradient runs as one
+ *            stride-1 correlation per stride-parity class of the input pixels (st*sh*sw launches)                      */
 int avid_split_bf16(const float* x, void* hi, void* lo /* may be NULL */, int64_t n, void* stream);
 int avid_conv_forward_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
                          const float* addend, float* out, void* stream);

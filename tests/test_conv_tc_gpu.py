@@ -18,6 +18,9 @@ TC_CASES = [
     (3, 128, 256, (2, 14, 14), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     (1, 512, 512, (1, 4, 4), (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # conv5x temporal at config-1 size (T = 1)
     (4, 64, 64, (8, 28, 28), (1, 3, 3), (1, 1, 1), (0, 1, 1)),     # config-1 conv2x spatial: 196 tiles
+    (2, 64, 64, (1, 25, 33), (1, 3, 3), (1, 2, 2), (0, 1, 1)),     # audio block entry, odd extents (ragged parity classes)
+    (2, 64, 128, (3, 7, 9), (3, 3, 3), (2, 2, 2), (1, 1, 1)),      # full 3-D strided filter: 8 parity classes
+    (1, 64, 64, (5, 6, 7), (3, 1, 1), (2, 1, 1), (0, 0, 0)),       # unpadded strided temporal (negative tap offsets)
 ]
 
 
@@ -54,10 +57,14 @@ def test_conv_tc_forward_and_dgrad(case, x3):
     d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
     dw = ops.filter_from_tapmajor(ops.conv_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo), wt.to(DEV))
     assert _rel(dw, wd.grad) < tol
-    if s == (1, 1, 1):
-        wd_hi, wd_lo = ops.split_bf16(w_tap, x3)          # dgrad: [taps, ci, co]
-        din = ops.conv_dgrad_tc(shape, d_hi, d_lo, wd_hi, wd_lo)
-        assert _rel(ops.nhwc_to_nchw(din), xd.grad) < tol
+    wd_hi, wd_lo = ops.split_bf16(w_tap, x3)              # dgrad: [taps, ci, co]
+    din = torch.full((n, t, h, w, ci), float("nan"), device=DEV)      # every pixel must be written, also by strided gradients
+    ops.conv_dgrad_tc(shape, d_hi, d_lo, wd_hi, wd_lo, out=din)
+    assert _rel(ops.nhwc_to_nchw(din), xd.grad) < tol
+    if k != (1, 1, 1):                                    # an addend needs every stride-parity class to meet a filter tap
+        add_in = torch.randn(x.shape, generator=g)
+        din2 = ops.conv_dgrad_tc(shape, d_hi, d_lo, wd_hi, wd_lo, addend=ops.nchw_to_nhwc(add_in.to(DEV)))
+        assert _rel(ops.nhwc_to_nchw(din2), xd.grad + add_in.double()) < tol
 
 
 def test_split_bf16_reconstructs_16_bits():

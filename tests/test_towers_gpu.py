@@ -221,7 +221,8 @@ def test_training_step_config1_matches_reference_golden(golden, math):
             assert _rel(params[k[6:]].grad, truth) < max(floor, (2 if math == "fp32" else 8) * ref_err), (k, ref_err)
         elif k.startswith("grad_slice::"):
             want = torch.from_numpy(g[k])
-            assert _rel(params[k[12:]].grad[:want.shape[0]], want) < 1e-2, k
+            # fp32 reference vs fp64 is already 4e-3 here (ReLU-gate flips, see above); 16 operand bits flip ~256x more gates
+            assert _rel(params[k[12:]].grad[:want.shape[0]], want) < (1e-2 if math == "fp32" else 5e-2), k
         elif k.startswith("rm::"):
             _close(sd[k[4:] + ".running_mean"], g[k], 1e-3, 1e-6)
         elif k.startswith("rv::"):
