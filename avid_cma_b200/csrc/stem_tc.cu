@@ -1,0 +1,495 @@
+// tcgen05 kernels for the two stem convolutions (video 3x7x7 / audio 7x7, stride 2 in h and w, Cin = 3 / 1): the layers
+// whose K dimension (kt*kh*kw*Cin = 441 / 49) has no 64-channel blocks for the generic im2col kernel (conv_tc.cu).
+//
+// Operand A without an im2col buffer ("Toeplitz view"): the clip is stored channels-last with Cin padded to 4 and the row
+// padded in w ([n][t][h][wp][4] bf16, avid_stem_pack).  One output pixel's 7 horizontal taps x 4 channels are then 28 of 32
+// CONTIGUOUS elements starting at padded pixel 2*wo, and consecutive output pixels start 2 pixels = 16 bytes apart -- so a
+// tiled tensor map whose dim-1 stride (16 B) is smaller than its dim-0 extent (64 B) delivers A[pixel][k = (kw, c)] rows
+// directly (TMA only requires 16-byte-multiple strides; verified on B200 by scripts/probes/toeplitz_tma.cu).  The vertical
+// stride 2 is the map's elementStride, vertical / temporal padding is TMA zero fill.
+//
+// Row reuse: a tile is an 8 (ho) x 16 (wo) output patch.  For one temporal tap and one row parity the kernel loads 11
+// input rows ONCE ([row][wo][32] = 1 KB per row, 64-byte swizzle); the A operand of vertical tap kh is the 128-row window
+// starting at row kh/2 of the slot of parity kh%2 -- 4 (or 3) taps share each load.  GEMM K per (kt, kh) "chunk" is 32.
+//
+// forward : D[128 pixels][64 co] += A_chunk[128][32] * W_chunk[64 co][32]^T; all filter chunks stay resident in shared
+//           memory, persistent CTAs, accumulator double-buffered in TMEM so the epilogue of tile i overlaps tile i+1.
+// wgrad   : dW[(kh-group, kw, c)][co] += A^T dZ with both operands MN-major (the pixel index is the smem row index); the 4
+//           vertical taps of one parity form the 128 accumulator rows (atoms 1 KB = one input row apart), one accumulator
+//           per (kt, parity) lives in TMEM for the whole kernel; pixels are split over persistent CTAs, fp32 atomics at the end.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace avid {
+using namespace tc;
+
+constexpr int kStemThreads = 192;            // warp 0: TMA, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+constexpr int kStemCo = 64;
+constexpr int kTileH = 8, kTileW = 16;       // output patch of one tile: 128 pixels = UMMA M (forward) / one k-block (wgrad)
+constexpr int kRowBytes = kTileW * 64;       // one input row of the Toeplitz view: 16 wo x 32 elements x 2 B
+constexpr int kSlotRows = 11;                // rows per (kt, parity, plane) unit: tap offsets kh/2 in 0..3 plus 8 output rows
+constexpr int kSlotBytes = kSlotRows * kRowBytes;
+constexpr int kChunkBBytes = kStemCo * 64;   // [64 co][32 k] bf16
+constexpr int kDzBytes = 128 * 128;          // [128 pixels][64 co] bf16
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448 - 1024;    // 227 KB minus alignment slack
+
+struct StemParams {
+    int n, to, ho, wo;      // output extents
+    int kt, kh, kw, ci;     // taps; ci = real input channels (<= 4)
+    int st, pt, ph;         // temporal stride / padding, vertical padding (vertical and horizontal strides are 2)
+    int tiles_h, tiles_w, num_tiles;
+    int x3, stages;
+};
+
+__device__ __forceinline__ void tile_coords(const StemParams& p, int tile, int& n_i, int& t_o, int& h0, int& w0) {
+    const int tw = tile % p.tiles_w;  tile /= p.tiles_w;
+    const int th = tile % p.tiles_h;  tile /= p.tiles_h;
+    t_o = tile % p.to;
+    n_i = tile / p.to;
+    h0 = th * kTileH;
+    w0 = tw * kTileW;
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const StemParams p,
+                    float* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int chunks = p.kt * p.kh, planes = p.x3 ? 2 : 1;
+    uint8_t* w_smem = smem;                                          // [plane][chunk][64 co][32 k]
+    uint8_t* ring = smem + planes * chunks * kChunkBBytes;           // [stage][11 rows][16 wo][32 k]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.stages * kSlotBytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* w_bar = empty_bar + kMaxStages;
+    uint64_t* tmem_full = w_bar + 1;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x_hi);
+        prefetch_tensormap(&map_w_hi);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(w_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);     // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);     // two 64-column accumulators
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: the filter once, then (kt, parity, plane) row slots of every tile =====
+        mbar_expect_tx(w_bar, (uint32_t)(planes * chunks * kChunkBBytes));
+        for (int pl = 0; pl < planes; ++pl)
+            for (int c = 0; c < chunks; ++c)
+                tma_load_2d(w_smem + (pl * chunks + c) * kChunkBBytes, pl ? &map_w_lo : &map_w_hi, w_bar, c * 32, 0);
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int n_i, t_o, h0, w0;
+            tile_coords(p, tile, n_i, t_o, h0, w0);
+            for (int a = 0; a < p.kt; ++a)
+                for (int par = 0; par < 2 && par < p.kh; ++par)
+                    for (int pl = 0; pl < planes; ++pl) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], kSlotRows * kRowBytes);
+                        tma_load_5d(ring + stage * kSlotBytes, pl ? &map_x_lo : &map_x_hi, &full_bar[stage], 0, w0, 2 * h0 - p.ph + par,
+                                    t_o * p.st - p.pt + a, n_i);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 0, 0);
+        mbar_wait(w_bar, 0);
+        const uint32_t w_base = smem_u32(w_smem);
+        int stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * kStemCo;
+            uint32_t accumulate = 0;
+            for (int a = 0; a < p.kt; ++a)
+                for (int par = 0; par < 2 && par < p.kh; ++par)
+                    for (int pl = 0; pl < planes; ++pl) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t slot = smem_u32(ring + stage * kSlotBytes);
+                        for (int kh = par; kh < p.kh; kh += 2) {
+                            const uint32_t wc = w_base + (a * p.kh + kh) * kChunkBBytes;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t da = make_smem_desc_sw64(slot + (kh >> 1) * kRowBytes + ks * 32, 16, 512);
+                                const uint64_t db_hi = make_smem_desc_sw64(wc + ks * 32, 16, 512);
+                                if (pl == 0) {
+                                    umma_bf16(acc, da, db_hi, idesc, accumulate);
+                                    accumulate = 1;
+                                    if (p.x3) umma_bf16(acc, da, make_smem_desc_sw64(wc + chunks * kChunkBBytes + ks * 32, 16, 512), idesc, 1);
+                                } else {
+                                    umma_bf16(acc, da, db_hi, idesc, 1);
+                                }
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+            umma_commit(&tmem_full[buf]);
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue: TMEM -> registers -> global, one output pixel (64 channels) per thread =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            int n_i, t_o, h0, w0;
+            tile_coords(p, tile, n_i, t_o, h0, w0);
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + buf * kStemCo + ((uint32_t)(q * 32) << 16);
+            tmem_ld_32x32b_x32(taddr, v0);
+            tmem_ld_32x32b_x32(taddr + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);     // the accumulator is in registers: the next tile may start
+            const int ho = h0 + r / kTileW, wo = w0 + r % kTileW;
+            if (ho < p.ho && wo < p.wo) {
+                float4* dst = reinterpret_cast<float4*>(out + ((((size_t)n_i * p.to + t_o) * p.ho + ho) * p.wo + wo) * kStemCo);
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    dst[v] = make_float4(__uint_as_float(v0[4 * v]), __uint_as_float(v0[4 * v + 1]), __uint_as_float(v0[4 * v + 2]),
+                                         __uint_as_float(v0[4 * v + 3]));
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    dst[8 + v] = make_float4(__uint_as_float(v1[4 * v]), __uint_as_float(v1[4 * v + 1]), __uint_as_float(v1[4 * v + 2]),
+                                             __uint_as_float(v1[4 * v + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// ---- filter gradient -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                  const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, const StemParams p,
+                  uint32_t tmem_cols, float* __restrict__ dfilt) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int planes = p.x3 ? 2 : 1;
+    uint8_t* dz_smem = smem;                                   // [2 buffers][plane][128 pixels][64 co]
+    uint8_t* ring = smem + 2 * planes * kDzBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.stages * kSlotBytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* dz_full = empty_bar + kMaxStages;   // [2]
+    uint64_t* dz_empty = dz_full + 2;             // [2]
+    uint64_t* accum_bar = dz_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x_hi);
+        prefetch_tensormap(&map_d_hi);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&dz_full[b], 1);
+            mbar_init(&dz_empty[b], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool has_work = (int)blockIdx.x < p.num_tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            int n_i, t_o, h0, w0;
+            tile_coords(p, tile, n_i, t_o, h0, w0);
+            const int buf = it & 1;
+            mbar_wait(&dz_empty[buf], ((it >> 1) & 1) ^ 1);
+            mbar_expect_tx(&dz_full[buf], (uint32_t)(planes * kDzBytes));
+            for (int pl = 0; pl < planes; ++pl)
+                tma_load_5d(dz_smem + (buf * planes + pl) * kDzBytes, pl ? &map_d_lo : &map_d_hi, &dz_full[buf], 0, w0, h0, t_o, n_i);
+            for (int a = 0; a < p.kt; ++a)
+                for (int par = 0; par < 2 && par < p.kh; ++par)
+                    for (int pl = 0; pl < planes; ++pl) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], kSlotRows * kRowBytes);
+                        tma_load_5d(ring + stage * kSlotBytes, pl ? &map_x_lo : &map_x_hi, &full_bar[stage], 0, w0, 2 * h0 - p.ph + par,
+                                    t_o * p.st - p.pt + a, n_i);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: A = x slot (MN-major, 64-byte swizzle, 4 tap atoms one row apart), B = dZ (MN-major, 128-byte swizzle) =====
+        constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 1, 1);
+        int stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&dz_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t dz_hi = smem_u32(dz_smem + buf * planes * kDzBytes), dz_lo = dz_hi + kDzBytes;
+            for (int a = 0; a < p.kt; ++a)
+                for (int par = 0; par < 2 && par < p.kh; ++par) {
+                    const uint32_t acc = tmem_base + (a * 2 + par) * kStemCo;
+                    for (int pl = 0; pl < planes; ++pl) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t slot = smem_u32(ring + stage * kSlotBytes);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {          // 16 pixels (one patch row) per MMA
+                            const uint64_t da = make_smem_desc_sw64(slot + ks * kRowBytes, kRowBytes, 512);
+                            const uint64_t db_hi = make_smem_desc_sw128(dz_hi + ks * 2048, 16, 1024);
+                            if (pl == 0) {
+                                umma_bf16(acc, da, db_hi, idesc, (it | ks) != 0);
+                                if (p.x3) umma_bf16(acc, da, make_smem_desc_sw128(dz_lo + ks * 2048, 16, 1024), idesc, 1);
+                            } else {
+                                umma_bf16(acc, da, db_hi, idesc, 1);
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            umma_commit(&dz_empty[buf]);
+        }
+        umma_commit(accum_bar);
+    } else if (warp >= 2 && has_work) {
+        // ===== epilogue: accumulator row = (tap kh = parity + 2*(row/32), kw = (row%32)/4, c = row%4) -> atomics into dW[tap][c][co] =====
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int kwi = (r & 31) >> 2, c = r & 3;
+        for (int a = 0; a < p.kt; ++a)
+            for (int par = 0; par < 2 && par < p.kh; ++par) {
+                const int kh = par + 2 * (r >> 5);
+                const bool valid = kh < p.kh && kwi < p.kw && c < p.ci;
+                float* dst = dfilt + ((size_t)(((a * p.kh + kh) * p.kw + kwi) * 4 + c)) * kStemCo;
+                const uint32_t taddr = tmem_base + (a * 2 + par) * kStemCo + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + j * 32, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            red_add_v4f(dst + j * 32 + 4 * u, __uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                                        __uint_as_float(v[4 * u + 3]));
+                    }
+                }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- packing kernels -------------------------------------------------------------------------------------------------
+// x [n][c][t*h][w] fp32 -> planes [n][t*h][wp][4] bf16 with the pixel w at padded position w + pad_left, zeros elsewhere
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                        int n, int c, int64_t th, int w, int wp, int pad_left) {
+    const int64_t total = (int64_t)n * th * wp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int wq = (int)(i % wp);
+        const int64_t row = i / wp;             // n * th + (t*h index)
+        const int64_t img = row / th, s = row - img * th;
+        const int wr = wq - pad_left;
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float v = (ch < c && wr >= 0 && wr < w) ? __ldg(x + ((img * c + ch) * th + s) * w + wr) : 0.f;
+            h[ch] = __float2bfloat16_rn(v);
+            l[ch] = __float2bfloat16_rn(v - __bfloat162float(h[ch]));
+        }
+        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+        if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// PyTorch filter [co][ci][kt][kh][kw] fp32 -> planes [co][(kt*kh) chunks][32 = (kw padded to 8) x 4 channels] bf16
+__global__ void stem_filter_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int co, int ci,
+                                        int chunks, int kw) {
+    const int total = co * chunks * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 31, chunk = (i >> 5) % chunks, o = (i >> 5) / chunks;
+        const int kwi = e >> 2, c = e & 3;
+        const float v = (kwi < kw && c < ci) ? __ldg(w + (((size_t)o * ci + c) * chunks + chunk) * kw + kwi) : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+static int encode_tiled_nd(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                           const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
+    const TensorMapApi& api = tensor_map_api();
+    if (!api.ok) { set_error("stem_tc: cuTensorMapEncode* driver entry points unavailable"); return AVID_ECUDA; }
+    CUresult r = api.tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("stem_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return AVID_ECUDA; }
+    return AVID_OK;
+}
+
+static int stem_check(const avid_conv_shape_t* s, int wp, StemParams* p) {
+    AVID_REQUIRE(s, "stem_tc: NULL shape");
+    AVID_REQUIRE(s->sh == 2 && s->sw == 2, "stem_tc: vertical and horizontal strides must be 2 (got %d, %d)", s->sh, s->sw);
+    AVID_REQUIRE(s->kw >= 1 && s->kw <= 8 && s->kh >= 1 && s->kh <= 8 && s->kt >= 1 && s->kt <= 4, "stem_tc: filter %dx%dx%d not supported", s->kt, s->kh, s->kw);
+    AVID_REQUIRE(s->ci >= 1 && s->ci <= 4 && s->co == kStemCo, "stem_tc: needs ci <= 4 and co == 64 (got %d, %d)", s->ci, s->co);
+    AVID_REQUIRE(wp == 2 * s->wo + 8, "stem_tc: padded row length must be 2*wo + 8 = %d (got %d)", 2 * s->wo + 8, wp);
+    AVID_REQUIRE(s->wi + s->pw <= wp && s->n > 0 && s->to > 0 && s->ho > 0 && s->wo > 0, "stem_tc: bad geometry");
+    p->n = s->n;  p->to = s->to;  p->ho = s->ho;  p->wo = s->wo;
+    p->kt = s->kt;  p->kh = s->kh;  p->kw = s->kw;  p->ci = s->ci;
+    p->st = s->st;  p->pt = s->pt;  p->ph = s->ph;
+    p->tiles_h = (s->ho + kTileH - 1) / kTileH;
+    p->tiles_w = (s->wo + kTileW - 1) / kTileW;
+    const int64_t tiles = (int64_t)s->n * s->to * p->tiles_h * p->tiles_w;
+    AVID_REQUIRE(tiles < ((int64_t)1 << 31), "stem_tc: too many tiles");
+    p->num_tiles = (int)tiles;
+    return AVID_OK;
+}
+
+static int encode_stem_x(CUtensorMap* map, const void* base, const avid_conv_shape_t* s, int wp) {
+    const cuuint64_t row = (cuuint64_t)wp * 8;   // bytes per padded input row (4 channels x bf16)
+    cuuint64_t dims[5] = {32, (cuuint64_t)s->wo, (cuuint64_t)s->hi, (cuuint64_t)s->ti, (cuuint64_t)s->n};
+    cuuint64_t strides[4] = {16, row, row * s->hi, row * s->hi * s->ti};
+    cuuint32_t box[5] = {32, kTileW, 2 * kSlotRows, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 2, 1, 1};
+    return encode_tiled_nd(map, base, 5, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+int stem_forward_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int wp, const void* w_hi, const void* w_lo, float* out,
+                     cudaStream_t st) {
+    StemParams p;
+    int rc = stem_check(s, wp, &p);
+    if (rc) return rc;
+    AVID_REQUIRE(x_hi && w_hi && out && (x_lo == nullptr) == (w_lo == nullptr), "stem_forward_tc: NULL pointer / mismatched lo planes");
+    p.x3 = x_lo != nullptr;
+    const int planes = p.x3 ? 2 : 1, chunks = p.kt * p.kh;
+    const int w_bytes = planes * chunks * kChunkBBytes;
+    p.stages = (kSmemLimit - 256 - w_bytes) / kSlotBytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    AVID_REQUIRE(p.stages >= 2, "stem_forward_tc: filter does not fit in shared memory");
+    const int smem = 1024 + w_bytes + p.stages * kSlotBytes + 256;
+    CUtensorMap mx[2], mw[2];
+    if ((rc = encode_stem_x(&mx[0], x_hi, s, wp))) return rc;
+    mx[1] = mx[0];
+    if (p.x3 && (rc = encode_stem_x(&mx[1], x_lo, s, wp))) return rc;
+    cuuint64_t wdims[2] = {(cuuint64_t)chunks * 32, kStemCo};
+    cuuint64_t wstr[1] = {(cuuint64_t)chunks * 64};
+    cuuint32_t wbox[2] = {32, kStemCo}, west[2] = {1, 1};
+    if ((rc = encode_tiled_nd(&mw[0], w_hi, 2, wdims, wstr, wbox, west, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    mw[1] = mw[0];
+    if (p.x3 && (rc = encode_tiled_nd(&mw[1], w_lo, 2, wdims, wstr, wbox, west, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) { set_error("stem_forward_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        configured = true;
+    }
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    stem_forward_kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], mw[0], mw[1], p, out);
+    return check_launch("stem_forward_kernel");
+}
+
+int stem_wgrad_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int wp, const void* d_hi, const void* d_lo, float* dfilt,
+                   cudaStream_t st) {
+    StemParams p;
+    int rc = stem_check(s, wp, &p);
+    if (rc) return rc;
+    AVID_REQUIRE(x_hi && d_hi && dfilt && (x_lo == nullptr) == (d_lo == nullptr), "stem_wgrad_tc: NULL pointer / mismatched lo planes");
+    p.x3 = x_lo != nullptr;
+    const int planes = p.x3 ? 2 : 1;
+    p.stages = (kSmemLimit - 256 - 2 * planes * kDzBytes) / kSlotBytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    const int smem = 1024 + 2 * planes * kDzBytes + p.stages * kSlotBytes + 256;
+    uint32_t cols = 32;
+    while ((int)cols < p.kt * 2 * kStemCo) cols <<= 1;
+    CUtensorMap mx[2], md[2];
+    if ((rc = encode_stem_x(&mx[0], x_hi, s, wp))) return rc;
+    mx[1] = mx[0];
+    if (p.x3 && (rc = encode_stem_x(&mx[1], x_lo, s, wp))) return rc;
+    cuuint64_t ddims[5] = {kStemCo, (cuuint64_t)s->wo, (cuuint64_t)s->ho, (cuuint64_t)s->to, (cuuint64_t)s->n};
+    cuuint64_t dstr[4] = {128, (cuuint64_t)s->wo * 128, (cuuint64_t)s->ho * s->wo * 128, (cuuint64_t)s->to * s->ho * s->wo * 128};
+    cuuint32_t dbox[5] = {kStemCo, kTileW, kTileH, 1, 1}, dest[5] = {1, 1, 1, 1, 1};
+    if ((rc = encode_tiled_nd(&md[0], d_hi, 5, ddims, dstr, dbox, dest, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    md[1] = md[0];
+    if (p.x3 && (rc = encode_tiled_nd(&md[1], d_lo, 5, ddims, dstr, dbox, dest, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) { set_error("stem_wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        configured = true;
+    }
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    stem_wgrad_kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], md[0], md[1], p, cols, dfilt);
+    return check_launch("stem_wgrad_kernel");
+}
+
+}  // namespace avid
+
+using namespace avid;
+
+extern "C" {
+
+int avid_stem_pack(const float* x, void* hi, void* lo, int32_t n, int32_t c, int32_t t, int32_t h, int32_t w, int32_t wp, int32_t pad_left,
+                   void* stream) {
+    AVID_REQUIRE(x && hi && n > 0 && c >= 1 && c <= 4 && t > 0 && h > 0 && w > 0 && wp >= w + pad_left && pad_left >= 0 && wp % 2 == 0,
+                 "stem_pack: bad arguments");
+    const int64_t total = (int64_t)n * t * h * wp;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    stem_pack_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n, c,
+                                                                                      (int64_t)t * h, w, wp, pad_left);
+    return check_launch("stem_pack_kernel");
+}
+
+int avid_stem_filter_pack(const float* w_oihw, void* hi, void* lo, int32_t co, int32_t ci, int32_t kt, int32_t kh, int32_t kw, void* stream) {
+    AVID_REQUIRE(w_oihw && hi && co > 0 && ci >= 1 && ci <= 4 && kt >= 1 && kh >= 1 && kw >= 1 && kw <= 8, "stem_filter_pack: bad arguments");
+    const int total = co * kt * kh * 32;
+    stem_filter_pack_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, static_cast<__nv_bfloat16*>(hi),
+                                                                                               static_cast<__nv_bfloat16*>(lo), co, ci, kt * kh, kw);
+    return check_launch("stem_filter_pack_kernel");
+}
+
+int avid_stem_forward_tc(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int32_t wp, const void* filt_hi, const void* filt_lo,
+                         float* out, void* stream) {
+    return stem_forward_run(s, x_hi, x_lo, wp, filt_hi, filt_lo, out, static_cast<cudaStream_t>(stream));
+}
+
+int avid_stem_wgrad_tc(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int32_t wp, const void* dout_hi, const void* dout_lo,
+                       float* dfilt, void* stream) {
+    return stem_wgrad_run(s, x_hi, x_lo, wp, dout_hi, dout_lo, dfilt, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -3,7 +3,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import Act
-from .network_blocks import Basic2DBlock, ConvBNReLU, pad_channels
+from .network_blocks import Basic2DBlock, ConvBNReLU, StemOp, pad_channels
 from ._tower import TowerMixin
 
 __all__ = ['Conv2D']
@@ -28,8 +28,12 @@ class Conv2D(TowerMixin, nn.Module):
         self.out_dim = 512
 
     def _fwd(self, x, training, math, taps=None):
-        xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])).unsqueeze(1))   # (B, 1, T, F, 4): a 2-D layer is t == 1
-        h, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)  # Cin = 1: CUDA-core kernel
+        if math == ops.MATH_FP32:
+            xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])).unsqueeze(1))   # (B, 1, T, F, 4): a 2-D layer is t == 1
+            h, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)  # CUDA-core kernel
+        else:   # Cin = 1: the Toeplitz-view tcgen05 stem kernel
+            op = StemOp(self.conv1[0], x.shape, math)
+            h, s_stem = ConvBNReLU.forward(op.pack(x), self.conv1[0], self.conv1[1], training, math, op=op)
         saved_blocks = []
         for blk, tag in zip((self.block1, self.block2, self.block3, self.block4), ('conv2x', 'conv3x', 'conv4x', 'conv5x')):
             h, sb = blk._fwd(h, training, math)

@@ -78,14 +78,46 @@ class ConvOp:
         return ops.conv_dgrad(self.shape, dz.f32, self.w_tap_t, addend=addend)
 
 
+class StemOp:
+    """The first convolution of a tower (Cin = 3 / 1, 7x7 stride 2) on the tcgen05 stem kernels (csrc/stem_tc.cu): same
+    interface as ConvOp, but its input Act holds the packed planes [n, t, h, wp, 4] written by `pack`."""
+    tc = True
+    unit_stride = False
+
+    def __init__(self, conv, x_shape, math):
+        n, c = x_shape[0], x_shape[1]
+        t, h, w = (1,) * (5 - len(x_shape)) + tuple(x_shape[2:])
+        self.conv = conv
+        self.k, self.s, self.p = _triple(conv.kernel_size), _triple(conv.stride), _triple(conv.padding, 0)
+        self.shape = ops.conv_shape(n, t, h, w, c, conv.out_channels, self.k, self.s, self.p)
+        self.x3 = math == ops.MATH_BF16X3
+        self.wp = 2 * self.shape.wo + 8
+        self.w_hi, self.w_lo = ops.stem_filter_pack(conv.weight.detach(), self.x3)
+
+    def pack(self, x):
+        hi, lo = ops.stem_pack(x, self.wp, self.p[2], self.x3)
+        return Act(None, hi, lo)
+
+    def forward(self, x, addend=None):
+        assert addend is None
+        return ops.stem_forward_tc(self.shape, x.hi, x.lo, self.w_hi, self.w_lo)
+
+    def needs_f32_dz(self):
+        return False
+
+    def wgrad(self, x, dz):
+        return ops.filter_from_tapmajor(ops.stem_wgrad_tc(self.shape, x.hi, x.lo, dz.hi, dz.lo), self.conv.weight)
+
+
 class ConvBNReLU:
     """conv -> train/eval BatchNorm -> ReLU, with an optional residual addend fused into the conv epilogue."""
 
     @staticmethod
-    def forward(x, conv, bn, training, math, addend=None, out_f32=False):
+    def forward(x, conv, bn, training, math, addend=None, out_f32=False, op=None, out_planes=None):
         """x: Act.  Returns (y: Act, saved).  In the tensor-core modes y carries the bf16 planes the next
         convolution reads (plus fp32 when `out_f32`: block outputs feed residual adds and pools)."""
-        op = ConvOp(conv, x.shape, math)
+        if op is None:
+            op = ConvOp(conv, x.shape, math)
         z = op.forward(x, addend)
         if training:
             st = ops.bn_train_stats(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bn.momentum)
@@ -96,7 +128,7 @@ class ConvBNReLU:
             st.mean.copy_(bn.running_mean)
             st.scale.copy_(bn.weight.detach() * st.invstd)
             st.shift.copy_(bn.bias.detach() - bn.running_mean * st.scale)
-        planes = math != ops.MATH_FP32
+        planes = math != ops.MATH_FP32 if out_planes is None else out_planes
         y = ops.bn_relu_forward_act(z, st.scale, st.shift, want_f32=out_f32 or not planes, want_planes=planes, x3=math == ops.MATH_BF16X3)
         return y, (op, x, z, st, bn)
 

@@ -4,7 +4,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import Act
-from .network_blocks import BasicR2P1DBlock, ConvBNReLU, pad_channels
+from .network_blocks import BasicR2P1DBlock, ConvBNReLU, StemOp, pad_channels
 from ._tower import TowerFunction, TowerMixin
 
 
@@ -48,8 +48,12 @@ class R2Plus1D(TowerMixin, nn.Module):
 
     def _fwd(self, x, training, math, taps=None):
         """x (B,3,T,H,W) -> pooled (B,512); saved record for _bwd.  `taps` collects channels-last stage outputs."""
-        xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])))
-        ya, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)   # Cin = 3: CUDA-core kernel
+        if math == ops.MATH_FP32:
+            xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])))
+            ya, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)   # CUDA-core kernel
+        else:   # Cin = 3: the Toeplitz-view tcgen05 stem kernel; its output only feeds the max pool (fp32)
+            op = StemOp(self.conv1[0], x.shape, math)
+            ya, s_stem = ConvBNReLU.forward(op.pack(x), self.conv1[0], self.conv1[1], training, math, out_f32=True, op=op, out_planes=False)
         y = ya.f32
         p = ops.maxpool_1x3x3_forward(y)
         if taps is not None:

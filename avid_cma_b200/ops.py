@@ -252,6 +252,47 @@ def conv_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo, ci_real=None):
     return dw
 
 
+def stem_pack(x, wp, pad_left, need_lo=True):
+    """(n, c, [t,] h, w) fp32 clip / spectrogram -> bf16 planes [n, t, h, wp, 4] of the stem kernels (c <= 4)."""
+    n, c = x.shape[0], x.shape[1]
+    t, h, w = (1,) * (5 - x.dim()) + tuple(x.shape[2:])
+    hi = torch.empty(n, t, h, wp, 4, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if need_lo else None
+    check(_lib.lib().avid_stem_pack(_p(x), _p(hi, torch.bfloat16), _p(lo, torch.bfloat16, optional=True), n, c, t, h, w, wp, pad_left, _stream()))
+    return hi, lo
+
+
+def stem_filter_pack(w, need_lo=True):
+    """PyTorch stem filter (co, ci, [kt,] kh, kw) -> bf16 planes [co, kt*kh, 32]."""
+    co, ci = w.shape[0], w.shape[1]
+    kt, kh, kw = (1,) * (5 - w.dim()) + tuple(w.shape[2:])
+    hi = torch.empty(co, kt * kh, 32, dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if need_lo else None
+    check(_lib.lib().avid_stem_filter_pack(_p(w), _p(hi, torch.bfloat16), _p(lo, torch.bfloat16, optional=True), co, ci, kt, kh, kw, _stream()))
+    return hi, lo
+
+
+def stem_forward_tc(s, x_hi, x_lo, w_hi, w_lo, out=None):
+    """tcgen05 stem convolution; s.ci is the real channel count, x_* the stem_pack planes, w_* the stem_filter_pack planes."""
+    if out is None:
+        out = torch.empty(s.n, s.to, s.ho, s.wo, s.co, dtype=torch.float32, device=x_hi.device)
+    e0 = _t0()
+    check(_lib.lib().avid_stem_forward_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), x_hi.shape[3],
+                                          _p(w_hi, torch.bfloat16), _p(w_lo, torch.bfloat16, optional=True), _p(out), _stream()))
+    _t1(e0, "stem_forward_tc", _conv_flops(s))
+    return out
+
+
+def stem_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo):
+    """tcgen05 stem filter gradient -> fp32 tap-major [taps, 4, co]."""
+    dw = torch.zeros(s.kt * s.kh * s.kw, 4, s.co, dtype=torch.float32, device=x_hi.device)
+    e0 = _t0()
+    check(_lib.lib().avid_stem_wgrad_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), x_hi.shape[3],
+                                        _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(dw), _stream()))
+    _t1(e0, "stem_wgrad_tc", _conv_flops(s))
+    return dw
+
+
 def filter_to_tapmajor(w, ci_pad=None, transpose=True):
     """PyTorch conv weight (co, ci, *k) -> ([taps, ci_pad, co], [taps, co, ci_pad] or None)."""
     co, ci = w.shape[0], w.shape[1]

@@ -230,7 +230,7 @@ def run_ours(a):
         families[name] = {"launches": cnt, "ms_per_step": dur / a.steps, "share_of_step": dur / ms}
         families[name]["GB/s" if name.startswith("nce") else "TFLOP/s"] = rate / (1e9 if name.startswith("nce") else 1e12)
     if fam:
-        top = max((n for n in fam if n.startswith("conv")), key=lambda n: fam[n][1])
+        top = max((n for n in fam if n.startswith(("conv", "stem"))), key=lambda n: fam[n][1])
         work, dur, cnt = fam[top]
         ach = work / (dur * 1e-3) / 1e12
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,

@@ -206,6 +206,24 @@ int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, con
 int avid_conv_wgrad_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* dout_hi, const void* dout_lo,
                        float* dfilt, void* stream);
 
+/* ---- tensor-core stems: the 7x7 / 3x7x7 stride-2 first convolutions with Cin <= 4 (video.py:20, audio.py:22) ------------
+ * The input is packed once per step as bf16 planes [n][t][h][wp][4] (channels zero-padded to 4, rows zero-padded in w to
+ * wp = 2*wo + 8 with pixel w stored at w + pad_left, pad_left = the convolution's pw) so that a tiled tensor map with a
+ * 16-byte pixel-pair stride hands the kernel A[pixel][(kw, c)] rows without an im2col buffer (csrc/stem_tc.cu).
+ * The shape's `ci` is the REAL channel count; sh == sw == 2, kw <= 8, kh <= 8, kt <= 4, co == 64.
+ *   avid_stem_pack        x [n][c][t][h][w] fp32 (the reference's NCDHW / NCHW input) -> hi / lo planes
+ *   avid_stem_filter_pack PyTorch filter [co][ci][kt][kh][kw] fp32 -> planes [co][kt*kh][32 = 8 kw x 4 c] (forward operand)
+ *   avid_stem_forward_tc  out [n,to,ho,wo,64] fp32
+ *   avid_stem_wgrad_tc    dfilt fp32 tap-major [taps][4][64] (the avid_conv_wgrad layout with ci_pad = 4), zeroed by the caller */
+int avid_stem_pack(const float* x, void* hi, void* lo /* may be NULL */, int32_t n, int32_t c, int32_t t, int32_t h, int32_t w,
+                   int32_t wp, int32_t pad_left, void* stream);
+int avid_stem_filter_pack(const float* w_oihw, void* hi, void* lo /* may be NULL */, int32_t co, int32_t ci, int32_t kt, int32_t kh, int32_t kw,
+                          void* stream);
+int avid_stem_forward_tc(const avid_conv_shape_t* s_host, const void* x_hi, const void* x_lo, int32_t wp, const void* filt_hi, const void* filt_lo,
+                         float* out, void* stream);
+int avid_stem_wgrad_tc(const avid_conv_shape_t* s_host, const void* x_hi, const void* x_lo, int32_t wp, const void* dout_hi, const void* dout_lo,
+                       float* dfilt, void* stream);
+
 /* PyTorch parameter layout [co, ci, taps] -> tap-major [taps, ci_pad, co] (channels ci..ci_pad-1 zero) and,
  * when w_tap_t != NULL, its transpose [taps, co, ci_pad] (the filter operand of avid_conv_dgrad). */
 int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, float* w_tap_t, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream);

@@ -72,3 +72,39 @@ def test_split_bf16_reconstructs_16_bits():
     x = torch.randn(4096, device=DEV) * 3
     hi, lo = ops.split_bf16(x)
     assert float(((hi.float() + lo.float()) - x).abs().max() / x.abs().max()) < 2 ** -15
+
+
+# (n, ci, (t,h,w), kernel, stride, padding): the two stems at reduced sizes (co = 64)
+STEM_CASES = [
+    (2, 3, (4, 20, 36), (3, 7, 7), (1, 2, 2), (1, 3, 3)),      # video stem, tiles ragged in h and w
+    (2, 1, (1, 37, 45), (1, 7, 7), (1, 2, 2), (0, 3, 3)),      # audio stem (2-D), odd extents
+    (1, 3, (2, 64, 64), (3, 7, 7), (1, 2, 2), (1, 3, 3)),      # full 16-wide tiles, more tiles than one wave would need rows
+    (3, 3, (8, 112, 112), (3, 7, 7), (1, 2, 2), (1, 3, 3)),    # config-1 video stem: 1176 tiles -> persistent loop, TMEM double buffer
+    (2, 1, (1, 100, 129), (1, 7, 7), (1, 2, 2), (0, 3, 3)),    # config-1 audio stem
+]
+
+
+@pytest.mark.parametrize("x3", [True, False], ids=["bf16x3", "bf16"])
+@pytest.mark.parametrize("case", STEM_CASES, ids=[f"s{i}" for i in range(len(STEM_CASES))])
+def test_stem_tc_forward_and_wgrad(case, x3):
+    from avid_cma_b200 import ops
+    n, ci, (t, h, w), k, s, p = case
+    co = 64
+    g = torch.Generator().manual_seed(hash(case) % 2 ** 31)
+    x = torch.randn(n, ci, t, h, w, generator=g)
+    wt = torch.randn(co, ci, *k, generator=g) / (ci * k[0] * k[1] * k[2]) ** 0.5
+    xd, wd = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    ref = F.conv3d(xd, wd, stride=s, padding=p)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout.double())
+    tol = 3e-5 if x3 else 1e-2
+    shape = ops.conv_shape(n, t, h, w, ci, co, k, s, p)
+    x_hi, x_lo = ops.stem_pack(x.to(DEV), 2 * shape.wo + 8, p[2], x3)
+    w_hi, w_lo = ops.stem_filter_pack(wt.to(DEV), x3)
+    out = ops.stem_forward_tc(shape, x_hi, x_lo, w_hi, w_lo)
+    torch.cuda.synchronize()
+    assert _rel(ops.nhwc_to_nchw(out), ref) < tol
+    d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
+    dw_tap = ops.stem_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo)
+    dw = ops.filter_from_tapmajor(dw_tap, wt.to(DEV))
+    assert _rel(dw, wd.grad) < tol

@@ -204,7 +204,7 @@ def test_training_step_config1_matches_reference_golden(golden, math):
     for n, p in model.named_parameters():
         assert p.grad is not None, n
         worst = max(worst, abs(float(p.grad.double().norm()) - norms[n]) / norms[n])
-    assert worst < 5e-3, worst
+    assert worst < (5e-3 if math == "fp32" else 2e-2), worst      # bf16x3: ReLU-gate flips, see the per-tensor check below
     params = dict(model.named_parameters())
     sd = model.state_dict()
     for k in g.files:
