@@ -5,10 +5,9 @@
 // forward score, the loss term and the gradient w.r.t. the embedding in the same pass.
 //
 // Kernel 1  nce_gather_kernel   grid (B, splits) x 128 threads.  A warp streams rows 8 at a time:
-//           8 x {video,audio} float4 per lane in flight, warp-shuffle dot products against the
-//           normalised embeddings, then ONE lane-parallel pass of the transcendental NCE math
-//           (lane = key*8 + row) and a shuffle-broadcast axpy into the per-lane gradient
-//           accumulators.  Partial (grad_hat, loss) per split go to the workspace.
+//           groups of 8 lanes own one row each (16 columns per lane, 128-byte coalesced group loads), 2 x 4 rows x
+//           2 banks in flight per warp; dot product = 16 FMAs + 3 shuffles, the NCE math runs per group, the
+//           gradient axpy needs no broadcast.  Partial (grad_hat, loss) per split go to the workspace.
 // Kernel 2  nce_reduce_finalize_kernel  grid (B) x 256 threads: fixed-order sum over splits
 //           (deterministic), backward of F.normalize, and -- in the last CTA to finish -- the
 //           batch means and the coefficient mix.
@@ -17,7 +16,6 @@
 
 namespace avid {
 
-constexpr int kRowsPerPass = 8;   // rows a warp holds in registers per bank
 constexpr int kGatherThreads = 128;
 constexpr int kGatherWarps = kGatherThreads / 32;
 
@@ -63,21 +61,47 @@ __device__ __forceinline__ void axpy4(float4& acc, float c, const float4& r) {
     acc.w = fmaf(c, r.w, acc.w);
 }
 
-// x / max(||x||, 1e-12) for the row `b` of a (B,128) matrix, one float4 per lane (avid.py:52-53)
-__device__ __forceinline__ float4 load_normalized(const float* emb, int b, int lane, float* norm_out = nullptr) {
-    float4 v = reinterpret_cast<const float4*>(emb + (size_t)b * kD)[lane];
-    float n = sqrtf(warp_sum(dot4(v, v)));
-    float inv = 1.0f / fmaxf(n, 1e-12f);
-    if (norm_out) *norm_out = n;
-    return make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+// Row layout inside a warp: a bank row (128 floats, 512 B) is owned by a GROUP of 8 lanes; lane l8 of the group holds the
+// four float4 at columns 4*l8 + 32*j (j = 0..3), so each load instruction of the group covers 128 contiguous bytes and a
+// warp instruction fetches 4 rows.  A dot product is 16 FMAs per lane + 3 shuffles for 4 rows at once.
+__device__ __forceinline__ float group_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+__device__ __forceinline__ float dot16(const float4 (&a)[4], const float4 (&b)[4]) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += dot4(a[j], b[j]);
+    return s;
 }
 
-__global__ void __launch_bounds__(kGatherThreads) nce_gather_kernel(const NceParams p) {
+// x / max(||x||, 1e-12) for the row `b` of a (B,128) matrix in the group layout (avid.py:52-53)
+__device__ __forceinline__ void load_normalized(const float* emb, int b, int l8, float4 (&out)[4]) {
+    const float4* src = reinterpret_cast<const float4*>(emb + (size_t)b * kD);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        out[j] = src[l8 + 8 * j];
+        ss += dot4(out[j], out[j]);
+    }
+    const float inv = 1.0f / fmaxf(sqrtf(group_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = make_float4(out[j].x * inv, out[j].y * inv, out[j].z * inv, out[j].w * inv);
+}
+
+// a warp keeps 2 row quads (4 rows each) per bank in flight: 2 x 4 rows x 2 banks x 512 B = 8 KB
+
+__global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {
     const int b = blockIdx.x, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, l8 = lane & 7;
     if (b == 0 && split == 0 && threadIdx.x == 0 && p.counter) *p.counter = 0u;
 
-    const float4 e_ctx[2] = {load_normalized(p.emb[0], b, lane), load_normalized(p.emb[1], b, lane)};
+    float4 e_ctx[2][4];
+    load_normalized(p.emb[0], b, l8, e_ctx[0]);
+    load_normalized(p.emb[1], b, l8, e_ctx[1]);
     const int64_t y = p.y[b];
     const float Z = p.Z ? *p.Z : 1.0f;
     const int32_t* pos_row = (p.positive_set && p.pos_k > 0) ? p.positive_set + (size_t)y * p.pos_k : nullptr;
@@ -87,11 +111,15 @@ __global__ void __launch_bounds__(kGatherThreads) nce_gather_kernel(const NcePar
     const int k_begin = split * p.kc, k_end = min(p.K, k_begin + p.kc);
     const int n_items = npos + max(0, k_end - k_begin);
 
-    // lane-parallel evaluation slot: row my_u of the pass, key my_key (+4 in the second key pass)
-    const int my_u = lane & 7;
-    float4 acc[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};  // grad_hat for ctx video / audio
+    float4 acc[2][4];                 // grad_hat for ctx video / audio, this lane's 16 columns
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the transcendental NCE math is lane-parallel inside a group: lane l8 evaluates (row quad l8 >> 2, key (l8 & 3) + 4 * pass)
     float loss_acc[2] = {0.f, 0.f};
     const int key_passes = (p.num_keys + 3) >> 2;
+    const int u_sel = l8 >> 2;
 
     for (int c0 = warp * 32; c0 < n_items; c0 += kGatherWarps * 32) {
         // each lane describes one item of the chunk: kind 0 = negative k, 1 = self, 2 = positive-set entry
@@ -111,50 +139,63 @@ __global__ void __launch_bounds__(kGatherThreads) nce_gather_kernel(const NcePar
                 if (p.neg_idx_out) p.neg_idx_out[(size_t)b * p.K + kk] = idx;
             }
         }
-        const bool held = idx >= p.row_begin && idx < p.row_end;
+        if (!(idx >= p.row_begin && idx < p.row_end)) kind = -1;      // rows another shard holds are scored there
         const int n_chunk = min(32, n_items - c0);
 
-        for (int j = 0; j < n_chunk; j += kRowsPerPass) {
-            float4 rv[kRowsPerPass], ra[kRowsPerPass];
+        for (int j0 = 0; j0 < n_chunk; j0 += 8) {
+            float4 rv[2][4], ra[2][4];
+            int kind_u[2], kk_u[2];
 #pragma unroll
-            for (int u = 0; u < kRowsPerPass; ++u) {
-                const int64_t idx_u = __shfl_sync(0xffffffffu, idx, (j + u) & 31);
-                const bool ok = __shfl_sync(0xffffffffu, (int)held, (j + u) & 31) && (j + u) < n_chunk;
-                rv[u] = make_float4(0, 0, 0, 0);
-                ra[u] = make_float4(0, 0, 0, 0);
-                if (ok) {
+            for (int u = 0; u < 2; ++u) {
+                const int src = (j0 + 4 * u + grp) & 31;          // the item this group scores in quad u
+                const int64_t idx_u = __shfl_sync(0xffffffffu, idx, src);
+                kind_u[u] = __shfl_sync(0xffffffffu, kind, src);
+                kk_u[u] = __shfl_sync(0xffffffffu, kk, src);
+                if (j0 + 4 * u + grp >= n_chunk) kind_u[u] = -1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    rv[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ra[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (kind_u[u] >= 0) {
                     const size_t off = (size_t)(idx_u - p.row_begin) * kD;
-                    if (p.bank_used[0]) rv[u] = ld_stream(reinterpret_cast<const float4*>(p.bank[0] + off) + lane);
-                    if (p.bank_used[1]) ra[u] = ld_stream(reinterpret_cast<const float4*>(p.bank[1] + off) + lane);
+                    if (p.bank_used[0]) {
+                        const float4* r = reinterpret_cast<const float4*>(p.bank[0] + off) + l8;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rv[u][j] = ld_stream(r + 8 * j);
+                    }
+                    if (p.bank_used[1]) {
+                        const float4* r = reinterpret_cast<const float4*>(p.bank[1] + off) + l8;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ra[u][j] = ld_stream(r + 8 * j);
+                    }
                 }
             }
-            // dots: d[bank][ctx] of row my_u end up on every lane with (lane & 7) == my_u
-            float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+            // d[u][bank][ctx] of this group's two rows, on all 8 lanes of the group
+            float d[2][2][2];
 #pragma unroll
-            for (int u = 0; u < kRowsPerPass; ++u) {
-                float t;
-                if (p.need[0][0]) { t = warp_sum(dot4(rv[u], e_ctx[0])); if (my_u == u) d00 = t; }
-                if (p.need[0][1]) { t = warp_sum(dot4(rv[u], e_ctx[1])); if (my_u == u) d01 = t; }
-                if (p.need[1][0]) { t = warp_sum(dot4(ra[u], e_ctx[0])); if (my_u == u) d10 = t; }
-                if (p.need[1][1]) { t = warp_sum(dot4(ra[u], e_ctx[1])); if (my_u == u) d11 = t; }
+            for (int u = 0; u < 2; ++u) {
+                d[u][0][0] = p.need[0][0] ? group_sum(dot16(rv[u], e_ctx[0])) : 0.f;
+                d[u][0][1] = p.need[0][1] ? group_sum(dot16(rv[u], e_ctx[1])) : 0.f;
+                d[u][1][0] = p.need[1][0] ? group_sum(dot16(ra[u], e_ctx[0])) : 0.f;
+                d[u][1][1] = p.need[1][1] ? group_sum(dot16(ra[u], e_ctx[1])) : 0.f;
             }
-            const int src = (j + my_u) & 31;
-            const int kind_m = __shfl_sync(0xffffffffu, kind, src);
-            const int kk_m = __shfl_sync(0xffffffffu, kk, src);
-            const bool ok_m = __shfl_sync(0xffffffffu, (int)held, src) && (j + my_u) < n_chunk;
-
+            const int kind_m = u_sel ? kind_u[1] : kind_u[0];
+            const int kk_m = u_sel ? kk_u[1] : kk_u[0];
+            float cf[2][2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};      // [u][bank][ctx]: dL/ds / T summed over keys
 #pragma unroll
             for (int kp = 0; kp < 2; ++kp) {
                 if (kp >= key_passes) break;
-                const int my_key = (lane >> 3) + 4 * kp;
+                const int my_key = (l8 & 3) + 4 * kp;
                 float coef = 0.f;
-                if (my_key < p.num_keys && ok_m) {
+                if (my_key < p.num_keys && kind_m >= 0) {
                     const KeyDev key = p.keys[my_key];
                     const bool applies = (kind_m == 0 && kk_m < key.num_neg) || (kind_m == 1 && key.pos_mode == 0) ||
                                          (kind_m == 2 && key.pos_mode == 1);
                     if (applies) {
-                        const float dsel = key.bank == 0 ? (key.ctx == 0 ? d00 : d01) : (key.ctx == 0 ? d10 : d11);
-                        const float s = dsel * p.inv_T;
+                        const float d0 = key.bank == 0 ? (key.ctx == 0 ? d[0][0][0] : d[0][0][1]) : (key.ctx == 0 ? d[0][1][0] : d[0][1][1]);
+                        const float d1 = key.bank == 0 ? (key.ctx == 0 ? d[1][0][0] : d[1][0][1]) : (key.ctx == 0 ? d[1][1][0] : d[1][1][1]);
+                        const float s = (u_sel ? d1 : d0) * p.inv_T;
                         if (p.scores) {
                             const int slot = kind_m == 1 ? 0 : (kind_m == 2 ? 1 + kk_m : 1 + p.score_pos_k + kk_m);
                             p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot] = s;
@@ -176,37 +217,61 @@ __global__ void __launch_bounds__(kGatherThreads) nce_gather_kernel(const NcePar
                     }
                 }
                 if (!p.Z) continue;
-                // grad_hat[ctx] += coef * row(bank): broadcast each slot's coefficient to the warp
+                // hand every (quad, key) coefficient to the 8 lanes of the group
                 const int nk = min(4, p.num_keys - 4 * kp);
                 for (int q = 0; q < nk; ++q) {
-                    const int bank = p.keys[q + 4 * kp].bank, ctx = p.keys[q + 4 * kp].ctx;
-#pragma unroll
-                    for (int u = 0; u < kRowsPerPass; ++u) {
-                        const float cf = __shfl_sync(0xffffffffu, coef, q * 8 + u);
-                        if (bank == 0) {
-                            if (ctx == 0) axpy4(acc[0], cf, rv[u]); else axpy4(acc[1], cf, rv[u]);
-                        } else {
-                            if (ctx == 0) axpy4(acc[0], cf, ra[u]); else axpy4(acc[1], cf, ra[u]);
-                        }
+                    const int bank = p.keys[q + 4 * kp].bank, ctx = p.keys[q + 4 * kp].ctx;      // uniform
+                    const float c0 = __shfl_sync(0xffffffffu, coef, (lane & 24) | q);
+                    const float c1 = __shfl_sync(0xffffffffu, coef, (lane & 24) | 4 | q);
+                    if (bank == 0) {
+                        if (ctx == 0) { cf[0][0][0] += c0; cf[1][0][0] += c1; } else { cf[0][0][1] += c0; cf[1][0][1] += c1; }
+                    } else {
+                        if (ctx == 0) { cf[0][1][0] += c0; cf[1][1][0] += c1; } else { cf[0][1][1] += c0; cf[1][1][1] += c1; }
                     }
                 }
             }
+            if (!p.Z) continue;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (p.need[0][c]) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) axpy4(acc[c][j], cf[u][0][c], rv[u][j]);
+                    }
+                    if (p.need[1][c]) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) axpy4(acc[c][j], cf[u][1][c], ra[u][j]);
+                    }
+                }
         }
     }
     if (!p.Z) return;
 
-    // CTA reduction over the 4 warps, fixed order
+    // sum the 4 groups of the warp (lanes with equal l8), then the 4 warps of the CTA in a fixed order
     __shared__ float4 s_acc[kGatherWarps][2][32];
     __shared__ float s_loss[kGatherWarps][AVID_MAX_KEYS];
-    s_acc[warp][0][lane] = acc[0];
-    s_acc[warp][1][lane] = acc[1];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 v = acc[c][j];
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+                v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+            }
+            if (grp == 0) s_acc[warp][c][l8 + 8 * j] = v;
+        }
 #pragma unroll
     for (int kp = 0; kp < 2; ++kp) {
-        float v = loss_acc[kp];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        float v = loss_acc[kp];         // lane l8 holds the terms of key (l8 & 3) + 4 * kp: sum over quads (xor 4) and groups (xor 8, 16)
         v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if ((lane & 7) == 0) s_loss[warp][(lane >> 3) + 4 * kp] = v;
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 4) s_loss[warp][lane + 4 * kp] = v;
     }
     __syncthreads();
     if (threadIdx.x < 64) {
@@ -341,13 +406,24 @@ __global__ void sample_negatives_kernel(const int64_t* y, int B, int K, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Items per CTA (a multiple of 128 = 4 warps x 32-item chunks) chosen to minimise waves x (items + fixed per-CTA cost) with
+// 3 resident CTAs per SM, so the grid neither ends in a thin second wave nor starves the SMs.
 static void choose_split(int B, int K, int* splits, int* kc) {
-    int s0 = (4 * kNumSMs + B - 1) / B;
-    if (s0 < 1) s0 = 1;
-    int c = (K + s0 - 1) / s0;
-    c = ((c + 127) / 128) * 128;   // 4 warps x 32-item chunks
-    *kc = c;
-    *splits = (K + c - 1) / c;
+    const int slots = 3 * kNumSMs;
+    long best_cost = -1;
+    int best_c = 128;
+    const int max_m = (K + 127) / 128;
+    for (int m = 1; m <= max_m; ++m) {
+        const int c = 128 * m;
+        const int sp = (K + c - 1) / c;
+        if (sp > 256) continue;
+        const long ctas = (long)B * sp;
+        const long waves = (ctas + slots - 1) / slots;
+        const long cost = waves * (c + 96);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+    }
+    *kc = best_c;
+    *splits = (K + best_c - 1) / best_c;
     if (*splits < 1) *splits = 1;
 }
 

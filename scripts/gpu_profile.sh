@@ -1,8 +1,9 @@
+# ncu --set full captures of the top kernels of the bf16x3 step (one launch each, warm: -s skips the first step's launches)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -k "config1" > gpurun_out/pytest_cfg1.log 2>&1; tail -3 gpurun_out/pytest_cfg1.log
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_fp32.csv python bench.py --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-wc -l gpurun_out/launches_r1_fp32.csv
-ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 40 -c 3 -o gpurun_out/prof_conv_fp32 -f python bench.py --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:nce_gather -s 1 -c 1 -o gpurun_out/prof_nce -f python bench.py --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline > gpurun_out/ncu_nce.log 2>&1
-ls -la gpurun_out
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_fp32.json 2> gpurun_out/bench_r1_fp32.err; cat gpurun_out/bench_r1_fp32.json
+B="python bench.py --steps 1 --warmup 1 --math bf16x3 --skip-e2e --no-cpu-baseline"
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 120 -c 2 -o gpurun_out/r1_conv_tc -f $B > gpurun_out/ncu_conv_tc.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stem_forward_kernel -s 2 -c 1 -o gpurun_out/r1_stem_fwd -f $B > gpurun_out/ncu_stem_fwd.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stem_wgrad_kernel -s 2 -c 1 -o gpurun_out/r1_stem_wgrad -f $B > gpurun_out/ncu_stem_wgrad.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:nce_gather_kernel -s 2 -c 1 -o gpurun_out/r1_nce -f $B > gpurun_out/ncu_nce.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bn_relu_backward_apply -s 90 -c 1 -o gpurun_out/r1_bn_bwd -f $B > gpurun_out/ncu_bn.log 2>&1
+ls -la gpurun_out/*.ncu-rep
