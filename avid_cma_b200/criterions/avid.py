@@ -6,6 +6,7 @@ the ATen chain normalize -> gather -> bmm -> exp/log -> autograd is replaced by 
 `avid_nce_forward_backward` over the gathered bank rows (forward scores, loss terms and the
 gradient w.r.t. the embeddings share the gather), and `update_memory` by `avid_bank_update`.
 """
+import os
 import pprint
 
 import torch
@@ -39,8 +40,21 @@ class _FusedNCE(torch.autograd.Function):
         return g_total * grad_v, g_total * grad_a, None, None
 
 
+def _torch_device(device):
+    return torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+
+
 class AVIDSimilarityMemoryBank(nn.Module):
-    def __init__(self, memory_size, embedding_dim, xModal=True, wModal=False, num_negatives=1024, momentum=0.5, device=0):
+    """Memory banks + fused NCE.  Two distributed layouts:
+
+    replicated (default, the reference's layout): every rank holds both (N,128) banks and update_memory
+        all-gathers (embeddings, y) from all ranks (avid.py:103-129);
+    sharded (AVID_SHARD_BANK=1 or shard=True): rank r holds rows [r*ceil(N/W), (r+1)*ceil(N/W)); per step the
+        queries (embeddings, y) of all ranks are all-gathered once, every rank scores the positives / negatives
+        it holds for all W*B queries, the partial gradients and loss terms are summed with one all-reduce, and
+        each rank updates the rows it owns from the already gathered embeddings."""
+
+    def __init__(self, memory_size, embedding_dim, xModal=True, wModal=False, num_negatives=1024, momentum=0.5, device=0, shard=None):
         super().__init__()
         if embedding_dim != 128:
             raise ValueError('the CUDA criterion kernels are specialised for embedding_dim == 128 (got %d)' % embedding_dim)
@@ -55,41 +69,77 @@ class AVIDSimilarityMemoryBank(nn.Module):
         self.wModal = wModal
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank() if self.distributed else 0
+        self.world = dist.get_world_size() if self.distributed else 1
+        if shard is None:
+            shard = os.environ.get('AVID_SHARD_BANK', '0') == '1'
+        self.sharded = bool(shard) and self.world > 1
+        self.rows_per_rank = (memory_size + self.world - 1) // self.world if self.sharded else memory_size
+        self.row_begin = min(memory_size, self.rank * self.rows_per_rank) if self.sharded else 0
+        self.row_end = min(memory_size, self.row_begin + self.rows_per_rank)
         # counter-based sampler state: (seed, offset) of the Philox stream shared by all ranks' kernels
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._offset = 0
         self._owner = None           # the AVID module (gives access to the NCECriterion and coefficients)
         self._ws = None
+        self._gathered = None        # (emb_v, emb_a, y) of all ranks, kept from the sharded scoring pass for update_memory
         self.init_memory(memory_size, embedding_dim)
+        self._register_load_state_dict_pre_hook(self._slice_full_banks)
 
     # ---- reference API -------------------------------------------------------------------------
     def init_memory(self, num_items, embedding_dim):
-        """avid.py:88-101: N(0,1) rows, L2-normalised, rank 0's copy broadcast to every rank."""
-        dev = torch.device('cuda', self.device) if isinstance(self.device, int) else torch.device(self.device)
+        """avid.py:88-101: N(0,1) rows, L2-normalised, rank 0's copy broadcast to every rank (a sharded rank keeps its rows)."""
+        dev = _torch_device(self.device)
         for name in ('view1_mem', 'view2_mem'):
             mem = torch.randn(num_items, embedding_dim, device=dev)
             ops.rows_l2_normalize_(mem)
+            if self.distributed:
+                dist.broadcast(mem, 0)
+            if self.sharded:
+                mem = mem[self.row_begin:self.row_end].clone()
             self.register_buffer(name, mem)
         if self.distributed:
-            dist.broadcast(self.view1_mem, 0)
-            dist.broadcast(self.view2_mem, 0)
             dist.barrier()
+
+    def _slice_full_banks(self, state_dict, prefix, *args):
+        """A checkpoint holds the full (N,128) banks (reference layout); a sharded rank loads its rows."""
+        if not self.sharded:
+            return
+        for name in ('view1_mem', 'view2_mem', 'positive_set'):
+            key = prefix + name
+            if name != 'positive_set' and key in state_dict and state_dict[key].shape[0] == self.memory_size:
+                state_dict[key] = state_dict[key][self.row_begin:self.row_end]
+
+    def full_banks(self):
+        """(view1_mem, view2_mem) as full (N,128) tensors in the reference's checkpoint layout (all-gathers the shards)."""
+        if not self.sharded:
+            return self.view1_mem, self.view2_mem
+        out = []
+        for mem in (self.view1_mem, self.view2_mem):
+            pad = torch.zeros(self.rows_per_rank, mem.shape[1], dtype=mem.dtype, device=mem.device)
+            pad[:mem.shape[0]] = mem
+            out.append(_gather_from_all(pad)[:self.memory_size])
+        return tuple(out)
 
     def sample_negatives(self, y, K):
         """avid.py:82-86: (B,K) indices uniform over [0,N) minus {y_b}, drawn on the device (Philox4x32-10).
 
         Tests inject the reference's host-drawn indices by replacing this method on the instance."""
-        idx = ops.sample_negatives(y, K, self.memory_size, self._seed, self._offset)
-        self._offset += y.shape[0] * K
+        B = y.shape[0]
+        idx = ops.sample_negatives(y, K, self.memory_size, self._seed, self._offset + self.rank * B * K)
+        self._offset += self.world * B * K
         return idx
 
     def update_memory(self, video_emb, audio_emb, y):
         """avid.py:103-129.  Takes the un-normalised embeddings: the kernel normalises them itself."""
-        if self.distributed:
+        if self._gathered is not None:
+            video_emb, audio_emb, y = self._gathered
+            self._gathered = None
+        elif self.distributed:
             video_emb = _gather_from_all(video_emb)
             audio_emb = _gather_from_all(audio_emb)
             y = _gather_from_all(y)
-        ops.bank_update(self.view1_mem, self.view2_mem, video_emb, audio_emb, y, float(self.momentum[0]), float(self.momentum[1]))
+        ops.bank_update(self.view1_mem, self.view2_mem, video_emb, audio_emb, y, float(self.momentum[0]), float(self.momentum[1]),
+                        row_begin=self.row_begin, row_end=self.row_end)
 
     # ---- fused path ----------------------------------------------------------------------------
     def keys(self):
@@ -109,28 +159,40 @@ class AVIDSimilarityMemoryBank(nn.Module):
         return 'sample_negatives' in self.__dict__
 
     def _draw(self, y):
-        """Returns (neg_idx or None, seed, offset): None means 'draw inside the kernel'."""
+        """Returns (neg_idx or None, seed, offset): None means 'draw inside the kernel'.  The Philox counter of query b of
+        rank r in step s is offset_s + (r*B + b)*K + k, i.e. the gathered batch of a sharded step draws exactly the
+        negatives the ranks of a replicated step draw."""
         K = int(self.num_negatives)
         if self._sampler_overridden():
             return self.sample_negatives(y, K).to(device=y.device, dtype=torch.int64).contiguous(), 0, 0
         off = self._offset
-        self._offset += y.shape[0] * K
+        self._offset += self.world * y.shape[0] * K
         return None, self._seed, off
 
-    def _run_fused(self, emb_v, emb_a, y):
-        owner = self._owner
-        crit = owner.criterion
+    def _key_tuples(self):
         keys = self.keys()
-        weights = owner._key_weights([k[0] for k in keys])
-        key_tuples = [(k[1], k[2], k[3], k[4], w) for k, w in zip(keys, weights)]
+        weights = self._owner._key_weights([k[0] for k in keys])
+        return keys, [(k[1], k[2], k[3], k[4], w) for k, w in zip(keys, weights)]
+
+    def _workspace(self, B, K, pos_k, nkeys, device):
+        if self._ws is None or self._ws_shape != (B, K, pos_k, nkeys):
+            self._ws = ops.nce_workspace(B, K, pos_k, nkeys, device)
+            self._ws_shape = (B, K, pos_k, nkeys)
+        return self._ws
+
+    def _run_fused(self, emb_v, emb_a, y):
+        y = y.to(device=emb_v.device, dtype=torch.int64).contiguous()
+        if self.sharded:
+            return self._run_sharded(emb_v, emb_a, y)
+        crit = self._owner.criterion
+        keys, key_tuples = self._key_tuples()
         B, K = emb_v.shape[0], int(self.num_negatives)
         pos = self._positive_set()
         pos_k = pos.shape[1] if pos is not None else 0
-        if self._ws is None or self._ws_shape != (B, K, pos_k, len(keys)):
-            self._ws = ops.nce_workspace(B, K, pos_k, len(keys), emb_v.device)
-            self._ws_shape = (B, K, pos_k, len(keys))
-        y = y.to(device=emb_v.device, dtype=torch.int64).contiguous()
+        ws = self._workspace(B, K, pos_k, len(keys), emb_v.device)
         neg_idx, seed, offset = self._draw(y)
+        if neg_idx is None:
+            offset += self.rank * B * K
         out = torch.empty(1 + len(keys) + 2 * B * 128, dtype=torch.float32, device=emb_v.device)
         loss_total, loss_keys = out[0:1], out[1:1 + len(keys)]
         grad_v = out[1 + len(keys):1 + len(keys) + B * 128].view(B, 128)
@@ -142,13 +204,60 @@ class AVIDSimilarityMemoryBank(nn.Module):
             # nce.py:21-36: Z <- mean exp(score) over the negatives of the first key of the first batch
             # (mean of the per-rank means when distributed), frozen afterwards.
             z = torch.empty(1, dtype=torch.float32, device=emb_v.device)
-            ops.nce_partition_mean(args, 0, z, self._ws)
+            ops.nce_partition_mean(args, 0, z, ws)
             if self.distributed:
                 dist.all_reduce(z)
                 z /= dist.get_world_size()
             crit.avg_exp_score.copy_(z.reshape(()))
             crit.mark_ready()
-        ops.nce_forward_backward(args, self._ws)
+        ops.nce_forward_backward(args, ws)
+        return loss_total.reshape(()), loss_keys, grad_v, grad_a
+
+    def _run_sharded(self, emb_v, emb_a, y):
+        """One step of the row-partitioned protocol: gather queries -> score owned rows -> all-reduce partials
+        -> finalize own queries.  Scores / gradients cross NVLink (4 B per negative), bank rows (512 B) never do."""
+        crit = self._owner.criterion
+        keys, key_tuples = self._key_tuples()
+        W, B, K, nk = self.world, emb_v.shape[0], int(self.num_negatives), len(keys)
+        dev = emb_v.device
+        pos = self._positive_set()
+        pos_k = pos.shape[1] if pos is not None else 0
+        neg_idx, seed, offset = self._draw(y)
+        # (1) queries of all ranks, rank-major (these are also what update_memory needs: avid.py:109-111)
+        all_v, all_a, all_y = _gather_from_all(emb_v), _gather_from_all(emb_a), _gather_from_all(y)
+        all_neg = _gather_from_all(neg_idx) if neg_idx is not None else None
+        self._gathered = (all_v, all_a, all_y)
+        ws = self._workspace(W * B, K, pos_k, nk, dev)
+        # (2) partial dL/d(normalised embedding) and per-query loss terms over the rows this rank holds
+        part = torch.zeros(2 * W * B * 128 + nk * W * B, dtype=torch.float32, device=dev)
+        gh_v, gh_a = part[:W * B * 128].view(W * B, 128), part[W * B * 128:2 * W * B * 128].view(W * B, 128)
+        loss_part = part[2 * W * B * 128:].view(nk, W * B)
+        args = ops.make_nce_args(all_v, all_a, all_y, self.view1_mem, self.view2_mem, key_tuples, K, crit.avg_exp_score,
+                                 num_rows=self.memory_size, row_begin=self.row_begin, row_end=self.row_end, neg_idx=all_neg, seed=seed,
+                                 offset=offset, positive_set=pos, mean_batch=B, temperature=self.temperature,
+                                 grad_hat_v=gh_v, grad_hat_a=gh_a, loss_part=loss_part)
+        if not crit.z_ready():
+            # the sharded partition pass returns the SUM of exp(score) over held rows; equal batches make the mean over all
+            # W*B*K negatives equal to the reference's mean of per-rank means (nce.py:27-33)
+            z = torch.empty(1, dtype=torch.float32, device=dev)
+            ops.nce_partition_mean(args, 0, z, ws)
+            dist.all_reduce(z)
+            z /= float(W * B * keys[0][4])
+            crit.avg_exp_score.copy_(z.reshape(()))
+            crit.mark_ready()
+        ops.nce_forward_backward(args, ws)
+        # (3) sum the partials over the shards
+        dist.all_reduce(part)
+        # (4) backward of F.normalize, batch means and coefficient mix for this rank's own queries
+        out = torch.empty(1 + nk + 2 * B * 128, dtype=torch.float32, device=dev)
+        loss_total, loss_keys = out[0:1], out[1:1 + nk]
+        grad_v, grad_a = out[1 + nk:1 + nk + B * 128].view(B, 128), out[1 + nk + B * 128:].view(B, 128)
+        lo, hi = self.rank * B, (self.rank + 1) * B
+        fin = ops.make_nce_args(emb_v, emb_a, y, self.view1_mem, self.view2_mem, key_tuples, K, crit.avg_exp_score,
+                                num_rows=self.memory_size, row_begin=self.row_begin, row_end=self.row_end, mean_batch=B,
+                                temperature=self.temperature, loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a,
+                                grad_hat_v=gh_v[lo:hi], grad_hat_a=gh_a[lo:hi], loss_part=loss_part[:, lo:hi].contiguous())
+        ops.nce_finalize(fin, ws)
         return loss_total.reshape(()), loss_keys, grad_v, grad_a
 
     def forward(self, video_emb, audio_emb, y):
@@ -190,12 +299,12 @@ class AVID(nn.Module):
         super().__init__()
         self.nce_average = AVIDSimilarityMemoryBank(memory_size=num_data, embedding_dim=embedding_dim, num_negatives=num_negatives,
                                                     momentum=momentum, xModal=xModal_coeff > 0., wModal=wModal_coeff > 0., device=device)
-        self.nce_average = self.nce_average.cuda(device)
+        self.nce_average = self.nce_average.to(_torch_device(device))
         object.__setattr__(self.nce_average, '_owner', self)
         sum_coeff = xModal_coeff + wModal_coeff
         self.xModal_coeff = xModal_coeff / sum_coeff
         self.wModal_coeff = wModal_coeff / sum_coeff
-        self.criterion = NCECriterion(num_data).cuda(device)
+        self.criterion = NCECriterion(num_data).to(_torch_device(device))
         if checkpoint is not None:
             _restore_bank_and_partition(self, checkpoint)
 

@@ -11,7 +11,7 @@ from torch import nn
 import torch.distributed as dist
 
 from .. import ops
-from .avid import AVIDSimilarityMemoryBank, _COMBO, _restore_bank_and_partition
+from .avid import AVIDSimilarityMemoryBank, _COMBO, _restore_bank_and_partition, _torch_device
 from .nce import NCECriterion
 
 __all__ = ['AVID_CMA']
@@ -54,31 +54,58 @@ class AVIDSimilarityPositiveExpansion(AVIDSimilarityMemoryBank):
             _, neg = self.memory_sampling(y)
             return neg.to(device=y.device, dtype=torch.int64).contiguous(), 0, 0
         off = self._offset
-        self._offset += y.shape[0] * int(self.num_negatives)
+        self._offset += self.world * y.shape[0] * int(self.num_negatives)
         return None, self._seed, off
 
     def memory_sampling(self, y):
         """avid_cma.py:196-209: (positive indices (B,pos_k) int64, negative indices (B,K) int64 that avoid them)."""
+        B, K = y.shape[0], int(self.num_negatives)
         pos = self.positive_set[y].long()
-        neg = ops.sample_negatives(y, int(self.num_negatives), self.memory_size, self._seed, self._offset, self.positive_set)
-        self._offset += y.shape[0] * int(self.num_negatives)
+        neg = ops.sample_negatives(y, K, self.memory_size, self._seed, self._offset + self.rank * B * K, self.positive_set)
+        self._offset += self.world * B * K
         return pos, neg
 
+    def _candidate_shards(self):
+        """(video rows, audio rows, first row) of every bank shard in turn; a sharded run streams the other ranks' rows
+        through one broadcast buffer, so no rank ever holds more than its own shard plus one visiting shard."""
+        if not self.sharded:
+            yield self.view1_mem, self.view2_mem, 0
+            return
+        N, per = self.memory_size, self.rows_per_rank
+        for r in range(self.world):
+            lo, hi = min(N, r * per), min(N, (r + 1) * per)
+            if hi <= lo:
+                continue
+            if r == self.rank:
+                cv, ca = self.view1_mem, self.view2_mem
+            else:
+                cv = torch.empty(hi - lo, 128, dtype=torch.float32, device=self.view1_mem.device)
+                ca = torch.empty_like(cv)
+            dist.broadcast(cv, r)
+            dist.broadcast(ca, r)
+            yield cv, ca, lo
+
     def find_correspondences(self):
-        """avid_cma.py:211-229."""
+        """avid_cma.py:211-229: every rank mines the positives of N/W queries against all N candidates; the slices are
+        all-gathered (the reference mines everything on rank 0 and broadcasts)."""
         pos_k = self.sampling_args['pos_k']
         if pos_k <= 0:
             return
-        N = self.view1_mem.shape[0]
-        world = dist.get_world_size() if self.distributed else 1
+        N = self.memory_size
+        world = self.world
         per = (N + world - 1) // world
         lo, hi = min(N, self.rank * per), min(N, (self.rank + 1) * per)
-        mine = torch.zeros(per, pos_k, dtype=torch.int32, device=self.view1_mem.device)
-        if hi > lo:
-            mine[:hi - lo] = ops.cma_topk(self.view1_mem[lo:hi], self.view2_mem[lo:hi], [(self.view1_mem, self.view2_mem, 0)],
-                                          pos_k, self.sampling_args['type'])
+        dev = self.view1_mem.device
+        mine = torch.zeros(per, pos_k, dtype=torch.int32, device=dev)
+        if self.sharded:
+            qv, qa = self.view1_mem, self.view2_mem          # the rows this rank owns are its queries
+        else:
+            qv, qa = self.view1_mem[lo:hi], self.view2_mem[lo:hi]
+        if hi > lo or self.sharded:
+            res = ops.cma_topk(qv, qa, self._candidate_shards(), pos_k, self.sampling_args['type'])
+            mine[:hi - lo] = res
         if self.distributed:
-            full = torch.empty(world * per, pos_k, dtype=torch.int32, device=mine.device)
+            full = torch.empty(world * per, pos_k, dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(full, mine)
             positive_set = full[:N].contiguous()
         else:
@@ -97,14 +124,14 @@ class AVID_CMA(nn.Module):
             memory_size=num_data, embedding_dim=embedding_dim, num_negatives=num_negatives, num_negatives_within=num_negatives_within,
             momentum=momentum, xModalInst=xModalInstCoeff > 0., xModalPos=xModalPosCoeff > 0., wModalInst=wModalInstCoeff > 0.,
             wModalPos=wModalPosCoeff > 0., sampling_args=sampling_args, device=device)
-        self.nce_average = self.nce_average.cuda(device)
+        self.nce_average = self.nce_average.to(_torch_device(device))
         object.__setattr__(self.nce_average, '_owner', self)
         sum_coeff = xModalInstCoeff + wModalInstCoeff + xModalPosCoeff + wModalPosCoeff
         self.xModalInstCoeff = xModalInstCoeff / sum_coeff
         self.wModalInstCoeff = wModalInstCoeff / sum_coeff
         self.xModalPosCoeff = xModalPosCoeff / sum_coeff
         self.wModalPosCoeff = wModalPosCoeff / sum_coeff
-        self.criterion = NCECriterion(num_data).cuda(device)
+        self.criterion = NCECriterion(num_data).to(_torch_device(device))
         if checkpoint is not None:
             _restore_bank_and_partition(self, checkpoint)
         self.resample_freq = resample_freq

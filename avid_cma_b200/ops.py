@@ -117,8 +117,9 @@ def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows
     a.grad_hat_video, a.grad_hat_audio = _p(grad_hat_v, optional=True), _p(grad_hat_a, optional=True)
     a.loss_part = _p(loss_part, optional=True)
     # the struct only carries raw pointers: keep the tensors alive as long as the args object
-    a._keepalive = (emb_v, emb_a, y, bank_v, bank_a, neg_idx, positive_set, Z, loss_keys, loss_total, grad_v, grad_a, scores,
-                    neg_idx_out, grad_hat_v, grad_hat_a, loss_part)
+    a.tensors = dict(emb_v=emb_v, emb_a=emb_a, y=y, bank_v=bank_v, bank_a=bank_a, neg_idx=neg_idx, positive_set=positive_set, Z=Z,
+                     loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a, scores=scores, neg_idx_out=neg_idx_out,
+                     grad_hat_v=grad_hat_v, grad_hat_a=grad_hat_a, loss_part=loss_part)
     return a
 
 

@@ -41,10 +41,12 @@ def parse():
     ap.add_argument("--spec", type=int, nargs=2, default=[200, 257])
     ap.add_argument("--bank", type=int, default=BANK_ROWS)
     ap.add_argument("--negatives", type=int, default=NUM_NEG)
-    ap.add_argument("--math", default=os.environ.get("AVID_MATH", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--math", default=os.environ.get("AVID_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end timed region")
+    ap.add_argument("--bank-mode", default="auto", choices=["auto", "replicated", "sharded"],
+                    help="memory-bank layout for N > 1: sharded = row-partitioned over the ranks (default), replicated = the reference's")
     return ap.parse_args()
 
 
@@ -52,7 +54,7 @@ def config_of(a, n_gpus):
     return {"workload": "Cross-N1024 AVID, 240k-entry memory bank (Kinetics-shape), batch=64/GPU 8x3x224x224 + 1x200x257",
             "global_batch": a.batch * n_gpus, "batch_per_gpu": a.batch, "clip": [3, a.frames, a.size, a.size], "spectrogram": [1] + list(a.spec),
             "bank_rows": a.bank, "num_negatives": a.negatives, "optimizer": "adam lr 2e-4 wd 1e-5",
-            "parallelism": f"dp{n_gpus}", "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
+            "parallelism": f"dp{n_gpus}", "bank_layout": "single" if n_gpus == 1 else ("replicated" if a.bank_mode == "replicated" else "row-sharded"), "math": a.math, "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -137,6 +139,7 @@ def run_ours(a):
 
     torch.manual_seed(0)
     model = models.av_wrapper('R2Plus1D', {'depth': 18}, 'Conv2D', {'depth': 10}, proj_dim=[512, 512, 128]).to(dev).train()
+    os.environ["AVID_SHARD_BANK"] = "0" if a.bank_mode == "replicated" else "1"
     crit = AVID(num_data=a.bank, embedding_dim=model.out_dim, num_negatives=a.negatives, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=local)
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
     opt = optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
