@@ -98,24 +98,35 @@ __device__ __forceinline__ void store_planes(__nv_bfloat16* hi, __nv_bfloat16* l
     if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
 }
 
+// Elementwise kernels: one float4 of channels per thread per iteration.  c4 (a power of two <= 256) divides the grid stride
+// (gridDim.x * 256), so a thread sees the SAME four channels in every iteration: their constants live in registers.
 __global__ void __launch_bounds__(256) bn_relu_forward_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, float* __restrict__ y,
                                                               __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
                                                               int64_t n4, int c4) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c4);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cc);
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cc);
-        float4 o;
-        o.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
-        o.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-        o.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
-        o.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
-        if (y) reinterpret_cast<float4*>(y)[i] = o;
-        if (y_hi) {
-            const float f[4] = {o.x, o.y, o.z, o.w};
-            store_planes(y_hi, y_lo, i, f);
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int cc = (int)(i0 % c4);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cc);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cc);
+    for (int64_t i = i0; i < n4; i += 2 * stride) {
+        const bool two = i + stride < n4;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 v1 = two ? __ldg(reinterpret_cast<const float4*>(x) + i + stride) : v0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const float4 v = u ? v1 : v0;
+            const int64_t k = i + u * stride;
+            float4 o;
+            o.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+            o.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+            o.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+            o.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+            if (y) reinterpret_cast<float4*>(y)[k] = o;
+            if (y_hi) {
+                const float f[4] = {o.x, o.y, o.z, o.w};
+                store_planes(y_hi, y_lo, k, f);
+            }
         }
     }
 }
@@ -134,23 +145,40 @@ __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float
             if (dbeta) dbeta[ch] = (float)sums[ch];
             if (dgamma) dgamma[ch] = (float)sums[c + ch];
         }
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c4);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + i);
-        const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
-        float o[4];
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int cc = (int)(i0 % c4);
+    // dx = k * (g - sg - xh * sgx),  xh = (x - mu) * is,  g = dy * [xh * ga + be > 0]
+    float mu[4], is[4], ga[4], be[4], kk[4], sg[4], sgx[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ch = cc * 4 + j;
-            const float is = invstd[ch], ga = gamma[ch];
-            const float xh = (xv[j] - mean[ch]) * is;
-            const float g = (xh * ga + beta[ch]) > 0.f ? dv[j] : 0.f;
-            const float sg = (float)sums[ch] * inv_n, sgx = (float)sums[c + ch] * inv_n;
-            o[j] = ga * is * (g - sg - xh * sgx);
+    for (int j = 0; j < 4; ++j) {
+        const int ch = cc * 4 + j;
+        mu[j] = mean[ch];  is[j] = invstd[ch];  ga[j] = gamma[ch];  be[j] = beta[ch];
+        kk[j] = ga[j] * is[j];
+        sg[j] = (float)sums[ch] * inv_n;
+        sgx[j] = (float)sums[c + ch] * inv_n;
+    }
+    for (int64_t i = i0; i < n4; i += 2 * stride) {
+        const bool two = i + stride < n4;
+        const float4 va = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 da = __ldg(reinterpret_cast<const float4*>(dy) + i);
+        const float4 vb = two ? __ldg(reinterpret_cast<const float4*>(x) + i + stride) : va;
+        const float4 db = two ? __ldg(reinterpret_cast<const float4*>(dy) + i + stride) : da;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const float4 v = u ? vb : va, d = u ? db : da;
+            const int64_t k = i + u * stride;
+            const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (xv[j] - mu[j]) * is[j];
+                const float g = (xh * ga[j] + be[j]) > 0.f ? dv[j] : 0.f;
+                o[j] = kk[j] * (g - sg[j] - xh * sgx[j]);
+            }
+            if (dx) reinterpret_cast<float4*>(dx)[k] = make_float4(o[0], o[1], o[2], o[3]);
+            if (dx_hi) store_planes(dx_hi, dx_lo, k, o);
         }
-        if (dx) reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
-        if (dx_hi) store_planes(dx_hi, dx_lo, i, o);
     }
 }
 

@@ -55,7 +55,7 @@ class R2Plus1D(TowerMixin, nn.Module):
             op = StemOp(self.conv1[0], x.shape, math)
             ya, s_stem = ConvBNReLU.forward(op.pack(x), self.conv1[0], self.conv1[1], training, math, out_f32=True, op=op, out_planes=False)
         y = ya.f32
-        p = ops.maxpool_1x3x3_forward(y)
+        p, pool_argmax = ops.maxpool_1x3x3_forward(y)
         if taps is not None:
             taps['conv1'] = p
         saved_blocks = []
@@ -67,12 +67,12 @@ class R2Plus1D(TowerMixin, nn.Module):
             if taps is not None:
                 taps[name] = h.f32
         pooled, argmax = ops.global_maxpool_forward(h.f32)
-        return pooled, (s_stem, y, p, saved_blocks, argmax, tuple(h.shape))
+        return pooled, (s_stem, tuple(y.shape), pool_argmax, saved_blocks, argmax, tuple(h.shape))
 
     def _bwd(self, dpooled, saved, grads, math):
-        s_stem, y, p, saved_blocks, argmax, hshape = saved
+        s_stem, yshape, pool_argmax, saved_blocks, argmax, hshape = saved
         d = ops.global_maxpool_backward(dpooled, argmax, hshape)
         for blk, sb in reversed(saved_blocks):
             d = blk._bwd(d, sb, grads)
-        dy = ops.maxpool_1x3x3_backward(y, p, d)
+        dy = ops.maxpool_1x3x3_backward(pool_argmax, d, yshape)
         ConvBNReLU.backward(dy, s_stem, grads, need_dx=False)

@@ -421,19 +421,20 @@ def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=No
     return Act(dx if want_f32 else None, hi, lo), dgamma, dbeta
 
 
-def maxpool_1x3x3_forward(x):
-    """x (n, t, h, w, c) -> (n, t, ho, wo, c)."""
+def maxpool_1x3x3_forward(x, need_argmax=True):
+    """x (n, t, h, w, c) -> (y (n, t, ho, wo, c), argmax uint8 (n, t, ho, wo, c) or None)."""
     n, t, h, w, c = x.shape
     ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
     y = torch.empty(n, t, ho, wo, c, dtype=torch.float32, device=x.device)
-    check(_lib.lib().avid_maxpool_1x3x3_forward(_p(x), _p(y), n * t, h, w, c, ho, wo, _stream()))
-    return y
+    am = torch.empty(n, t, ho, wo, c, dtype=torch.uint8, device=x.device) if need_argmax else None
+    check(_lib.lib().avid_maxpool_1x3x3_forward(_p(x), _p(y), _p(am, torch.uint8, optional=True), n * t, h, w, c, ho, wo, _stream()))
+    return y, am
 
 
-def maxpool_1x3x3_backward(x, y, dy):
-    n, t, h, w, c = x.shape
-    dx = torch.zeros_like(x)
-    check(_lib.lib().avid_maxpool_1x3x3_backward(_p(x), _p(y), _p(dy), _p(dx), n * t, h, w, c, y.shape[2], y.shape[3], _stream()))
+def maxpool_1x3x3_backward(argmax, dy, in_shape):
+    n, t, h, w, c = in_shape
+    dx = torch.empty(in_shape, dtype=torch.float32, device=dy.device)
+    check(_lib.lib().avid_maxpool_1x3x3_backward(_p(argmax, torch.uint8), _p(dy), _p(dx), n * t, h, w, c, argmax.shape[2], argmax.shape[3], _stream()))
     return dx
 
 

@@ -262,11 +262,12 @@ int avid_bn_relu_backward_apply_ex(const float* x, const float* dy, const float*
                                    const float* gamma, const float* beta, const double* sums,
                                    int64_t rows, int32_t c, float* dx, void* dx_hi, void* dx_lo, float* dgamma, float* dbeta, void* stream);
 
-/* nn.MaxPool3d((1,3,3), stride (1,2,2), padding (0,1,1)) on [n*t, h, w, c] (video.py:23) */
-int avid_maxpool_1x3x3_forward(const float* x, float* y, int32_t nt, int32_t h, int32_t w, int32_t c,
+/* nn.MaxPool3d((1,3,3), stride (1,2,2), padding (0,1,1)) on [n*t, h, w, c] (video.py:23).  argmax (optional, one byte per
+ * output element) records the winning window position dh*3+dw -- the first maximum in scan order, like ATen. */
+int avid_maxpool_1x3x3_forward(const float* x, float* y, uint8_t* argmax, int32_t nt, int32_t h, int32_t w, int32_t c,
                                int32_t ho, int32_t wo, void* stream);
-/* dx zeroed by caller; routes dy to the first maximal element of each window (atomic add) */
-int avid_maxpool_1x3x3_backward(const float* x, const float* y, const float* dy, float* dx,
+/* routes dy to the recorded argmax of each window; gather form: every dx element is written exactly once, x is not read */
+int avid_maxpool_1x3x3_backward(const uint8_t* argmax, const float* dy, float* dx,
                                 int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream);
 
 /* nn.AdaptiveMaxPool{2d,3d}(1) (video.py:41, audio.py:31): x [n, thw, c] -> y [n, c], argmax [n, c] */

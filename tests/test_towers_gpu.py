@@ -117,10 +117,18 @@ def test_pools_forward_backward():
     dy = torch.randn(ref.shape, generator=g)
     ref.backward(dy.double())
     xc = ops.nchw_to_nhwc(x.to(DEV))
-    y = ops.maxpool_1x3x3_forward(xc)
+    y, amax = ops.maxpool_1x3x3_forward(xc)
     _close(ops.nhwc_to_nchw(y), ref, 0, 0)
-    dx = ops.maxpool_1x3x3_backward(xc, y, ops.nchw_to_nhwc(dy.to(DEV)))
+    dx = ops.maxpool_1x3x3_backward(amax, ops.nchw_to_nhwc(dy.to(DEV)), xc.shape)
     _close(ops.nhwc_to_nchw(dx), xd.grad, 1e-6, 1e-6)
+    # ties: after ReLU half the inputs are exact zeros; the gradient must go to the FIRST maximum of a window, like ATen
+    xr = torch.relu(x).double().requires_grad_(True)
+    refr = F.max_pool3d(xr, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    refr.backward(dy.double())
+    yr, amr = ops.maxpool_1x3x3_forward(ops.nchw_to_nhwc(torch.relu(x).to(DEV)))
+    dxr = ops.maxpool_1x3x3_backward(amr, ops.nchw_to_nhwc(dy.to(DEV)), xc.shape)
+    _close(ops.nhwc_to_nchw(yr), refr, 0, 0)
+    _close(ops.nhwc_to_nchw(dxr), xr.grad, 1e-6, 1e-6)
     xd2 = x.double().requires_grad_(True)
     ref2 = F.adaptive_max_pool3d(xd2, 1).flatten(1)
     dy2 = torch.randn(ref2.shape, generator=g)
