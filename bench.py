@@ -32,7 +32,7 @@ STEP_GFLOP_PER_CLIP = 75.66
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--bank", type=int, default=BANK_ROWS)
     ap.add_argument("--negatives", type=int, default=NUM_NEG)
     ap.add_argument("--math", default=os.environ.get("AVID_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end timed region")
     ap.add_argument("--bank-mode", default="auto", choices=["auto", "replicated", "sharded"],
@@ -235,7 +235,8 @@ def run_ours(a):
         return
 
     clips = B * world * a.steps
-    # roofline of the dominant kernel family, from CUDA events recorded around every launch of the timed region
+    # roofline of the dominant kernel, from CUDA events recorded around every launch of the timed region.  Families are the
+    # instrumented entry points of ops.py; conv_forward_tc and conv_dgrad_tc are the same kernel (conv_tc_kernel) and are merged.
     fam = {}
     for name, work, dur in prof:
         f = fam.setdefault(name, [0.0, 0.0, 0])
@@ -251,13 +252,43 @@ def run_ours(a):
         rate = work / (dur * 1e-3) if dur > 0 else 0.0
         families[name] = {"launches": cnt, "ms_per_step": dur / a.steps, "share_of_step": dur / ms}
         families[name]["GB/s" if name.startswith("nce") else "TFLOP/s"] = rate / (1e9 if name.startswith("nce") else 1e12)
-    if fam:
-        top = max((n for n in fam if n.startswith(("conv", "stem"))), key=lambda n: fam[n][1])
-        work, dur, cnt = fam[top]
+    kernels = {}
+    for name, (work, dur, cnt) in fam.items():
+        kname = {"conv_forward_tc": "conv_tc_kernel", "conv_dgrad_tc": "conv_tc_kernel", "conv_wgrad_tc": "wgrad_tc_kernel",
+                 "stem_forward_tc": "stem_forward_kernel", "stem_wgrad_tc": "stem_wgrad_kernel", "conv_forward": "conv_igemm_kernel",
+                 "conv_dgrad": "conv_igemm_kernel", "conv_wgrad": "conv_wgrad_kernel"}.get(name)
+        if kname:
+            k = kernels.setdefault(kname, [0.0, 0.0, 0])
+            k[0] += work; k[1] += dur; k[2] += cnt
+    if kernels:
+        top = max(kernels, key=lambda n: kernels[n][1])
+        work, dur, cnt = kernels[top]
         ach = work / (dur * 1e-3) / 1e12
+        mma_factor = 3 if a.math == "bf16x3" and top != "conv_igemm_kernel" else 1
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of this kernel from the committed ncu pass of the same command (profiles/)
+            prof_k = json.load(open(os.path.join(ROOT, "profiles", "r1_%s_kernels.json" % a.math)))["kernels"]
+            rows = [r for r in prof_k if top in r["kernel"]]
+            n_l = sum(r["launches_per_step"] for r in rows)
+            traffic = sum((r["dram_read_MB_per_launch"] + r["dram_write_MB_per_launch"]) * 1e6 * r["launches_per_step"] for r in rows) / n_l
+            traffic_src = "profiles/r1_%s_kernels.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)" % a.math
+        except Exception:
+            pass
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
-                    "launches_timed": cnt, "avg_launch_ms": dur / cnt, "families": families}
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else "fallback",
+                    "launches_timed": cnt, "avg_launch_ms": dur / cnt, "share_of_step": dur / ms,
+                    "algorithmic_flops_per_launch": work / cnt,
+                    "executed_mma_factor": mma_factor, "executed_frac": ach * mma_factor / tensor_peak,
+                    "note": "achieved counts each product once (2*MAC of the convolution); bf16x3 issues 3 bf16 MMAs per product, so the "
+                            "tensor pipe executes executed_mma_factor x that",
+                    "families": families}
+        if "nce_fused" in fam:
+            w_, d_, c_ = fam["nce_fused"]
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            roofline["nce"] = {"kernel": "nce_gather_kernel + nce_reduce_finalize_kernel", "bound": "hbm", "achieved": w_ / (d_ * 1e-3) / 1e9,
+                               "peak": hbm, "unit": "GB/s", "frac": w_ / (d_ * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_launch": w_ / c_,
+                               "sweep": "profiles/r1_nce_sweep.json (K = 256..16384: 0.09 .. 0.77 of measured HBM)"}
 
     line = {"metric": METRIC, "value": clips / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -267,7 +298,7 @@ def run_ours(a):
             "gpu_launches": launches, "roofline": roofline, "last_loss": last_loss,
             "step_tflops": clips * STEP_GFLOP_PER_CLIP * 1e9 / (ms * 1e-3) / 1e12 / world}
     if world == 1 and not a.no_cpu_baseline:
-        cb, _ = cpu_reference(a, 2, 1, a.cpu_sample_batch)
+        cb, _ = cpu_reference(a, 6, 1, a.cpu_sample_batch)
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     if world > 1:
