@@ -108,3 +108,66 @@ def test_stem_tc_forward_and_wgrad(case, x3):
     dw_tap = ops.stem_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo)
     dw = ops.filter_from_tapmajor(dw_tap, wt.to(DEV))
     assert _rel(dw, wd.grad) < tol
+
+
+# BASELINE config-2 layer geometries at full resolution (batch reduced to keep the fp64 checks cheap); checked through
+# size-independent properties: the adjoint identities <conv(x), d> = <x, dgrad(d)> = <w, wgrad(x, d)> and a spot check of
+# random output pixels against a direct fp64 evaluation of the convolution sum.
+FULL_CASES = [
+    (8, 64, 64, (8, 56, 56), (1, 3, 3), (1, 1, 1), (0, 1, 1)),       # conv2x spatial
+    (8, 64, 64, (8, 56, 56), (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # conv2x temporal
+    (8, 64, 128, (8, 56, 56), (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # conv3x entry, strided
+    (8, 128, 128, (8, 28, 28), (3, 1, 1), (2, 1, 1), (1, 0, 0)),     # conv3x strided temporal
+    (4, 3, 64, (8, 224, 224), (3, 7, 7), (1, 2, 2), (1, 3, 3)),      # video stem
+    (8, 1, 64, (1, 200, 257), (1, 7, 7), (1, 2, 2), (0, 3, 3)),      # audio stem
+]
+
+
+def _spot_check(x, wt, out_nchw, k, s, p, gen, points=256):
+    n, ci, t, h, w = x.shape
+    co = wt.shape[0]
+    _, _, to, ho, wo = out_nchw.shape
+    xp = F.pad(x.double(), (p[2], p[2], p[1], p[1], p[0], p[0]))
+    idx = torch.stack([torch.randint(0, m, (points,), generator=gen) for m in (n, to, ho, wo)], 1)
+    worst = 0.0
+    for ni, ti, hi, wi in idx.tolist():
+        patch = xp[ni, :, ti * s[0]:ti * s[0] + k[0], hi * s[1]:hi * s[1] + k[1], wi * s[2]:wi * s[2] + k[2]]
+        ref = (wt.double() * patch.unsqueeze(0)).sum((1, 2, 3, 4))
+        got = out_nchw[ni, :, ti, hi, wi].double().cpu()
+        worst = max(worst, float((got - ref).norm() / ref.norm().clamp_min(1e-30)))
+    return worst
+
+
+@pytest.mark.parametrize("case", FULL_CASES, ids=[f"f{i}" for i in range(len(FULL_CASES))])
+def test_conv_tc_full_resolution_properties(case):
+    from avid_cma_b200 import ops
+    n, ci, co, (t, h, w), k, s, p = case
+    g = torch.Generator().manual_seed(1000 + ci + co)
+    x = torch.randn(n, ci, t, h, w, generator=g)
+    wt = torch.randn(co, ci, *k, generator=g) / (ci * k[0] * k[1] * k[2]) ** 0.5
+    shape = ops.conv_shape(n, t, h, w, ci, co, k, s, p)
+    dout = torch.randn(n, co, shape.to, shape.ho, shape.wo, generator=g)
+    dc = ops.nchw_to_nhwc(dout.to(DEV))
+    d_hi, d_lo = ops.split_bf16(dc)
+    stem = ci < 64
+    if stem:
+        x_hi, x_lo = ops.stem_pack(x.to(DEV), 2 * shape.wo + 8, p[2])
+        w_hi, w_lo = ops.stem_filter_pack(wt.to(DEV))
+        out = ops.stem_forward_tc(shape, x_hi, x_lo, w_hi, w_lo)
+        dw = ops.filter_from_tapmajor(ops.stem_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo), wt.to(DEV))
+    else:
+        xc = ops.nchw_to_nhwc(x.to(DEV))
+        w_tap, w_tap_t = ops.filter_to_tapmajor(wt.to(DEV))
+        x_hi, x_lo = ops.split_bf16(xc)
+        wf_hi, wf_lo = ops.split_bf16(w_tap_t)
+        wd_hi, wd_lo = ops.split_bf16(w_tap)
+        out = ops.conv_forward_tc(shape, x_hi, x_lo, wf_hi, wf_lo)
+        dw = ops.filter_from_tapmajor(ops.conv_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo), wt.to(DEV))
+        din = ops.conv_dgrad_tc(shape, d_hi, d_lo, wd_hi, wd_lo)
+    out_nchw = ops.nhwc_to_nchw(out)
+    assert _spot_check(x, wt, out_nchw, k, s, p, g) < 3e-5
+    lhs = float((out.double() * dc.double()).sum())                         # <conv(x), d>
+    scale = float(out.double().norm() * dc.double().norm())
+    assert abs(lhs - float((dw.double() * wt.to(DEV).double()).sum())) < 2e-5 * scale    # = <w, wgrad(x, d)>
+    if not stem:
+        assert abs(lhs - float((ops.nhwc_to_nchw(din).double() * x.to(DEV).double()).sum())) < 2e-5 * scale   # = <x, dgrad(d)>
