@@ -61,12 +61,12 @@ _SIGNATURES = {
     "avid_conv_dgrad": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _I, _P]),
     "avid_conv_wgrad": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _I, _P]),
     "avid_split_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
-    "avid_conv_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P]),
+    "avid_conv_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P, _P]),
     "avid_conv_dgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P]),
     "avid_conv_wgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P]),
     "avid_stem_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "avid_stem_filter_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "avid_stem_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _I, _P, _P, _P, _P]),
+    "avid_stem_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _I, _P, _P, _P, _P, _P]),
     "avid_stem_wgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _I, _P, _P, _P, _P]),
     "avid_filter_to_tapmajor": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "avid_filter_from_tapmajor": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),

@@ -69,26 +69,34 @@ struct TcSmem {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kStages = BN <= 64 ? 4 : 3;
-    static constexpr int kBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kStatBytes = 4 * 2 * BN * 4;           // [4 epilogue warps][sum, sum of squares][BN] floats
+    static constexpr int kBytes = kStages * kStageBytes + kStatBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// Persistent: CTA i works on tiles i, i + gridDim.x, ...; a tile is (128 destination pixels) x (BN destination channels), tiles
+// of the same pixels are adjacent so concurrently running CTAs share the A tile in L2.  The accumulator is double-buffered in
+// TMEM (2 x BN columns): the epilogue of tile k (TMEM -> registers -> global, BatchNorm statistics) overlaps the TMA / MMA of
+// tile k + 1.
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcConvParams p,
-               const float* __restrict__ addend, float* __restrict__ out) {
+               const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats) {
     using S = TcSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+    float* s_stat = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kStatBytes);
     uint64_t* empty_bar = full_bar + S::kStages;
-    uint64_t* accum_bar = empty_bar + S::kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* tmem_full = empty_bar + S::kStages;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
     const int cblocks = p.cs / kBK;
     const int nkb = p.ntaps * cblocks;
+    const int nblocks = p.cd / BN;
+    const int num_tiles = ((p.M + kBM - 1) / kBM) * nblocks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a_hi);
@@ -101,10 +109,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);      // one arrive per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -112,94 +123,137 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
-        int m = m0;
-        const int w_o = m % p.wq;  m /= p.wq;
-        const int h_o = m % p.hq;  m /= p.hq;
-        const int t_o = m % p.tq;
-        const int n_i = m / p.tq;
-        const int bw = w_o * p.sw + p.bw, bh = h_o * p.sh + p.bh, bt = t_o * p.st + p.bt;   // source pixel read by tap offset 0
         const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
         int stage = 0, phase = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kBK;
-            const uint32_t tp = p.taps[tap];
-            const uint16_t c = tp & 0xFF, b = (tp >> 8) & 0xFF, a = (tp >> 16) & 0xFF;
-            const int ftap = tp >> 24;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * S::kStageBytes;
-            mbar_expect_tx(&full_bar[stage], tx);
-            tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
-            tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
-            if (p.x3) {
-                tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
-                tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n0 = (tile % nblocks) * BN;
+            int m = (tile / nblocks) * kBM;
+            const int w_o = m % p.wq;  m /= p.wq;
+            const int h_o = m % p.hq;  m /= p.hq;
+            const int t_o = m % p.tq;
+            const int n_i = m / p.tq;
+            const int bw = w_o * p.sw + p.bw, bh = h_o * p.sh + p.bh, bt = t_o * p.st + p.bt;   // source pixel read by tap offset 0
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kBK;
+                const uint32_t tp = p.taps[tap];
+                const uint16_t c = tp & 0xFF, b = (tp >> 8) & 0xFF, a = (tp >> 16) & 0xFF;
+                const int ftap = tp >> 24;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* st = smem + stage * S::kStageBytes;
+                mbar_expect_tx(&full_bar[stage], tx);
+                tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
+                tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
+                if (p.x3) {
+                    tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
+                    tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
+                }
+                if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
-            if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
-        int stage = 0, phase = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+        int stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-            const uint32_t sb = sa + 2 * S::kABytes;
+            const uint32_t acc = tmem_base + buf * BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+                const uint32_t sb = sa + 2 * S::kABytes;
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-                // K-major SW128 tiles: 8-row groups are 1024 bytes apart; a K=16 slice is 32 bytes into the swizzle row
-                const uint64_t a_hi = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                const uint64_t b_hi = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
-                if (p.x3) {
-                    const uint64_t a_lo = make_smem_desc_sw128(sa + S::kABytes + k * 32, 16, 1024);
-                    const uint64_t b_lo = make_smem_desc_sw128(sb + S::kBBytes + k * 32, 16, 1024);
-                    umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
-                    umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+                for (int k = 0; k < kBK / 16; ++k) {
+                    // K-major SW128 tiles: 8-row groups are 1024 bytes apart; a K=16 slice is 32 bytes into the swizzle row
+                    const uint64_t a_hi = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t b_hi = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                    umma_bf16(acc, a_hi, b_hi, idesc, (kb | k) != 0);
+                    if (p.x3) {
+                        const uint64_t a_lo = make_smem_desc_sw128(sa + S::kABytes + k * 32, 16, 1024);
+                        const uint64_t b_lo = make_smem_desc_sw128(sb + S::kBBytes + k * 32, 16, 1024);
+                        umma_bf16(acc, a_hi, b_lo, idesc, 1);
+                        umma_bf16(acc, a_lo, b_hi, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs have read it
+                if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tmem_full[buf]);           // accumulator complete
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue: TMEM -> registers -> global (one output pixel per thread), optional BatchNorm statistics =====
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int n0 = (tile % nblocks) * BN;
+            const int m = (tile / nblocks) * kBM + q * 32 + lane;
+            size_t pix = (size_t)m;
+            if (p.strided_out) {        // one stride-parity class of a strided input gradient: scatter rows to their pixels
+                int r = m;
+                const int w_o = r % p.wq;  r /= p.wq;
+                const int h_o = r % p.hq;  r /= p.hq;
+                const int t_o = r % p.tq;
+                const int n_i = r / p.tq;
+                pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
+            }
+            const size_t row = pix * p.cd + n0;
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + j * 32, r);
+                tmem_ld_wait();
+                if (j == BN / 32 - 1) {             // the whole accumulator is in registers: hand the TMEM buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                float o[32];
+#pragma unroll
+                for (int v = 0; v < 32; ++v) o[v] = __uint_as_float(r[v]);
+                if (m < p.M) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        if (addend) {
+                            const float4 ad = __ldg(reinterpret_cast<const float4*>(addend + row + j * 32) + v);
+                            o[4 * v] += ad.x; o[4 * v + 1] += ad.y; o[4 * v + 2] += ad.z; o[4 * v + 3] += ad.w;
+                        }
+                        reinterpret_cast<float4*>(out + row + j * 32)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+                    }
+                }
+                if (stats) {
+                    // per-channel sum and sum of squares of the stored tile: fp32 within the tile, fp64 atomics across tiles
+                    float sq[32];
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) {
+                        if (m >= p.M) o[v] = 0.f;
+                        sq[v] = o[v] * o[v];
+                    }
+                    const float cs = warp_column_sums(o, lane), cq = warp_column_sums(sq, lane);
+                    s_stat[(q * 2 + 0) * BN + j * 32 + lane] = cs;
+                    s_stat[(q * 2 + 1) * BN + j * 32 + lane] = cq;
                 }
             }
-            umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs have read it
-            if (++stage == S::kStages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(accum_bar);                 // accumulator complete
-    } else if (warp >= 2) {
-        // ===== epilogue: TMEM -> registers -> global (one output pixel per thread) =====
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int m = m0 + q * 32 + lane;
-        size_t pix = (size_t)m;
-        if (p.strided_out) {            // one stride-parity class of a strided input gradient: scatter rows to their pixels
-            int r = m;
-            const int w_o = r % p.wq;  r /= p.wq;
-            const int h_o = r % p.hq;  r /= p.hq;
-            const int t_o = r % p.tq;
-            const int n_i = r / p.tq;
-            pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
-        }
-        const size_t row = pix * p.cd + n0;
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, r);
-            tmem_ld_wait();
-            if (m < p.M) {
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                                           __uint_as_float(r[4 * v + 3]));
-                    if (addend) {
-                        const float4 ad = __ldg(reinterpret_cast<const float4*>(addend + row + j * 32) + v);
-                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                    }
-                    reinterpret_cast<float4*>(out + row + j * 32)[v] = o;
+            if (stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+                const int t = threadIdx.x - 64;                      // 0..127
+                for (int i = t; i < 2 * BN; i += 128) {
+                    const int which = i / BN, ch = i - which * BN;
+                    const float tot = s_stat[(0 * 2 + which) * BN + ch] + s_stat[(1 * 2 + which) * BN + ch] + s_stat[(2 * 2 + which) * BN + ch] +
+                                      s_stat[(3 * 2 + which) * BN + ch];
+                    atomicAdd(stats + (size_t)which * p.cd + n0 + ch, (double)tot);
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // s_stat is rewritten by the next tile
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---- filter gradient ---------------------------------------------------------------------------------
@@ -415,15 +469,16 @@ static int encode_tiled_2d(CUtensorMap* map, const void* base, uint64_t rows, ui
 }
 
 template <int BN>
-static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const float* addend, float* out, cudaStream_t st) {
+static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const float* addend, float* out, double* stats, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kBytes);
         if (e != cudaSuccess) { set_error("conv_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
         configured = true;
     }
-    dim3 grid((p.M + kBM - 1) / kBM, p.cd / BN);
-    conv_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out);
+    const int tiles = ((p.M + kBM - 1) / kBM) * (p.cd / BN);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    conv_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats);
     return check_launch("conv_tc_kernel");
 }
 
@@ -470,7 +525,7 @@ static DimPlan plan_dgrad(int dst, int src, int k, int s, int pad, int r) {
 // dgrad == 1: out[n,ti,hi,wi,ci] = conv_transpose(dout, filt); a_* = dout planes, b_* = filter planes [taps][ci][co].  A strided
 //             input gradient is one launch per stride-parity class (st * sh * sw of them), each a stride-1 correlation.
 int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
-                const float* addend, float* out, cudaStream_t st) {
+                const float* addend, float* out, double* stats, cudaStream_t st) {
     AVID_REQUIRE(s && a_hi && b_hi && out, "conv_tc: NULL pointer");
     AVID_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "conv_tc: give both lo planes (bf16x3) or neither (bf16)");
     AVID_REQUIRE(s->kt >= 1 && s->kh >= 1 && s->kw >= 1 && s->kt <= 8 && s->kh <= 8 && s->kw <= 8 && s->kt * s->kh * s->kw <= kMaxTaps,
@@ -546,7 +601,7 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                 if (x3 && (rc = encode_im2col(&maps[1], a_lo, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
                 maps[2] = map_b[0];
                 maps[3] = map_b[1];
-                rc = bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, st) : launch_conv_tc<64>(maps, p, addend, out, st);
+                rc = bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, stats, st) : launch_conv_tc<64>(maps, p, addend, out, stats, st);
                 if (rc) return rc;
             }
     return AVID_OK;
@@ -628,13 +683,13 @@ int avid_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream)
 }
 
 int avid_conv_forward_tc(const avid_conv_shape_t* s, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
-                         const float* addend, float* out, void* stream) {
-    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, out, static_cast<cudaStream_t>(stream));
+                         const float* addend, float* out, double* bn_stats, void* stream) {
+    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, out, bn_stats, static_cast<cudaStream_t>(stream));
 }
 
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
                        const float* addend, float* din, void* stream) {
-    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, din, static_cast<cudaStream_t>(stream));
+    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, din, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -54,7 +54,7 @@ __device__ __forceinline__ void tile_coords(const StemParams& p, int tile, int& 
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const StemParams p,
-                    float* __restrict__ out) {
+                    float* __restrict__ out, double* __restrict__ stats) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int chunks = p.kt * p.kh, planes = p.x3 ? 2 : 1;
@@ -151,6 +151,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         const int q = warp & 3;
         const int r = q * 32 + lane;
         int it = 0;
+        double run_s[2] = {0.0, 0.0}, run_q[2] = {0.0, 0.0};     // BatchNorm statistics of channels lane and 32 + lane over this warp's rows
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             int n_i, t_o, h0, w0;
@@ -166,7 +167,8 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);     // the accumulator is in registers: the next tile may start
             const int ho = h0 + r / kTileW, wo = w0 + r % kTileW;
-            if (ho < p.ho && wo < p.wo) {
+            const bool valid = ho < p.ho && wo < p.wo;
+            if (valid) {
                 float4* dst = reinterpret_cast<float4*>(out + ((((size_t)n_i * p.to + t_o) * p.ho + ho) * p.wo + wo) * kStemCo);
 #pragma unroll
                 for (int v = 0; v < 8; ++v)
@@ -177,6 +179,33 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
                     dst[8 + v] = make_float4(__uint_as_float(v1[4 * v]), __uint_as_float(v1[4 * v + 1]), __uint_as_float(v1[4 * v + 2]),
                                              __uint_as_float(v1[4 * v + 3]));
             }
+            if (stats) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float o[32], sq[32];
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) {
+                        o[v] = valid ? __uint_as_float(j ? v1[v] : v0[v]) : 0.f;
+                        sq[v] = o[v] * o[v];
+                    }
+                    run_s[j] += (double)warp_column_sums(o, lane);
+                    run_q[j] += (double)warp_column_sums(sq, lane);
+                }
+            }
+        }
+        if (stats) {
+            // all tiles are done (every MMA has completed), so the row-slot ring is free: [4 warps][2][64] doubles
+            double* s_stat = reinterpret_cast<double*>(ring);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                s_stat[(q * 2 + 0) * kStemCo + j * 32 + lane] = run_s[j];
+                s_stat[(q * 2 + 1) * kStemCo + j * 32 + lane] = run_q[j];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = threadIdx.x - 64;      // 0..127 = (which, channel)
+            const int which = t >> 6, ch = t & 63;
+            atomicAdd(stats + which * kStemCo + ch, s_stat[(0 * 2 + which) * kStemCo + ch] + s_stat[(1 * 2 + which) * kStemCo + ch] +
+                                                        s_stat[(2 * 2 + which) * kStemCo + ch] + s_stat[(3 * 2 + which) * kStemCo + ch]);
         }
     }
     tc_fence_before();
@@ -389,7 +418,7 @@ static int encode_stem_x(CUtensorMap* map, const void* base, const avid_conv_sha
 }
 
 int stem_forward_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int wp, const void* w_hi, const void* w_lo, float* out,
-                     cudaStream_t st) {
+                     double* stats, cudaStream_t st) {
     StemParams p;
     int rc = stem_check(s, wp, &p);
     if (rc) return rc;
@@ -418,7 +447,7 @@ int stem_forward_run(const avid_conv_shape_t* s, const void* x_hi, const void* x
         configured = true;
     }
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    stem_forward_kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], mw[0], mw[1], p, out);
+    stem_forward_kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], mw[0], mw[1], p, out, stats);
     return check_launch("stem_forward_kernel");
 }
 
@@ -483,8 +512,8 @@ int avid_stem_filter_pack(const float* w_oihw, void* hi, void* lo, int32_t co, i
 }
 
 int avid_stem_forward_tc(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int32_t wp, const void* filt_hi, const void* filt_lo,
-                         float* out, void* stream) {
-    return stem_forward_run(s, x_hi, x_lo, wp, filt_hi, filt_lo, out, static_cast<cudaStream_t>(stream));
+                         float* out, double* bn_stats, void* stream) {
+    return stem_forward_run(s, x_hi, x_lo, wp, filt_hi, filt_lo, out, bn_stats, static_cast<cudaStream_t>(stream));
 }
 
 int avid_stem_wgrad_tc(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo, int32_t wp, const void* dout_hi, const void* dout_lo,

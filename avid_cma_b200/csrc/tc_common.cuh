@@ -133,6 +133,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Column sums of a 32 x 32 block held one row per lane (v[c] = element (lane, c)): butterfly transpose-reduce, 31 shuffles.
+// Returns, on lane l, the sum over the 32 lanes of column l.  v is destroyed.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
 }  // namespace tc
 
 // ---- host: tensor-map encoding through the driver entry points (no link-time libcuda dependency) ----

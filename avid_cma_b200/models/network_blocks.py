@@ -56,10 +56,11 @@ class ConvOp:
             self.wd_hi, self.wd_lo = ops.split_bf16(w_tap, self.x3)             # dgrad operand, K-major in co
             self.w_tap = self.w_tap_t = None
 
-    def forward(self, x, addend=None):
+    def forward(self, x, addend=None, bn_stats=None):
+        """bn_stats: (2, co) fp64 zeros the tensor-core epilogue accumulates the BatchNorm statistics into (tc only)."""
         if self.tc:
             x.ensure_planes(self.x3)
-            return ops.conv_forward_tc(self.shape, x.hi, x.lo, self.wf_hi, self.wf_lo, addend=addend, ci_real=self.ci_real)
+            return ops.conv_forward_tc(self.shape, x.hi, x.lo, self.wf_hi, self.wf_lo, addend=addend, ci_real=self.ci_real, bn_stats=bn_stats)
         return ops.conv_forward(self.shape, x.f32, self.w_tap, addend=addend, ci_real=self.ci_real)
 
     def needs_f32_dz(self):
@@ -98,9 +99,9 @@ class StemOp:
         hi, lo = ops.stem_pack(x, self.wp, self.p[2], self.x3)
         return Act(None, hi, lo)
 
-    def forward(self, x, addend=None):
+    def forward(self, x, addend=None, bn_stats=None):
         assert addend is None
-        return ops.stem_forward_tc(self.shape, x.hi, x.lo, self.w_hi, self.w_lo)
+        return ops.stem_forward_tc(self.shape, x.hi, x.lo, self.w_hi, self.w_lo, bn_stats=bn_stats)
 
     def needs_f32_dz(self):
         return False
@@ -118,11 +119,14 @@ class ConvBNReLU:
         convolution reads (plus fp32 when `out_f32`: block outputs feed residual adds and pools)."""
         if op is None:
             op = ConvOp(conv, x.shape, math)
-        z = op.forward(x, addend)
         if training:
-            st = ops.bn_train_stats(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bn.momentum)
+            # tensor-core convolutions accumulate the batch statistics in their epilogue; the fp32 kernels need a separate pass
+            st = ops.BNState(conv.out_channels, x.device) if op.tc else None
+            z = op.forward(x, addend, bn_stats=st.stats) if op.tc else op.forward(x, addend)
+            st = ops.bn_train_stats(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bn.momentum, state=st)
             bn.num_batches_tracked += 1
         else:
+            z = op.forward(x, addend)
             st = ops.BNState(conv.out_channels, z.device)
             st.invstd.copy_(torch.rsqrt(bn.running_var + bn.eps))
             st.mean.copy_(bn.running_mean)

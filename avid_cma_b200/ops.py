@@ -221,13 +221,14 @@ def split_bf16(x, need_lo=True):
     return hi, lo
 
 
-def conv_forward_tc(s, x_hi, x_lo, w_hi, w_lo, addend=None, out=None, ci_real=None):
+def conv_forward_tc(s, x_hi, x_lo, w_hi, w_lo, addend=None, out=None, ci_real=None, bn_stats=None):
     """tcgen05 forward conv; x_* planes [n,t,h,w,ci] bf16, w_* planes [taps,co,ci] bf16 (lo planes None -> single-pass bf16)."""
     if out is None:
         out = torch.empty(s.n, s.to, s.ho, s.wo, s.co, dtype=torch.float32, device=x_hi.device)
     e0 = _t0()
     check(_lib.lib().avid_conv_forward_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
-                                          _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out), _stream()))
+                                          _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out),
+                                          _p(bn_stats, torch.float64, optional=True), _stream()))
     _t1(e0, "conv_forward_tc", _conv_flops(s, ci_real))
     return out
 
@@ -273,13 +274,14 @@ def stem_filter_pack(w, need_lo=True):
     return hi, lo
 
 
-def stem_forward_tc(s, x_hi, x_lo, w_hi, w_lo, out=None):
+def stem_forward_tc(s, x_hi, x_lo, w_hi, w_lo, out=None, bn_stats=None):
     """tcgen05 stem convolution; s.ci is the real channel count, x_* the stem_pack planes, w_* the stem_filter_pack planes."""
     if out is None:
         out = torch.empty(s.n, s.to, s.ho, s.wo, s.co, dtype=torch.float32, device=x_hi.device)
     e0 = _t0()
     check(_lib.lib().avid_stem_forward_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), x_hi.shape[3],
-                                          _p(w_hi, torch.bfloat16), _p(w_lo, torch.bfloat16, optional=True), _p(out), _stream()))
+                                          _p(w_hi, torch.bfloat16), _p(w_lo, torch.bfloat16, optional=True), _p(out),
+                                          _p(bn_stats, torch.float64, optional=True), _stream()))
     _t1(e0, "stem_forward_tc", _conv_flops(s))
     return out
 
@@ -343,13 +345,16 @@ class BNState:
         self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
 
 
-def bn_train_stats(x, gamma, beta, running_mean, running_var, eps=BN_EPS, momentum=BN_MOMENTUM):
-    """x (..., c) channels-last.  Computes batch statistics, updates running stats, returns BNState."""
+def bn_train_stats(x, gamma, beta, running_mean, running_var, eps=BN_EPS, momentum=BN_MOMENTUM, state=None):
+    """x (..., c) channels-last.  Computes batch statistics, updates running stats, returns BNState.  With `state` given its
+    `stats` were already accumulated by the producing convolution's epilogue and only the finalize kernel runs."""
     c = x.shape[-1]
     rows = x.numel() // c
-    s = BNState(c, x.device)
     L = _lib.lib()
-    check(L.avid_bn_stats(_p(x), rows, c, _p(s.stats, torch.float64), _stream()))
+    s = state
+    if s is None:
+        s = BNState(c, x.device)
+        check(L.avid_bn_stats(_p(x), rows, c, _p(s.stats, torch.float64), _stream()))
     check(L.avid_bn_finalize(_p(s.stats, torch.float64), rows, c, _p(gamma), _p(beta), eps, momentum,
                              _p(running_mean, optional=True), _p(running_var, optional=True),
                              _p(s.mean), _p(s.invstd), _p(s.scale), _p(s.shift), _stream()))

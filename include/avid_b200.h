@@ -192,13 +192,16 @@ int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const floa
  * (avid_split_bf16).  With both planes the kernel accumulates hi*hi + hi*lo + lo*hi in fp32 ("bf16x3",
  * AVID_MATH_BF16X3, ~16 significand bits per operand); with lo == NULL it is a plain bf16 product
  * (AVID_MATH_BF16).  Activations are fetched by TMA im2col-mode loads, filters by tiled TMA loads.
+ * The forward kernels take an optional `bn_stats` (2, co) double buffer, zeroed by the caller: the epilogue adds the
+ * per-channel sum and sum of squares of the stored output (after the addend), i.e. what avid_bn_stats would compute in a
+ * separate pass over the tensor, so that avid_bn_finalize can follow directly.
  * Channel counts must be multiples of 64 (every layer of both towers except the two stems).
  *   forward: in planes [n,ti,hi,wi,ci], filter planes K-major [taps][co][ci] (the w_tap_t layout)
  *   dgrad  : dout planes [n,to,ho,wo,co], filter planes [taps][ci][co] (the w_tap layout); a strided gradient runs as one
  *            stride-1 correlation per stride-parity class of the input pixels (st*sh*sw launches)                      */
 int avid_split_bf16(const float* x, void* hi, void* lo /* may be NULL */, int64_t n, void* stream);
 int avid_conv_forward_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
-                         const float* addend, float* out, void* stream);
+                         const float* addend, float* out, double* bn_stats, void* stream);
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
                        const float* addend, float* din, void* stream);
 /*   wgrad  : in planes [n,ti,hi,wi,ci], dout planes [n,to,ho,wo,co] -> dfilt fp32 tap-major [taps][ci][co], zeroed by the
@@ -220,7 +223,7 @@ int avid_stem_pack(const float* x, void* hi, void* lo /* may be NULL */, int32_t
 int avid_stem_filter_pack(const float* w_oihw, void* hi, void* lo /* may be NULL */, int32_t co, int32_t ci, int32_t kt, int32_t kh, int32_t kw,
                           void* stream);
 int avid_stem_forward_tc(const avid_conv_shape_t* s_host, const void* x_hi, const void* x_lo, int32_t wp, const void* filt_hi, const void* filt_lo,
-                         float* out, void* stream);
+                         float* out, double* bn_stats, void* stream);
 int avid_stem_wgrad_tc(const avid_conv_shape_t* s_host, const void* x_hi, const void* x_lo, int32_t wp, const void* dout_hi, const void* dout_lo,
                        float* dfilt, void* stream);
 

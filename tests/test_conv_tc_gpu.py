@@ -52,8 +52,12 @@ def test_conv_tc_forward_and_dgrad(case, x3):
     torch.cuda.synchronize()
     assert _rel(ops.nhwc_to_nchw(out), ref) < tol
     add_c = ops.nchw_to_nhwc(addend.to(DEV))
-    out2 = ops.conv_forward_tc(shape, x_hi, x_lo, wf_hi, wf_lo, addend=add_c)
+    stats = torch.zeros(2, co, dtype=torch.float64, device=DEV)
+    out2 = ops.conv_forward_tc(shape, x_hi, x_lo, wf_hi, wf_lo, addend=add_c, bn_stats=stats)
     assert _rel(ops.nhwc_to_nchw(out2), ref + addend.double()) < tol
+    # fused BatchNorm statistics = per-channel sum / sum of squares of what was stored
+    flat = out2.double().reshape(-1, co)
+    assert _rel(stats[0], flat.sum(0)) < 1e-5 and _rel(stats[1], (flat * flat).sum(0)) < 1e-5
     d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
     dw = ops.filter_from_tapmajor(ops.conv_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo), wt.to(DEV))
     assert _rel(dw, wd.grad) < tol
@@ -101,9 +105,12 @@ def test_stem_tc_forward_and_wgrad(case, x3):
     shape = ops.conv_shape(n, t, h, w, ci, co, k, s, p)
     x_hi, x_lo = ops.stem_pack(x.to(DEV), 2 * shape.wo + 8, p[2], x3)
     w_hi, w_lo = ops.stem_filter_pack(wt.to(DEV), x3)
-    out = ops.stem_forward_tc(shape, x_hi, x_lo, w_hi, w_lo)
+    stats = torch.zeros(2, co, dtype=torch.float64, device=DEV)
+    out = ops.stem_forward_tc(shape, x_hi, x_lo, w_hi, w_lo, bn_stats=stats)
     torch.cuda.synchronize()
     assert _rel(ops.nhwc_to_nchw(out), ref) < tol
+    flat = out.double().reshape(-1, co)
+    assert _rel(stats[0], flat.sum(0)) < 1e-5 and _rel(stats[1], (flat * flat).sum(0)) < 1e-5
     d_hi, d_lo = ops.split_bf16(ops.nchw_to_nhwc(dout.to(DEV)), x3)
     dw_tap = ops.stem_wgrad_tc(shape, x_hi, x_lo, d_hi, d_lo)
     dw = ops.filter_from_tapmajor(dw_tap, wt.to(DEV))
