@@ -153,6 +153,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+        // K-major SW128 tiles: 8-row groups are 1024 bytes apart; a K=16 slice is 32 bytes into the swizzle row.  Descriptors
+        // differ only in the start-address field (bytes >> 4): encode once and add offsets, so that the single issuing thread
+        // spends a couple of instructions per MMA (an N = 64 MMA is only 32 tensor-pipe cycles).
+        const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+        const bool x3 = p.x3 != 0;
         int stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -162,20 +167,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-                const uint32_t sb = sa + 2 * S::kABytes;
+                const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
+                const uint64_t b_hi = a_hi + (uint32_t)((2 * S::kABytes) >> 4);
+                if (x3) {
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    // K-major SW128 tiles: 8-row groups are 1024 bytes apart; a K=16 slice is 32 bytes into the swizzle row
-                    const uint64_t a_hi = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t b_hi = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_bf16(acc, a_hi, b_hi, idesc, (kb | k) != 0);
-                    if (p.x3) {
-                        const uint64_t a_lo = make_smem_desc_sw128(sa + S::kABytes + k * 32, 16, 1024);
-                        const uint64_t b_lo = make_smem_desc_sw128(sb + S::kBBytes + k * 32, 16, 1024);
-                        umma_bf16(acc, a_hi, b_lo, idesc, 1);
-                        umma_bf16(acc, a_lo, b_hi, idesc, 1);
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16(acc, a_hi + 2 * k, b_hi + (uint32_t)(S::kBBytes >> 4) + 2 * k, idesc, 1);
+                        umma_bf16(acc, a_hi + (uint32_t)(S::kABytes >> 4) + 2 * k, b_hi + 2 * k, idesc, 1);
                     }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
                 }
                 umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs have read it
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
@@ -367,25 +370,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), kSubTile, 1024);
+        const bool x3 = p.x3 != 0;
         int stage = 0, phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t a_hi_s = smem_u32(smem + stage * S::kStageBytes);
-            const uint32_t b_hi_s = a_hi_s + S::kABytes;
-            const uint32_t a_lo_s = a_hi_s + S::kABytes + S::kBBytes;
-            const uint32_t b_lo_s = a_lo_s + S::kABytes;
+            const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
+            const uint64_t b_hi = a_hi + (uint32_t)(S::kABytes >> 4);
+            constexpr uint32_t kLo = (uint32_t)((S::kABytes + S::kBBytes) >> 4);      // hi -> lo plane of the same operand
+            if (x3) {
 #pragma unroll
-            for (int k = 0; k < kWgKB / 16; ++k) {
-                const uint64_t a_hi = make_smem_desc_sw128(a_hi_s + k * 2048, kSubTile, 1024);
-                const uint64_t b_hi = make_smem_desc_sw128(b_hi_s + k * 2048, kSubTile, 1024);
-                umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
-                if (p.x3) {
-                    const uint64_t a_lo = make_smem_desc_sw128(a_lo_s + k * 2048, kSubTile, 1024);
-                    const uint64_t b_lo = make_smem_desc_sw128(b_lo_s + k * 2048, kSubTile, 1024);
-                    umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
-                    umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+                for (int k = 0; k < kWgKB / 16; ++k) {          // a K = 16 step advances 2 KB = 128 encoded units
+                    umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
+                    umma_bf16(tmem_base, a_hi + 128 * k, b_hi + kLo + 128 * k, idesc, 1);
+                    umma_bf16(tmem_base, a_hi + kLo + 128 * k, b_hi + 128 * k, idesc, 1);
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kWgKB / 16; ++k) umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }

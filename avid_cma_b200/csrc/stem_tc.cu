@@ -51,6 +51,10 @@ __device__ __forceinline__ void tile_coords(const StemParams& p, int tile, int& 
     w0 = tw * kTileW;
 }
 
+// KH > 0: the vertical tap count is a compile-time constant (7 for both towers' stems) so the MMA issue loop unrolls into
+// straight-line code -- with N = 64 an MMA is only 32 tensor-pipe cycles, and a single thread issuing through runtime loops
+// and descriptor re-encoding (~100 cycles per MMA, measured) was the bottleneck of this kernel.  KH == 0: generic path.
+template <int KH, bool X3>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const StemParams p,
@@ -112,7 +116,12 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 0, 0);
         mbar_wait(w_bar, 0);
-        const uint32_t w_base = smem_u32(w_smem);
+        // descriptors differ only in the 14-bit start-address field (bytes >> 4): encode once, then add offsets
+        const uint64_t desc0 = make_smem_desc_sw64(0, 16, 512);
+        const uint64_t w_desc = desc0 + (smem_u32(w_smem) >> 4);
+        const uint64_t ring_desc = desc0 + (smem_u32(ring) >> 4);
+        const int kh_n = KH > 0 ? KH : p.kh;
+        const uint32_t lo_off = (uint32_t)(chunks * kChunkBBytes) >> 4;      // hi -> lo filter plane
         int stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -120,22 +129,27 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * kStemCo;
             uint32_t accumulate = 0;
-            for (int a = 0; a < p.kt; ++a)
-                for (int par = 0; par < 2 && par < p.kh; ++par)
-                    for (int pl = 0; pl < planes; ++pl) {
+            for (int a = 0; a < p.kt; ++a) {
+                const uint64_t w_a = w_desc + (uint32_t)((a * kh_n * kChunkBBytes) >> 4);
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    if (par >= kh_n) break;
+#pragma unroll
+                    for (int pl = 0; pl < (X3 ? 2 : 1); ++pl) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t slot = smem_u32(ring + stage * kSlotBytes);
-                        for (int kh = par; kh < p.kh; kh += 2) {
-                            const uint32_t wc = w_base + (a * p.kh + kh) * kChunkBBytes;
+                        const uint64_t slot = ring_desc + (uint32_t)((stage * kSlotBytes) >> 4);
+#pragma unroll
+                        for (int kh = par; kh < (KH > 0 ? KH : 8); kh += 2) {
+                            if (KH == 0 && kh >= kh_n) break;
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t da = make_smem_desc_sw64(slot + (kh >> 1) * kRowBytes + ks * 32, 16, 512);
-                                const uint64_t db_hi = make_smem_desc_sw64(wc + ks * 32, 16, 512);
+                                const uint64_t da = slot + (uint32_t)(((kh >> 1) * kRowBytes + ks * 32) >> 4);
+                                const uint64_t db_hi = w_a + (uint32_t)((kh * kChunkBBytes + ks * 32) >> 4);
                                 if (pl == 0) {
                                     umma_bf16(acc, da, db_hi, idesc, accumulate);
                                     accumulate = 1;
-                                    if (p.x3) umma_bf16(acc, da, make_smem_desc_sw64(wc + chunks * kChunkBBytes + ks * 32, 16, 512), idesc, 1);
+                                    if (X3) umma_bf16(acc, da, db_hi + lo_off, idesc, 1);
                                 } else {
                                     umma_bf16(acc, da, db_hi, idesc, 1);
                                 }
@@ -144,6 +158,8 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
                         umma_commit(&empty_bar[stage]);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
+                }
+            }
             umma_commit(&tmem_full[buf]);
         }
     } else if (warp >= 2) {
@@ -218,6 +234,7 @@ __device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <bool X3>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                   const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, const StemParams p,
@@ -280,26 +297,29 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer: A = x slot (MN-major, 64-byte swizzle, 4 tap atoms one row apart), B = dZ (MN-major, 128-byte swizzle) =====
         constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 1, 1);
+        const uint64_t ring_desc = make_smem_desc_sw64(0, kRowBytes, 512) + (smem_u32(ring) >> 4);
+        const uint64_t dz_desc = make_smem_desc_sw128(0, 16, 1024) + (smem_u32(dz_smem) >> 4);
         int stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait(&dz_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t dz_hi = smem_u32(dz_smem + buf * planes * kDzBytes), dz_lo = dz_hi + kDzBytes;
+            const uint64_t dz_hi = dz_desc + (uint32_t)((buf * planes * kDzBytes) >> 4);
             for (int a = 0; a < p.kt; ++a)
                 for (int par = 0; par < 2 && par < p.kh; ++par) {
                     const uint32_t acc = tmem_base + (a * 2 + par) * kStemCo;
-                    for (int pl = 0; pl < planes; ++pl) {
+#pragma unroll
+                    for (int pl = 0; pl < (X3 ? 2 : 1); ++pl) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t slot = smem_u32(ring + stage * kSlotBytes);
+                        const uint64_t slot = ring_desc + (uint32_t)((stage * kSlotBytes) >> 4);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {          // 16 pixels (one patch row) per MMA
-                            const uint64_t da = make_smem_desc_sw64(slot + ks * kRowBytes, kRowBytes, 512);
-                            const uint64_t db_hi = make_smem_desc_sw128(dz_hi + ks * 2048, 16, 1024);
+                            const uint64_t da = slot + (uint32_t)((ks * kRowBytes) >> 4);
+                            const uint64_t db_hi = dz_hi + (uint32_t)((ks * 2048) >> 4);
                             if (pl == 0) {
                                 umma_bf16(acc, da, db_hi, idesc, (it | ks) != 0);
-                                if (p.x3) umma_bf16(acc, da, make_smem_desc_sw128(dz_lo + ks * 2048, 16, 1024), idesc, 1);
+                                if (X3) umma_bf16(acc, da, db_hi + (uint32_t)(kDzBytes >> 4), idesc, 1);
                             } else {
                                 umma_bf16(acc, da, db_hi, idesc, 1);
                             }
@@ -440,14 +460,20 @@ int stem_forward_run(const avid_conv_shape_t* s, const void* x_hi, const void* x
     if ((rc = encode_tiled_nd(&mw[0], w_hi, 2, wdims, wstr, wbox, west, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     mw[1] = mw[0];
     if (p.x3 && (rc = encode_tiled_nd(&mw[1], w_lo, 2, wdims, wstr, wbox, west, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    typedef void (*Kernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, StemParams, float*, double*);
+    const Kernel kernel = p.kh == 7 ? (p.x3 ? (Kernel)stem_forward_kernel<7, true> : (Kernel)stem_forward_kernel<7, false>)
+                                    : (p.x3 ? (Kernel)stem_forward_kernel<0, true> : (Kernel)stem_forward_kernel<0, false>);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(stem_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) { set_error("stem_forward_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        for (Kernel k : {(Kernel)stem_forward_kernel<7, true>, (Kernel)stem_forward_kernel<7, false>, (Kernel)stem_forward_kernel<0, true>,
+                         (Kernel)stem_forward_kernel<0, false>}) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            if (e != cudaSuccess) { set_error("stem_forward_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        }
         configured = true;
     }
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    stem_forward_kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], mw[0], mw[1], p, out, stats);
+    kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], mw[0], mw[1], p, out, stats);
     return check_launch("stem_forward_kernel");
 }
 
@@ -476,12 +502,14 @@ int stem_wgrad_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_l
     if (p.x3 && (rc = encode_tiled_nd(&md[1], d_lo, 5, ddims, dstr, dbox, dest, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(stem_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) { set_error("stem_wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
         configured = true;
     }
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    stem_wgrad_kernel<<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], md[0], md[1], p, cols, dfilt);
+    if (p.x3) stem_wgrad_kernel<true><<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], md[0], md[1], p, cols, dfilt);
+    else stem_wgrad_kernel<false><<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], md[0], md[1], p, cols, dfilt);
     return check_launch("stem_wgrad_kernel");
 }
 
