@@ -40,9 +40,16 @@ __global__ void __launch_bounds__(256) linear_dx_kernel(const float* __restrict_
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * in_f) return;
     const int r = idx / in_f, i = idx - r * in_f;
-    float acc = 0.f;
-    for (int o = 0; o < out_f; ++o) acc = fmaf(__ldg(dy + (size_t)r * out_f + o), __ldg(w + (size_t)o * in_f + i), acc);
-    dx[idx] = acc;
+    // four independent accumulation chains, 8 loads in flight: the problem is a single partial wave, i.e. latency bound
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int o = 0;
+#pragma unroll 2
+    for (; o + 4 <= out_f; o += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(__ldg(dy + (size_t)r * out_f + o + u), __ldg(w + (size_t)(o + u) * in_f + i), acc[u]);
+    }
+    for (; o < out_f; ++o) acc[0] = fmaf(__ldg(dy + (size_t)r * out_f + o), __ldg(w + (size_t)o * in_f + i), acc[0]);
+    dx[idx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 // dW[o, i] = sum_r dy[r, o] x[r, i]; db[o] = sum_r dy[r, o]

@@ -1,4 +1,6 @@
 // Layout conversions, the fused Adam step and small elementwise helpers (include/avid_b200.h).
+#include <cuda_bf16.h>
+#include <math.h>
 #include "common.cuh"
 
 namespace avid {
@@ -81,6 +83,61 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// PyTorch filter [co, ci, taps] -> bf16 (hi, lo) planes of both tensor-core operand layouts in one pass:
+//   fwd planes [taps][co][ci] (K-major in ci), dgrad planes [taps][ci][co] (K-major in co)
+__global__ void __launch_bounds__(256) filter_to_planes_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ f_hi,
+                                                               __nv_bfloat16* __restrict__ f_lo, __nv_bfloat16* __restrict__ d_hi,
+                                                               __nv_bfloat16* __restrict__ d_lo, int co, int ci, int taps) {
+    const int64_t total = (int64_t)taps * ci * co;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ci);            // forward layout index: ((t * co + o) * ci + c)
+        int64_t r = i / ci;
+        const int o = (int)(r % co), t = (int)(r / co);
+        const float v = __ldg(w + ((size_t)o * ci + c) * taps + t);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        f_hi[i] = h;
+        if (f_lo) f_lo[i] = l;
+        const size_t j = ((size_t)t * ci + c) * co + o;
+        d_hi[j] = h;
+        if (d_lo) d_lo[j] = l;
+    }
+}
+
+// torch.optim.Adam on up to kAdamMaxTensors tensors per launch: block b works on a 4096-element chunk of the tensor whose
+// block range contains b
+constexpr int kAdamMaxTensors = 32, kAdamChunk = 4096;
+struct AdamBatch {
+    float* p[kAdamMaxTensors];
+    const float* g[kAdamMaxTensors];
+    float* m[kAdamMaxTensors];
+    float* v[kAdamMaxTensors];
+    int64_t n[kAdamMaxTensors];
+    int block_begin[kAdamMaxTensors + 1];
+    int count;
+};
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamBatch b, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                                         float bc1, float bc2_sqrt, float grad_scale) {
+    int t = 0;
+    while (t + 1 < b.count && (int)blockIdx.x >= b.block_begin[t + 1]) ++t;
+    const int64_t base = (int64_t)(blockIdx.x - b.block_begin[t]) * kAdamChunk;
+    const int64_t end = min(b.n[t], base + kAdamChunk);
+    float* __restrict__ p = b.p[t];
+    const float* __restrict__ g = b.g[t];
+    float* __restrict__ m = b.m[t];
+    float* __restrict__ v = b.v[t];
+    for (int64_t i = base + threadIdx.x; i < end; i += 256) {
+        const float pi = p[i];
+        const float gi = fmaf(weight_decay, pi, g[i] * grad_scale);
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
 static unsigned grid_for(int64_t n) {
     int64_t b = (n + 255) / 256;
     const int64_t cap = 16 * kNumSMs;
@@ -124,6 +181,49 @@ int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int
     AVID_REQUIRE(w_oihw && w_tap && co > 0 && ci > 0 && taps > 0 && ci_pad >= ci, "filter_from_tapmajor: bad arguments");
     filter_from_tap_kernel<<<grid_for((int64_t)taps * ci * co), 256, 0, static_cast<cudaStream_t>(stream)>>>(w_tap, w_oihw, co, ci, taps, ci_pad);
     return check_launch("filter_from_tap_kernel");
+}
+
+int avid_filter_to_planes(const float* w_oihw, void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, int32_t co, int32_t ci, int32_t taps,
+                          void* stream) {
+    AVID_REQUIRE(w_oihw && fwd_hi && dgrad_hi && co > 0 && ci > 0 && taps > 0, "filter_to_planes: bad arguments");
+    AVID_REQUIRE((fwd_lo == nullptr) == (dgrad_lo == nullptr), "filter_to_planes: give both lo planes or neither");
+    filter_to_planes_kernel<<<grid_for((int64_t)taps * ci * co), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw, static_cast<__nv_bfloat16*>(fwd_hi), static_cast<__nv_bfloat16*>(fwd_lo), static_cast<__nv_bfloat16*>(dgrad_hi),
+        static_cast<__nv_bfloat16*>(dgrad_lo), co, ci, taps);
+    return check_launch("filter_to_planes_kernel");
+}
+
+int avid_adam_step_multi(float* const* params, const float* const* grads, float* const* exp_avgs, float* const* exp_avg_sqs,
+                         const int64_t* sizes, int32_t count, int64_t step, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, float grad_scale, void* stream) {
+    AVID_REQUIRE(params && grads && exp_avgs && exp_avg_sqs && sizes && count > 0 && step > 0, "adam_step_multi: bad arguments");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    for (int first = 0; first < count; first += kAdamMaxTensors) {
+        AdamBatch b;
+        b.count = count - first < kAdamMaxTensors ? count - first : kAdamMaxTensors;
+        int blocks = 0;
+        for (int i = 0; i < b.count; ++i) {
+            AVID_REQUIRE(params[first + i] && grads[first + i] && exp_avgs[first + i] && exp_avg_sqs[first + i] && sizes[first + i] > 0,
+                         "adam_step_multi: tensor %d has a NULL pointer or no elements", first + i);
+            b.p[i] = params[first + i];  b.g[i] = grads[first + i];  b.m[i] = exp_avgs[first + i];  b.v[i] = exp_avg_sqs[first + i];
+            b.n[i] = sizes[first + i];
+            b.block_begin[i] = blocks;
+            blocks += (int)((sizes[first + i] + kAdamChunk - 1) / kAdamChunk);
+        }
+        b.block_begin[b.count] = blocks;
+        adam_multi_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(b, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                                                (float)sqrt(bc2), grad_scale);
+        int rc = check_launch("adam_multi_kernel");
+        if (rc) return rc;
+    }
+    return AVID_OK;
+}
+
+int avid_zero_bytes(void* p, size_t bytes, void* stream) {
+    AVID_REQUIRE(p && bytes > 0, "zero_bytes: bad arguments");
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { set_error("zero_bytes: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+    return AVID_OK;
 }
 
 int avid_add_inplace(float* a, const float* b, int64_t n, void* stream) {

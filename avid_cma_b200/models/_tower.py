@@ -16,14 +16,26 @@ def default_math():
 class TowerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tower, x, *params):
-        pooled, saved = tower._fwd(x.detach().contiguous().float(), tower.training, tower.math)
+        arena = tower.__dict__.setdefault('_fwd_arena', ops.ZeroArena())
+        arena.begin(x.device)
+        ops.set_arena(arena)
+        try:
+            pooled, saved = tower._fwd(x.detach().contiguous().float(), tower.training, tower.math)
+        finally:
+            ops.set_arena(None)
         ctx.tower, ctx.saved, ctx.params = tower, saved, params
         return pooled
 
     @staticmethod
     def backward(ctx, dpooled):
         grads = {}
-        ctx.tower._bwd(dpooled.contiguous(), ctx.saved, grads, ctx.tower.math)
+        arena = ctx.tower.__dict__.setdefault('_bwd_arena', ops.ZeroArena())
+        arena.begin(dpooled.device)
+        ops.set_arena(arena)
+        try:
+            ctx.tower._bwd(dpooled.contiguous(), ctx.saved, grads, ctx.tower.math)
+        finally:
+            ops.set_arena(None)
         ctx.saved = None
         return (None, None) + tuple(grads.get(p) for p in ctx.params)
 

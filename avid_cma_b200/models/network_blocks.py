@@ -49,12 +49,12 @@ class ConvOp:
         self.x3 = math == ops.MATH_BF16X3
         self.unit_stride = self.s == (1, 1, 1)
         self.ci_real = conv.in_channels
-        w_tap, w_tap_t = ops.filter_to_tapmajor(conv.weight.detach(), ci_pad=ci)
-        self.w_tap, self.w_tap_t = w_tap, w_tap_t          # fp32 [taps, ci, co] / [taps, co, ci]
         if self.tc:
-            self.wf_hi, self.wf_lo = ops.split_bf16(w_tap_t, self.x3)           # forward operand, K-major in ci
-            self.wd_hi, self.wd_lo = ops.split_bf16(w_tap, self.x3)             # dgrad operand, K-major in co
+            # forward operand [taps, co, ci] (K-major in ci) and dgrad operand [taps, ci, co] (K-major in co), one launch
+            (self.wf_hi, self.wf_lo), (self.wd_hi, self.wd_lo) = ops.filter_to_planes(conv.weight.detach(), self.x3)
             self.w_tap = self.w_tap_t = None
+        else:
+            self.w_tap, self.w_tap_t = ops.filter_to_tapmajor(conv.weight.detach(), ci_pad=ci)   # fp32 [taps, ci, co] / [taps, co, ci]
 
     def forward(self, x, addend=None, bn_stats=None):
         """bn_stats: (2, co) fp64 zeros the tensor-core epilogue accumulates the BatchNorm statistics into (tc only)."""

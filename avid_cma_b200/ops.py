@@ -64,6 +64,51 @@ def _t1(e0, name, work):
         _prof.append((name, work, e0, e1))
 
 
+class ZeroArena:
+    """Zero-initialised scratch for one forward or backward pass of a tower: the accumulators the kernels add into with
+    atomics (filter gradients, BatchNorm sums) come from ONE buffer zeroed by ONE memset instead of a fill kernel each.
+    The first pass measures the demand (and falls back to torch.zeros); later passes reuse the buffer."""
+
+    def __init__(self):
+        self.buf, self.capacity, self.pos, self.demand = None, 0, 0, 0
+
+    def begin(self, device):
+        if self.demand > self.capacity:
+            self.buf = torch.empty(self.demand, dtype=torch.uint8, device=device)
+            self.capacity = self.demand
+        if self.buf is not None:
+            check(_lib.lib().avid_zero_bytes(C.c_void_p(self.buf.data_ptr()), self.capacity, _stream()))
+        self.pos, self.demand = 0, 0
+
+    def zeros(self, shape, dtype, device):
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        aligned = (nbytes + 255) & ~255
+        self.demand += aligned
+        if self.buf is not None and self.pos + aligned <= self.capacity and self.buf.device == device:
+            out = self.buf[self.pos:self.pos + nbytes].view(dtype).view(shape)
+            self.pos += aligned
+            return out
+        return torch.zeros(shape, dtype=dtype, device=device)
+
+
+_arena = None
+
+
+def set_arena(arena):
+    """Route the accumulator allocations of the following kernel wrappers through `arena` (None: plain torch.zeros)."""
+    global _arena
+    _arena = arena
+
+
+def _zeros(shape, dtype, device):
+    if _arena is not None:
+        return _arena.zeros(tuple(shape), dtype, torch.device(device))
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
 def _conv_flops(s, ci_real=None):
     return 2.0 * s.n * s.to * s.ho * s.wo * s.kt * s.kh * s.kw * (ci_real or s.ci) * s.co
 
@@ -206,7 +251,7 @@ def conv_dgrad(s, dout, w_tap_t, addend=None, out=None, math=MATH_FP32):
 
 
 def conv_wgrad(s, x, dout, math=MATH_FP32, ci_real=None):
-    dw = torch.zeros(s.kt * s.kh * s.kw, s.ci, s.co, dtype=torch.float32, device=x.device)
+    dw = _zeros((s.kt * s.kh * s.kw, s.ci, s.co), torch.float32, x.device)
     e0 = _t0()
     check(_lib.lib().avid_conv_wgrad(C.byref(s), _p(x), _p(dout), _p(dw), math, _stream()))
     _t1(e0, "conv_wgrad", _conv_flops(s, ci_real))
@@ -246,7 +291,7 @@ def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None):
 
 def conv_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo, ci_real=None):
     """tcgen05 filter gradient; returns fp32 tap-major [taps, ci, co]."""
-    dw = torch.zeros(s.kt * s.kh * s.kw, s.ci, s.co, dtype=torch.float32, device=x_hi.device)
+    dw = _zeros((s.kt * s.kh * s.kw, s.ci, s.co), torch.float32, x_hi.device)
     e0 = _t0()
     check(_lib.lib().avid_conv_wgrad_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), _p(d_hi, torch.bfloat16),
                                         _p(d_lo, torch.bfloat16, optional=True), _p(dw), _stream()))
@@ -288,12 +333,24 @@ def stem_forward_tc(s, x_hi, x_lo, w_hi, w_lo, out=None, bn_stats=None):
 
 def stem_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo):
     """tcgen05 stem filter gradient -> fp32 tap-major [taps, 4, co]."""
-    dw = torch.zeros(s.kt * s.kh * s.kw, 4, s.co, dtype=torch.float32, device=x_hi.device)
+    dw = _zeros((s.kt * s.kh * s.kw, 4, s.co), torch.float32, x_hi.device)
     e0 = _t0()
     check(_lib.lib().avid_stem_wgrad_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), x_hi.shape[3],
                                         _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(dw), _stream()))
     _t1(e0, "stem_wgrad_tc", _conv_flops(s))
     return dw
+
+
+def filter_to_planes(w, need_lo=True):
+    """PyTorch conv weight (co, ci, *k) -> bf16 planes ((fwd_hi, fwd_lo) [taps, co, ci], (dgrad_hi, dgrad_lo) [taps, ci, co])."""
+    co, ci = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    mk = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    f_hi, d_hi = mk(taps, co, ci), mk(taps, ci, co)
+    f_lo, d_lo = (mk(taps, co, ci), mk(taps, ci, co)) if need_lo else (None, None)
+    check(_lib.lib().avid_filter_to_planes(_p(w), _p(f_hi, torch.bfloat16), _p(f_lo, torch.bfloat16, optional=True), _p(d_hi, torch.bfloat16),
+                                           _p(d_lo, torch.bfloat16, optional=True), co, ci, taps, _stream()))
+    return (f_hi, f_lo), (d_hi, d_lo)
 
 
 def filter_to_tapmajor(w, ci_pad=None, transpose=True):
@@ -340,7 +397,7 @@ class BNState:
     __slots__ = ("stats", "mean", "invstd", "scale", "shift")
 
     def __init__(self, c, device):
-        self.stats = torch.zeros(2, c, dtype=torch.float64, device=device)
+        self.stats = _zeros((2, c), torch.float64, device)
         buf = torch.empty(4, c, dtype=torch.float32, device=device)
         self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
 
@@ -412,7 +469,7 @@ def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=No
     """Backward of y = relu(bn_train(x)); the gradient w.r.t. x as an Act (fp32 and / or bf16 planes)."""
     c = x.shape[-1]
     rows = x.numel() // c
-    sums = torch.zeros(2, c, dtype=torch.float64, device=x.device)
+    sums = _zeros((2, c), torch.float64, x.device)
     if want_f32 and dx is None:
         dx = torch.empty_like(x)
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes else None
@@ -482,6 +539,19 @@ def linear_backward(x, w, y, dy, relu, need_dx=True):
 def add_(a, b):
     check(_lib.lib().avid_add_inplace(_p(a), _p(b), a.numel(), _stream()))
     return a
+
+
+def adam_step_multi_(params, grads, exp_avgs, exp_avg_sqs, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """One Adam update of many fp32 tensors (32 per kernel launch)."""
+    n = len(params)
+    if n == 0:
+        return
+    for t in list(params) + list(grads) + list(exp_avgs) + list(exp_avg_sqs):
+        _p(t)                                      # validates device / dtype / contiguity
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    sizes = (C.c_int64 * n)(*[t.numel() for t in params])
+    check(_lib.lib().avid_adam_step_multi(arr(params), arr(grads), arr(exp_avgs), arr(exp_avg_sqs), sizes, n, step, lr, betas[0], betas[1], eps,
+                                          weight_decay, grad_scale, _stream()))
 
 
 def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):

@@ -17,6 +17,7 @@ class Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
+            by_step = {}
             for p in group['params']:
                 if p.grad is None:
                     continue
@@ -26,6 +27,8 @@ class Adam(torch.optim.Optimizer):
                     st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st['step'] += 1
-                ops.adam_step_(p.data, p.grad.contiguous(), st['exp_avg'], st['exp_avg_sq'], st['step'], group['lr'],
-                               group['betas'], group['eps'], group['weight_decay'], grad_scale)
+                by_step.setdefault(st['step'], []).append((p.data, p.grad.contiguous(), st['exp_avg'], st['exp_avg_sq']))
+            for step, items in by_step.items():      # normally one entry: every parameter has taken the same number of steps
+                ps, gs, ms, vs = zip(*items)
+                ops.adam_step_multi_(ps, gs, ms, vs, step, group['lr'], group['betas'], group['eps'], group['weight_decay'], grad_scale)
         return loss

@@ -233,6 +233,11 @@ int avid_filter_to_tapmajor(const float* w_oihw, float* w_tap, float* w_tap_t, i
 /* tap-major [taps, ci_pad, co] (a filter gradient) -> PyTorch layout [co, ci, taps] */
 int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int32_t ci, int32_t taps, int32_t ci_pad, void* stream);
 
+/* PyTorch filter [co, ci, taps] fp32 -> the bf16 (hi, lo) planes of both tensor-core operand layouts in one pass:
+ * forward planes [taps][co][ci], dgrad planes [taps][ci][co] (lo planes NULL for single-pass bf16) */
+int avid_filter_to_planes(const float* w_oihw, void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, int32_t co, int32_t ci, int32_t taps,
+                          void* stream);
+
 /* [n, c, thw] -> [n, thw, c_pad] (c_pad > c only for c <= 4: the 3-channel clip / 1-channel spectrogram)
  * and back [n, thw, c] -> [n, c, thw] */
 int avid_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int64_t thw, int32_t c_pad, void* stream);
@@ -294,6 +299,13 @@ int avid_add_inplace(float* a, const float* b, int64_t n, void* stream);   /* a 
  * (1/world_size after a sum all-reduce). */
 int avid_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
+/* the same update for `count` tensors given as HOST arrays of device pointers / element counts (32 tensors per launch) */
+int avid_adam_step_multi(float* const* params_host, const float* const* grads_host, float* const* exp_avgs_host, float* const* exp_avg_sqs_host,
+                         const int64_t* sizes_host, int32_t count, int64_t step, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, float grad_scale, void* stream);
+/* cudaMemsetAsync(p, 0, bytes): one call zeroes the per-step arena of accumulators (filter gradients, BatchNorm sums) */
+int avid_zero_bytes(void* p, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -173,6 +173,33 @@ def test_adam_step_matches_torch():
         _close(p, ref, 1e-5, 1e-7)
 
 
+def test_adam_multi_tensor_matches_torch():
+    """avid_adam_step_multi over 70 tensors of ragged sizes (3 launches of <= 32 tensors) == torch.optim.Adam."""
+    from avid_cma_b200 import optim
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 4096, 4097, 64 * 64 * 9, 512] * 11 + [100003, 3, 12289, 5]
+    ours = [torch.randn(n, generator=g).to(DEV).requires_grad_(True) for n in sizes]
+    ref = [p.detach().clone().requires_grad_(True) for p in ours]
+    o1, o2 = optim.Adam(ours, lr=2e-4, weight_decay=1e-5), torch.optim.Adam(ref, lr=2e-4, weight_decay=1e-5)
+    for _ in range(3):
+        for a, b in zip(ours, ref):
+            a.grad = torch.randn(a.shape, generator=g).to(DEV)
+            b.grad = a.grad.clone()
+        o1.step()
+        o2.step()
+    for a, b in zip(ours, ref):
+        _close(a, b, 1e-5, 1e-7)
+
+
+def test_filter_to_planes_matches_tapmajor_split():
+    from avid_cma_b200 import ops
+    w = torch.randn(128, 64, 1, 3, 3, generator=torch.Generator().manual_seed(2)).to(DEV)
+    (f_hi, f_lo), (d_hi, d_lo) = ops.filter_to_planes(w)
+    w_tap, w_tap_t = ops.filter_to_tapmajor(w)
+    for got, want in ((f_hi, f_lo), ops.split_bf16(w_tap_t)), ((d_hi, d_lo), ops.split_bf16(w_tap)):
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
 def _load_model(seed=0, math="fp32"):
     from avid_cma_b200 import models
     from avid_cma_b200.models._tower import _MATH
