@@ -79,6 +79,9 @@ _SIGNATURES = {
     "avid_bn_relu_backward_apply_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _P]),
     "avid_bn_relu_backward_reduce": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "avid_bn_relu_backward_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),
+    "avid_bn_relu_maxpool_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "avid_bn_relu_maxpool_backward_reduce": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "avid_bn_relu_maxpool_backward_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "avid_maxpool_1x3x3_forward": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "avid_maxpool_1x3x3_backward": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "avid_global_maxpool_forward": (C.c_int, [_P, _P, _P, _I, _L, _I, _P]),

@@ -4,16 +4,55 @@
 // square root, running statistics updated with the unbiased variance.  Sums are accumulated in
 // fp64 so the statistics do not depend on the (atomic) summation order to fp32 precision.
 #include <cuda_bf16.h>
+#include <math.h>
 #include "common.cuh"
 
 namespace avid {
 
+// The video stem is conv -> BN -> ReLU -> MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (models/video.py:20-23).  In the fused path the
+// ReLU output is never written: the forward pools relu(bn(z)) on the fly and records the winning window position; the
+// backward kernels obtain "dy" (the gradient at the ReLU output) by gathering the pooled gradient through that argmax.
+struct PoolGather {
+    const uint8_t* argmax;      // [nt, ho, wo, c] winning position dh*3+dw, or nullptr: dy is a plain tensor
+    const float* dyp;           // [nt, ho, wo, c] gradient at the pooled output
+    int h, w, ho, wo;
+    const float* z;             // [nt, h, w, c] conv output (only read by the pooled reduce when gamma == 0)
+};
+
+// gradient at the (unpooled) pixel `row` = (img * h + ih) * w + iw, channels 4*lane_c .. 4*lane_c+3.  32-bit index arithmetic
+// (the host checks that the tensor has fewer than 2^31 float4): 64-bit divisions by run-time extents cost more than the loads.
+__device__ __forceinline__ float4 pool_gather(const PoolGather& g, uint32_t row, int lane_c, int c4) {
+    const uint32_t r = row / (uint32_t)g.w;
+    const int iw = (int)(row - r * (uint32_t)g.w);
+    const uint32_t img = r / (uint32_t)g.h;
+    const int ih = (int)(r - img * (uint32_t)g.h);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int oh0 = ih >> 1, oh1 = min((ih + 1) >> 1, g.ho - 1), ow0 = iw >> 1, ow1 = min((iw + 1) >> 1, g.wo - 1);
+    for (int oh = oh0; oh <= oh1; ++oh)
+        for (int ow = ow0; ow <= ow1; ++ow) {
+            const uint32_t oi = ((img * (uint32_t)g.ho + oh) * (uint32_t)g.wo + ow) * (uint32_t)c4 + lane_c;
+            const uint32_t pos = (uint32_t)((ih - (oh * 2 - 1)) * 3 + (iw - (ow * 2 - 1)));
+            const uchar4 am = __ldg(reinterpret_cast<const uchar4*>(g.argmax) + oi);
+            if (am.x != pos && am.y != pos && am.z != pos && am.w != pos) continue;
+            const float4 d = __ldg(reinterpret_cast<const float4*>(g.dyp) + oi);
+            if (am.x == pos) o.x += d.x;
+            if (am.y == pos) o.y += d.y;
+            if (am.z == pos) o.z += d.z;
+            if (am.w == pos) o.w += d.w;
+        }
+    return o;
+}
+
 // one thread = one float4 of channels, striding over rows; blockDim.x = 256
-template <bool BACKWARD>
+// MODE 0: forward statistics of x.  MODE 1: backward sums (sum g, sum g*xhat), g = dy * relu'(bn(x)).  MODE 2: the same sums for a
+// pooled layer, computed from the POOLED tensors only (x = pooled output p, dy = its gradient): g is non-zero only at window
+// maxima, where y = p, so relu'(y) = [p > 0] and xhat = (p - beta) / gamma -- a pass over 1/4 of the elements, no gather.
+template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        int64_t rows, int c, int64_t rows_per_block, double* __restrict__ out) {
+                                                        int64_t rows, int c, int64_t rows_per_block, double* __restrict__ out,
+                                                        const PoolGather pool) {
     extern __shared__ double s_red[];   // [2][rpi][c]  (rpi = row groups per iteration)
     const int c4 = c >> 2;
     const int rpi = 256 / c4;                    // c4 <= 256 and divides 256 (c in 64..1024, power of two)
@@ -22,7 +61,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     const int64_t r1 = min(rows, r0 + rows_per_block);
     double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
     float mu[4], is[4], ga[4], be[4];
-    if (BACKWARD) {
+    if (MODE != 0) {
         *reinterpret_cast<float4*>(mu) = reinterpret_cast<const float4*>(mean)[lane_c];
         *reinterpret_cast<float4*>(is) = reinterpret_cast<const float4*>(invstd)[lane_c];
         *reinterpret_cast<float4*>(ga) = reinterpret_cast<const float4*>(gamma)[lane_c];
@@ -31,13 +70,13 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     for (int64_t r = r0 + rg; r < r1; r += rpi) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * c) + lane_c);
         const float xv[4] = {v.x, v.y, v.z, v.w};
-        if (!BACKWARD) {
+        if (MODE == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 a0[j] += (double)xv[j];
                 a1[j] += (double)xv[j] * (double)xv[j];
             }
-        } else {
+        } else if (MODE == 1) {
             const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * c) + lane_c);
             const float dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -46,6 +85,25 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
                 const float g = (xh * ga[j] + be[j]) > 0.f ? dv[j] : 0.f;   // relu'(bn(x))
                 a0[j] += (double)g;
                 a1[j] += (double)g * (double)xh;
+            }
+        } else {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * c) + lane_c);
+            const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!(xv[j] > 0.f)) continue;                               // relu'(y) at the window maximum
+                float xh;
+                if (ga[j] != 0.f) {
+                    xh = (xv[j] - be[j]) / ga[j];
+                } else {        // degenerate affine: recover xhat from the conv output at the recorded argmax
+                    const uint32_t rr = (uint32_t)r, r2 = rr / (uint32_t)pool.wo, img = r2 / (uint32_t)pool.ho;
+                    const int ow = (int)(rr - r2 * (uint32_t)pool.wo), oh = (int)(r2 - img * (uint32_t)pool.ho);
+                    const int am = pool.argmax[(size_t)r * c + lane_c * 4 + j];
+                    const int ih = oh * 2 - 1 + am / 3, iw = ow * 2 - 1 + am % 3;
+                    xh = (pool.z[(((size_t)img * pool.h + ih) * pool.w + iw) * c + lane_c * 4 + j] - mu[j]) * is[j];
+                }
+                a0[j] += (double)dv[j];
+                a1[j] += (double)dv[j] * (double)xh;
             }
         }
     }
@@ -131,12 +189,56 @@ __global__ void __launch_bounds__(256) bn_relu_forward_kernel(const float* __res
     }
 }
 
+// pooled[nt, ho, wo, c] = max over the 3x3 / stride 2 / pad 1 window of relu(z * scale + shift); one thread per float4 of
+// pooled channels (its four channels are the same in every grid-stride iteration)
+__global__ void __launch_bounds__(256) bn_relu_maxpool_forward_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, float* __restrict__ p,
+                                                                      __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo,
+                                                                      uint8_t* __restrict__ argmax, int nt, int h, int w, int c4, int ho, int wo) {
+    const int64_t total = (int64_t)nt * ho * wo * c4;
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int cc = (int)(i0 % c4);
+    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(scale) + cc);
+    const float4 sh4 = __ldg(reinterpret_cast<const float4*>(shift) + cc);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+    for (int64_t i = i0; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t r = (uint32_t)i / (uint32_t)c4;                 // 32-bit index arithmetic: the host checks the tensor size
+        const uint32_t r1 = r / (uint32_t)wo;
+        const int ow = (int)(r - r1 * (uint32_t)wo);
+        const uint32_t img = r1 / (uint32_t)ho;
+        const int oh = (int)(r1 - img * (uint32_t)ho);
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        uint8_t am[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh) {
+            const int ih = oh * 2 - 1 + dh;
+            if (ih < 0 || ih >= h) continue;
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+                const int iw = ow * 2 - 1 + dw;
+                if (iw < 0 || iw >= w) continue;
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(z) + ((img * (uint32_t)h + ih) * (uint32_t)w + iw) * (uint32_t)c4 + cc);
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float y = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+                    if (y > m[j]) { m[j] = y; am[j] = (uint8_t)(dh * 3 + dw); }      // strictly greater keeps the first maximum
+                }
+            }
+        }
+        if (p) reinterpret_cast<float4*>(p)[i] = make_float4(m[0], m[1], m[2], m[3]);
+        if (p_hi) store_planes(p_hi, p_lo, i, m);
+        if (argmax) reinterpret_cast<uchar4*>(argmax)[i] = make_uchar4(am[0], am[1], am[2], am[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      const double* __restrict__ sums, int64_t rows, int c,
                                                                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
-                                                                     __nv_bfloat16* __restrict__ dx_lo, float* dgamma, float* dbeta) {
+                                                                     __nv_bfloat16* __restrict__ dx_lo, float* dgamma, float* dbeta,
+                                                                     const PoolGather pool) {
     const int c4 = c >> 2;
     const int64_t n4 = rows * c4;
     const float inv_n = 1.0f / (float)rows;
@@ -160,9 +262,15 @@ __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float
     for (int64_t i = i0; i < n4; i += 2 * stride) {
         const bool two = i + stride < n4;
         const float4 va = __ldg(reinterpret_cast<const float4*>(x) + i);
-        const float4 da = __ldg(reinterpret_cast<const float4*>(dy) + i);
         const float4 vb = two ? __ldg(reinterpret_cast<const float4*>(x) + i + stride) : va;
-        const float4 db = two ? __ldg(reinterpret_cast<const float4*>(dy) + i + stride) : da;
+        float4 da, db;
+        if (pool.argmax) {
+            da = pool_gather(pool, (uint32_t)i / (uint32_t)c4, cc, c4);
+            db = two ? pool_gather(pool, (uint32_t)(i + stride) / (uint32_t)c4, cc, c4) : da;
+        } else {
+            da = __ldg(reinterpret_cast<const float4*>(dy) + i);
+            db = two ? __ldg(reinterpret_cast<const float4*>(dy) + i + stride) : da;
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !two) break;
@@ -194,9 +302,9 @@ static unsigned ew_grid(int64_t n4) {
     return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
-template <bool BACKWARD>
+template <int MODE>
 static int launch_reduce(const float* x, const float* dy, const float* mean, const float* invstd, const float* gamma,
-                         const float* beta, int64_t rows, int c, double* out, cudaStream_t st) {
+                         const float* beta, int64_t rows, int c, double* out, cudaStream_t st, const PoolGather pool = PoolGather{}) {
     const int c4 = c >> 2, rpi = 256 / c4;
     int64_t blocks = 8 * kNumSMs;
     int64_t rpb = (rows + blocks - 1) / blocks;
@@ -204,8 +312,8 @@ static int launch_reduce(const float* x, const float* dy, const float* mean, con
     if (rpb < min_rpb) rpb = min_rpb;
     blocks = (rows + rpb - 1) / rpb;
     const size_t smem = sizeof(double) * 2 * rpi * c;   // = 2 * 256 * 4 * 8 = 16 KB
-    bn_reduce_kernel<BACKWARD><<<(unsigned)blocks, 256, smem, st>>>(x, dy, mean, invstd, gamma, beta, rows, c, rpb, out);
-    return check_launch(BACKWARD ? "bn_reduce_kernel<bwd>" : "bn_reduce_kernel<fwd>");
+    bn_reduce_kernel<MODE><<<(unsigned)blocks, 256, smem, st>>>(x, dy, mean, invstd, gamma, beta, rows, c, rpb, out, pool);
+    return check_launch(MODE == 0 ? "bn_reduce_kernel<fwd>" : (MODE == 1 ? "bn_reduce_kernel<bwd>" : "bn_reduce_kernel<pooled bwd>"));
 }
 
 }  // namespace avid
@@ -218,7 +326,7 @@ int avid_bn_stats(const float* x, int64_t rows, int32_t c, double* stats, void* 
     int rc = check_bn_shape(rows, c);
     if (rc) return rc;
     AVID_REQUIRE(x && stats, "bn_stats: NULL pointer");
-    return launch_reduce<false>(x, nullptr, nullptr, nullptr, nullptr, nullptr, rows, c, stats, static_cast<cudaStream_t>(stream));
+    return launch_reduce<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, rows, c, stats, static_cast<cudaStream_t>(stream));
 }
 
 int avid_bn_finalize(const double* stats, int64_t rows, int32_t c, const float* gamma, const float* beta,
@@ -255,7 +363,7 @@ int avid_bn_relu_backward_reduce(const float* x, const float* dy, const float* m
     int rc = check_bn_shape(rows, c);
     if (rc) return rc;
     AVID_REQUIRE(x && dy && mean && invstd && gamma && beta && sums, "bn_relu_backward_reduce: NULL pointer");
-    return launch_reduce<true>(x, dy, mean, invstd, gamma, beta, rows, c, sums, static_cast<cudaStream_t>(stream));
+    return launch_reduce<1>(x, dy, mean, invstd, gamma, beta, rows, c, sums, static_cast<cudaStream_t>(stream));
 }
 
 int avid_bn_relu_backward_apply_ex(const float* x, const float* dy, const float* mean, const float* invstd,
@@ -266,8 +374,51 @@ int avid_bn_relu_backward_apply_ex(const float* x, const float* dy, const float*
     AVID_REQUIRE(x && dy && mean && invstd && gamma && beta && sums && (dx || dx_hi), "bn_relu_backward_apply: NULL pointer");
     AVID_REQUIRE(dx_hi || !dx_lo, "bn_relu_backward_apply: a lo plane needs the hi plane");
     bn_relu_backward_apply_kernel<<<ew_grid(rows * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, dy, mean, invstd, gamma, beta, sums, rows, c, dx, static_cast<__nv_bfloat16*>(dx_hi), static_cast<__nv_bfloat16*>(dx_lo), dgamma, dbeta);
+        x, dy, mean, invstd, gamma, beta, sums, rows, c, dx, static_cast<__nv_bfloat16*>(dx_hi), static_cast<__nv_bfloat16*>(dx_lo), dgamma, dbeta,
+        PoolGather{});
     return check_launch("bn_relu_backward_apply_kernel");
+}
+
+static int check_pool_shape(int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo) {
+    AVID_REQUIRE(nt > 0 && h > 0 && w > 0, "bn_relu_maxpool: bad extents");
+    AVID_REQUIRE(ho == (h + 2 - 3) / 2 + 1 && wo == (w + 2 - 3) / 2 + 1, "bn_relu_maxpool: pooled extent mismatch");
+    AVID_REQUIRE((int64_t)nt * h * w * (c / 4) < ((int64_t)1 << 31), "bn_relu_maxpool: tensor too large for 32-bit indexing");
+    return check_bn_shape((int64_t)nt * h * w, c);
+}
+
+int avid_bn_relu_maxpool_forward(const float* z, const float* scale, const float* shift, float* p, void* p_hi, void* p_lo, uint8_t* argmax,
+                                 int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream) {
+    int rc = check_pool_shape(nt, h, w, c, ho, wo);
+    if (rc) return rc;
+    AVID_REQUIRE(z && scale && shift && (p || p_hi), "bn_relu_maxpool_forward: NULL pointer");
+    AVID_REQUIRE(p_hi || !p_lo, "bn_relu_maxpool_forward: a lo plane needs the hi plane");
+    bn_relu_maxpool_forward_kernel<<<ew_grid((int64_t)nt * ho * wo * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, scale, shift, p, static_cast<__nv_bfloat16*>(p_hi), static_cast<__nv_bfloat16*>(p_lo), argmax, nt, h, w, c >> 2, ho, wo);
+    return check_launch("bn_relu_maxpool_forward_kernel");
+}
+
+int avid_bn_relu_maxpool_backward_reduce(const float* z, const float* pooled, const uint8_t* argmax, const float* dyp, const float* mean,
+                                         const float* invstd, const float* gamma, const float* beta, int32_t nt, int32_t h, int32_t w, int32_t c,
+                                         int32_t ho, int32_t wo, double* sums, void* stream) {
+    int rc = check_pool_shape(nt, h, w, c, ho, wo);
+    if (rc) return rc;
+    AVID_REQUIRE(z && pooled && argmax && dyp && mean && invstd && gamma && beta && sums, "bn_relu_maxpool_backward_reduce: NULL pointer");
+    return launch_reduce<2>(pooled, dyp, mean, invstd, gamma, beta, (int64_t)nt * ho * wo, c, sums, static_cast<cudaStream_t>(stream),
+                            PoolGather{argmax, dyp, h, w, ho, wo, z});
+}
+
+int avid_bn_relu_maxpool_backward_apply(const float* z, const uint8_t* argmax, const float* dyp, const float* mean, const float* invstd,
+                                        const float* gamma, const float* beta, const double* sums, int32_t nt, int32_t h, int32_t w, int32_t c,
+                                        int32_t ho, int32_t wo, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, void* stream) {
+    int rc = check_pool_shape(nt, h, w, c, ho, wo);
+    if (rc) return rc;
+    AVID_REQUIRE(z && argmax && dyp && mean && invstd && gamma && beta && sums && (dz || dz_hi), "bn_relu_maxpool_backward_apply: NULL pointer");
+    AVID_REQUIRE(dz_hi || !dz_lo, "bn_relu_maxpool_backward_apply: a lo plane needs the hi plane");
+    const int64_t rows = (int64_t)nt * h * w;
+    bn_relu_backward_apply_kernel<<<ew_grid(rows * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, nullptr, mean, invstd, gamma, beta, sums, rows, c, dz, static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), dgamma,
+        dbeta, PoolGather{argmax, dyp, h, w, ho, wo, z});
+    return check_launch("bn_relu_backward_apply_kernel(pool)");
 }
 
 int avid_bn_relu_backward_apply(const float* x, const float* dy, const float* mean, const float* invstd,

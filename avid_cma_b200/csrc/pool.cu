@@ -16,11 +16,12 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
                                                           int nt, int h, int w, int c4, int ho, int wo) {
     const int64_t total = (int64_t)nt * ho * wo * c4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c4);
-        int64_t r = i / c4;
-        const int ow = (int)(r % wo);  r /= wo;
-        const int oh = (int)(r % ho);
-        const int64_t img = r / ho;
+        const uint32_t r0 = (uint32_t)i / (uint32_t)c4;          // 32-bit index arithmetic (size checked by the host)
+        const int cc = (int)((uint32_t)i - r0 * (uint32_t)c4);
+        const uint32_t r1 = r0 / (uint32_t)wo;
+        const int ow = (int)(r0 - r1 * (uint32_t)wo);
+        const uint32_t img = r1 / (uint32_t)ho;
+        const int oh = (int)(r1 - img * (uint32_t)ho);
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         uint8_t am[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -53,11 +54,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restr
                                                           float* __restrict__ dx, int nt, int h, int w, int c4, int ho, int wo) {
     const int64_t total = (int64_t)nt * h * w * c4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c4);
-        int64_t r = i / c4;
-        const int iw = (int)(r % w);  r /= w;
-        const int ih = (int)(r % h);
-        const int64_t img = r / h;
+        const uint32_t r0 = (uint32_t)i / (uint32_t)c4;
+        const int cc = (int)((uint32_t)i - r0 * (uint32_t)c4);
+        const uint32_t r1 = r0 / (uint32_t)w;
+        const int iw = (int)(r0 - r1 * (uint32_t)w);
+        const uint32_t img = r1 / (uint32_t)h;
+        const int ih = (int)(r1 - img * (uint32_t)h);
         float o[4] = {0.f, 0.f, 0.f, 0.f};
         for (int oh = ih >> 1; oh <= ((ih + 1) >> 1) && oh < ho; ++oh)
             for (int ow = iw >> 1; ow <= ((iw + 1) >> 1) && ow < wo; ++ow) {
@@ -114,6 +116,7 @@ extern "C" {
 int avid_maxpool_1x3x3_forward(const float* x, float* y, uint8_t* argmax, int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo,
                                void* stream) {
     AVID_REQUIRE(x && y && nt > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool_forward: bad arguments");
+    AVID_REQUIRE((int64_t)nt * h * w * (c / 4) < ((int64_t)1 << 31), "maxpool_forward: tensor too large for 32-bit indexing");
     AVID_REQUIRE(ho == (h + 2 - 3) / 2 + 1 && wo == (w + 2 - 3) / 2 + 1, "maxpool_forward: output extent mismatch");
     maxpool_fwd_kernel<<<grid_for((int64_t)nt * ho * wo * (c / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, argmax, nt, h, w, c / 4, ho, wo);
     return check_launch("maxpool_fwd_kernel");
@@ -122,6 +125,7 @@ int avid_maxpool_1x3x3_forward(const float* x, float* y, uint8_t* argmax, int32_
 int avid_maxpool_1x3x3_backward(const uint8_t* argmax, const float* dy, float* dx,
                                 int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream) {
     AVID_REQUIRE(argmax && dy && dx && nt > 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, "maxpool_backward: bad arguments");
+    AVID_REQUIRE((int64_t)nt * h * w * (c / 4) < ((int64_t)1 << 31), "maxpool_backward: tensor too large for 32-bit indexing");
     AVID_REQUIRE(ho == (h + 2 - 3) / 2 + 1 && wo == (w + 2 - 3) / 2 + 1, "maxpool_backward: output extent mismatch");
     maxpool_bwd_kernel<<<grid_for((int64_t)nt * h * w * (c / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(argmax, dy, dx, nt, h, w, c / 4, ho, wo);
     return check_launch("maxpool_bwd_kernel");

@@ -114,9 +114,10 @@ class ConvBNReLU:
     """conv -> train/eval BatchNorm -> ReLU, with an optional residual addend fused into the conv epilogue."""
 
     @staticmethod
-    def forward(x, conv, bn, training, math, addend=None, out_f32=False, op=None, out_planes=None):
+    def forward(x, conv, bn, training, math, addend=None, out_f32=False, op=None, out_planes=None, pool=False):
         """x: Act.  Returns (y: Act, saved).  In the tensor-core modes y carries the bf16 planes the next
-        convolution reads (plus fp32 when `out_f32`: block outputs feed residual adds and pools)."""
+        convolution reads (plus fp32 when `out_f32`: block outputs feed residual adds and pools).  `pool`: y is
+        additionally max-pooled (1,3,3)/(1,2,2) in the same kernel (the video stem); the ReLU output is not stored."""
         if op is None:
             op = ConvOp(conv, x.shape, math)
         if training:
@@ -133,6 +134,9 @@ class ConvBNReLU:
             st.scale.copy_(bn.weight.detach() * st.invstd)
             st.shift.copy_(bn.bias.detach() - bn.running_mean * st.scale)
         planes = math != ops.MATH_FP32 if out_planes is None else out_planes
+        if pool:
+            y, amax = ops.bn_relu_maxpool_forward(z, st.scale, st.shift, want_f32=True, want_planes=planes, x3=math == ops.MATH_BF16X3)
+            return y, (op, x, z, st, bn, amax, y.f32)
         y = ops.bn_relu_forward_act(z, st.scale, st.shift, want_f32=out_f32 or not planes, want_planes=planes, x3=math == ops.MATH_BF16X3)
         return y, (op, x, z, st, bn)
 
@@ -140,10 +144,14 @@ class ConvBNReLU:
     def backward(dy, saved, grads, need_dx=True, dx_addend=None, dz_f32=False):
         """dy: fp32 gradient at the ReLU output.  Returns (dx fp32 or None, dz: Act at the conv output, i.e. after
         the residual sum)."""
-        op, x, z, st, bn = saved
+        op, x, z, st, bn = saved[:5]
         want_f32 = dz_f32 or not op.tc or (need_dx and op.needs_f32_dz())
-        dz, dgamma, dbeta = ops.bn_relu_backward_act(z, dy, st, bn.weight.detach(), bn.bias.detach(), want_f32=want_f32,
-                                                     want_planes=op.tc, x3=op.x3)
+        if len(saved) > 5:      # pooled layer: dy is the gradient at the pooled output
+            dz, dgamma, dbeta = ops.bn_relu_maxpool_backward_act(z, saved[6], saved[5], dy, st, bn.weight.detach(), bn.bias.detach(),
+                                                                 want_f32=want_f32, want_planes=op.tc, x3=op.x3)
+        else:
+            dz, dgamma, dbeta = ops.bn_relu_backward_act(z, dy, st, bn.weight.detach(), bn.bias.detach(), want_f32=want_f32,
+                                                         want_planes=op.tc, x3=op.x3)
         grads[bn.weight], grads[bn.bias] = dgamma, dbeta
         grads[op.conv.weight] = op.wgrad(x, dz)
         dx = op.dgrad(dz, addend=dx_addend) if need_dx else None

@@ -48,18 +48,16 @@ class R2Plus1D(TowerMixin, nn.Module):
 
     def _fwd(self, x, training, math, taps=None):
         """x (B,3,T,H,W) -> pooled (B,512); saved record for _bwd.  `taps` collects channels-last stage outputs."""
+        # stem: conv -> BN -> ReLU -> max pool, the last three in one kernel (the ReLU output is never stored)
         if math == ops.MATH_FP32:
             xc = Act(ops.nchw_to_nhwc(x, c_pad=pad_channels(x.shape[1])))
-            ya, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32)   # CUDA-core kernel
-        else:   # Cin = 3: the Toeplitz-view tcgen05 stem kernel; its output only feeds the max pool (fp32)
+            h, s_stem = ConvBNReLU.forward(xc, self.conv1[0], self.conv1[1], training, ops.MATH_FP32, pool=True)   # CUDA-core kernel
+        else:   # Cin = 3: the Toeplitz-view tcgen05 stem kernel
             op = StemOp(self.conv1[0], x.shape, math)
-            ya, s_stem = ConvBNReLU.forward(op.pack(x), self.conv1[0], self.conv1[1], training, math, out_f32=True, op=op, out_planes=False)
-        y = ya.f32
-        p, pool_argmax = ops.maxpool_1x3x3_forward(y)
+            h, s_stem = ConvBNReLU.forward(op.pack(x), self.conv1[0], self.conv1[1], training, math, out_f32=True, op=op, pool=True)
         if taps is not None:
-            taps['conv1'] = p
+            taps['conv1'] = h.f32
         saved_blocks = []
-        h = Act(p)
         for name, blocks in self._stages():
             for blk in blocks:
                 h, sb = blk._fwd(h, training, math)
@@ -67,12 +65,11 @@ class R2Plus1D(TowerMixin, nn.Module):
             if taps is not None:
                 taps[name] = h.f32
         pooled, argmax = ops.global_maxpool_forward(h.f32)
-        return pooled, (s_stem, tuple(y.shape), pool_argmax, saved_blocks, argmax, tuple(h.shape))
+        return pooled, (s_stem, saved_blocks, argmax, tuple(h.shape))
 
     def _bwd(self, dpooled, saved, grads, math):
-        s_stem, yshape, pool_argmax, saved_blocks, argmax, hshape = saved
+        s_stem, saved_blocks, argmax, hshape = saved
         d = ops.global_maxpool_backward(dpooled, argmax, hshape)
         for blk, sb in reversed(saved_blocks):
             d = blk._bwd(d, sb, grads)
-        dy = ops.maxpool_1x3x3_backward(pool_argmax, d, yshape)
-        ConvBNReLU.backward(dy, s_stem, grads, need_dx=False)
+        ConvBNReLU.backward(d, s_stem, grads, need_dx=False)

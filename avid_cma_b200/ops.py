@@ -483,6 +483,39 @@ def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=No
     return Act(dx if want_f32 else None, hi, lo), dgamma, dbeta
 
 
+def bn_relu_maxpool_forward(z, scale, shift, want_f32, want_planes, x3):
+    """maxpool_1x3x3(relu(z * scale + shift)) without materialising the ReLU output.  z (n, t, h, w, c).
+    Returns (Act of the pooled tensor (n, t, ho, wo, c), argmax uint8)."""
+    n, t, h, w, c = z.shape
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    shape = (n, t, ho, wo, c)
+    p = torch.empty(shape, dtype=torch.float32, device=z.device) if want_f32 else None
+    hi = torch.empty(shape, dtype=torch.bfloat16, device=z.device) if want_planes else None
+    lo = torch.empty(shape, dtype=torch.bfloat16, device=z.device) if want_planes and x3 else None
+    am = torch.empty(shape, dtype=torch.uint8, device=z.device)
+    check(_lib.lib().avid_bn_relu_maxpool_forward(_p(z), _p(scale), _p(shift), _p(p, optional=True), _p(hi, torch.bfloat16, optional=True),
+                                                  _p(lo, torch.bfloat16, optional=True), _p(am, torch.uint8), n * t, h, w, c, ho, wo, _stream()))
+    return Act(p, hi, lo), am
+
+
+def bn_relu_maxpool_backward_act(z, pooled, argmax, dyp, s, gamma, beta, want_f32, want_planes, x3):
+    """Backward of pooled = maxpool(relu(bn_train(z))): the gradient w.r.t. z as an Act, dgamma, dbeta."""
+    n, t, h, w, c = z.shape
+    ho, wo = argmax.shape[2], argmax.shape[3]
+    sums = _zeros((2, c), torch.float64, z.device)
+    dz = torch.empty_like(z) if want_f32 else None
+    hi = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device) if want_planes else None
+    lo = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device) if want_planes and x3 else None
+    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+    L = _lib.lib()
+    common = (_p(z), _p(argmax, torch.uint8), _p(dyp), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta))
+    check(L.avid_bn_relu_maxpool_backward_reduce(_p(z), _p(pooled), *common[1:], n * t, h, w, c, ho, wo, _p(sums, torch.float64), _stream()))
+    check(L.avid_bn_relu_maxpool_backward_apply(*common, _p(sums, torch.float64), n * t, h, w, c, ho, wo, _p(dz, optional=True),
+                                                _p(hi, torch.bfloat16, optional=True), _p(lo, torch.bfloat16, optional=True),
+                                                _p(dgamma), _p(dbeta), _stream()))
+    return Act(dz, hi, lo), dgamma, dbeta
+
+
 def maxpool_1x3x3_forward(x, need_argmax=True):
     """x (n, t, h, w, c) -> (y (n, t, ho, wo, c), argmax uint8 (n, t, ho, wo, c) or None)."""
     n, t, h, w, c = x.shape

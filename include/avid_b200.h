@@ -270,6 +270,20 @@ int avid_bn_relu_backward_apply_ex(const float* x, const float* dy, const float*
                                    const float* gamma, const float* beta, const double* sums,
                                    int64_t rows, int32_t c, float* dx, void* dx_hi, void* dx_lo, float* dgamma, float* dbeta, void* stream);
 
+/* Fused BatchNorm -> ReLU -> MaxPool3d((1,3,3),(1,2,2),(0,1,1)) of the video stem (video.py:21-23): the ReLU output
+ * [nt, h, w, c] is never materialised.  forward: pooled = maxpool(relu(z*scale + shift)) as fp32 and / or bf16 planes, plus
+ * the winning window position per pooled element; backward: the gradient at the ReLU output is gathered from the pooled
+ * gradient dyp [nt, ho, wo, c] through that argmax inside the BatchNorm backward apply kernel; the backward reduce needs only
+ * the pooled tensors (the gradient is non-zero at window maxima only, where y = pooled and xhat = (pooled - beta) / gamma). */
+int avid_bn_relu_maxpool_forward(const float* z, const float* scale, const float* shift, float* pooled, void* pooled_hi, void* pooled_lo,
+                                 uint8_t* argmax, int32_t nt, int32_t h, int32_t w, int32_t c, int32_t ho, int32_t wo, void* stream);
+int avid_bn_relu_maxpool_backward_reduce(const float* z, const float* pooled, const uint8_t* argmax, const float* dyp, const float* mean,
+                                         const float* invstd, const float* gamma, const float* beta, int32_t nt, int32_t h, int32_t w, int32_t c,
+                                         int32_t ho, int32_t wo, double* sums, void* stream);
+int avid_bn_relu_maxpool_backward_apply(const float* z, const uint8_t* argmax, const float* dyp, const float* mean, const float* invstd,
+                                        const float* gamma, const float* beta, const double* sums, int32_t nt, int32_t h, int32_t w, int32_t c,
+                                        int32_t ho, int32_t wo, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, void* stream);
+
 /* nn.MaxPool3d((1,3,3), stride (1,2,2), padding (0,1,1)) on [n*t, h, w, c] (video.py:23).  argmax (optional, one byte per
  * output element) records the winning window position dh*3+dw -- the first maximum in scan order, like ATen. */
 int avid_maxpool_1x3x3_forward(const float* x, float* y, uint8_t* argmax, int32_t nt, int32_t h, int32_t w, int32_t c,
