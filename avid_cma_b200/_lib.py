@@ -36,6 +36,10 @@ class NceArgs(C.Structure):
     ]
 
 
+class BnBackwardFuse(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("z", "mean", "invstd", "gamma", "beta", "sums")]
+
+
 class ConvShape(C.Structure):
     _fields_ = [(n, c_int32) for n in ("n", "ti", "hi", "wi", "ci", "to", "ho", "wo", "co", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw")]
 
@@ -62,7 +66,7 @@ _SIGNATURES = {
     "avid_conv_wgrad": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _I, _P]),
     "avid_split_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
     "avid_conv_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "avid_conv_dgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P]),
+    "avid_conv_dgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, C.POINTER(BnBackwardFuse), _P]),
     "avid_conv_wgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P]),
     "avid_stem_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "avid_stem_filter_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -63,13 +63,25 @@ struct TcConvParams {
     int Td, Hd, Wd, ot, oh, ow, rt, rh, rw;
 };
 
+// Optional fusion of the NEXT BatchNorm backward's reduction into an input-gradient launch: the tensor this launch writes is
+// the gradient dy at the ReLU output of the previous layer, whose BatchNorm backward needs sum(g) and sum(g * xhat) per
+// channel with g = dy * relu'(bn(z)), xhat = (z - mean) * invstd (z = that layer's conv output, same shape as dy).
+struct BnBwdFuse {
+    const float* z = nullptr;
+    const float* mean = nullptr;
+    const float* invstd = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    double* sums = nullptr;          // (2, channels) doubles, zeroed by the caller
+};
+
 template <int BN>
 struct TcSmem {
     static constexpr int kABytes = kBM * kBK * 2;   // 16 KB
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kStages = BN <= 64 ? 4 : 3;
-    static constexpr int kStatBytes = 4 * 2 * BN * 4;           // [4 epilogue warps][sum, sum of squares][BN] floats
+    static constexpr int kStatBytes = 4 * 2 * BN * 4 + BN * 16; // [4 epilogue warps][2 sums][BN] floats + [BN] float4 BatchNorm constants
     static constexpr int kBytes = kStages * kStageBytes + kStatBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -81,11 +93,12 @@ template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcConvParams p,
-               const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats) {
+               const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats, const BnBwdFuse fuse) {
     using S = TcSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* s_stat = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
+    float4* s_par = reinterpret_cast<float4*>(s_stat + 4 * 2 * BN);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kStatBytes);
     uint64_t* empty_bar = full_bar + S::kStages;
     uint64_t* tmem_full = empty_bar + S::kStages;     // [2]
@@ -203,6 +216,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
             }
             const size_t row = pix * p.cd + n0;
+            double* const acc_out = stats ? stats : fuse.sums;       // which per-channel sums this launch accumulates, if any
+            if (fuse.z) {       // BatchNorm constants of this tile's channels (the previous tile's readers passed the barrier below)
+                const int t = threadIdx.x - 64;
+                if (t < BN) s_par[t] = make_float4(__ldg(fuse.mean + n0 + t), __ldg(fuse.invstd + n0 + t), __ldg(fuse.gamma + n0 + t), __ldg(fuse.beta + n0 + t));
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll
@@ -228,29 +247,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         reinterpret_cast<float4*>(out + row + j * 32)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
                     }
                 }
-                if (stats) {
-                    // per-channel sum and sum of squares of the stored tile: fp32 within the tile, fp64 atomics across tiles
-                    float sq[32];
+                if (acc_out) {
+                    // per-channel sums over the tile's rows: fp32 within the tile, fp64 atomics across tiles.
+                    //   forward (stats):      sum(o), sum(o^2) of the stored output -> BatchNorm statistics
+                    //   input gradient (fuse): sum(g), sum(g * xhat) with g = o * relu'(bn(z)) -> the next BatchNorm backward
+                    float second[32];
+                    if (fuse.z) {
+                        float zr[32];
 #pragma unroll
-                    for (int v = 0; v < 32; ++v) {
-                        if (m >= p.M) o[v] = 0.f;
-                        sq[v] = o[v] * o[v];
+                        for (int v = 0; v < 8; ++v) {
+                            const float4 zz = m < p.M ? __ldg(reinterpret_cast<const float4*>(fuse.z + row + j * 32) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            zr[4 * v] = zz.x; zr[4 * v + 1] = zz.y; zr[4 * v + 2] = zz.z; zr[4 * v + 3] = zz.w;
+                        }
+#pragma unroll
+                        for (int v = 0; v < 32; ++v) {
+                            const float4 par = s_par[j * 32 + v];           // mean, invstd, gamma, beta (warp-wide broadcast)
+                            const float xh = (zr[v] - par.x) * par.y;
+                            const float g = (m < p.M && fmaf(xh, par.z, par.w) > 0.f) ? o[v] : 0.f;
+                            o[v] = g;
+                            second[v] = g * xh;
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 32; ++v) {
+                            if (m >= p.M) o[v] = 0.f;
+                            second[v] = o[v] * o[v];
+                        }
                     }
-                    const float cs = warp_column_sums(o, lane), cq = warp_column_sums(sq, lane);
+                    const float cs = warp_column_sums(o, lane), cq = warp_column_sums(second, lane);
                     s_stat[(q * 2 + 0) * BN + j * 32 + lane] = cs;
                     s_stat[(q * 2 + 1) * BN + j * 32 + lane] = cq;
                 }
             }
-            if (stats) {
+            if (acc_out) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
                 const int t = threadIdx.x - 64;                      // 0..127
                 for (int i = t; i < 2 * BN; i += 128) {
                     const int which = i / BN, ch = i - which * BN;
                     const float tot = s_stat[(0 * 2 + which) * BN + ch] + s_stat[(1 * 2 + which) * BN + ch] + s_stat[(2 * 2 + which) * BN + ch] +
                                       s_stat[(3 * 2 + which) * BN + ch];
-                    atomicAdd(stats + (size_t)which * p.cd + n0 + ch, (double)tot);
+                    atomicAdd(acc_out + (size_t)which * p.cd + n0 + ch, (double)tot);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // s_stat is rewritten by the next tile
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // s_stat / s_par are rewritten by the next tile
             }
         }
     }
@@ -472,7 +510,8 @@ static int encode_tiled_2d(CUtensorMap* map, const void* base, uint64_t rows, ui
 }
 
 template <int BN>
-static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const float* addend, float* out, double* stats, cudaStream_t st) {
+static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const float* addend, float* out, double* stats, const BnBwdFuse& fuse,
+                          cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kBytes);
@@ -481,7 +520,7 @@ static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const 
     }
     const int tiles = ((p.M + kBM - 1) / kBM) * (p.cd / BN);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    conv_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats);
+    conv_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
     return check_launch("conv_tc_kernel");
 }
 
@@ -528,8 +567,10 @@ static DimPlan plan_dgrad(int dst, int src, int k, int s, int pad, int r) {
 // dgrad == 1: out[n,ti,hi,wi,ci] = conv_transpose(dout, filt); a_* = dout planes, b_* = filter planes [taps][ci][co].  A strided
 //             input gradient is one launch per stride-parity class (st * sh * sw of them), each a stride-1 correlation.
 int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
-                const float* addend, float* out, double* stats, cudaStream_t st) {
+                const float* addend, float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
     AVID_REQUIRE(s && a_hi && b_hi && out, "conv_tc: NULL pointer");
+    AVID_REQUIRE(!(stats && fuse.z), "conv_tc: forward statistics and the fused BatchNorm backward reduction are exclusive");
+    AVID_REQUIRE(!fuse.z || (fuse.mean && fuse.invstd && fuse.gamma && fuse.beta && fuse.sums), "conv_tc: incomplete BatchNorm fusion arguments");
     AVID_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "conv_tc: give both lo planes (bf16x3) or neither (bf16)");
     AVID_REQUIRE(s->kt >= 1 && s->kh >= 1 && s->kw >= 1 && s->kt <= 8 && s->kh <= 8 && s->kw <= 8 && s->kt * s->kh * s->kw <= kMaxTaps,
                  "conv_tc: filter %dx%dx%d not supported (at most 8 per dimension, %d taps)", s->kt, s->kh, s->kw, kMaxTaps);
@@ -604,7 +645,7 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                 if (x3 && (rc = encode_im2col(&maps[1], a_lo, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
                 maps[2] = map_b[0];
                 maps[3] = map_b[1];
-                rc = bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, stats, st) : launch_conv_tc<64>(maps, p, addend, out, stats, st);
+                rc = bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, stats, fuse, st) : launch_conv_tc<64>(maps, p, addend, out, stats, fuse, st);
                 if (rc) return rc;
             }
     return AVID_OK;
@@ -687,12 +728,19 @@ int avid_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream)
 
 int avid_conv_forward_tc(const avid_conv_shape_t* s, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
                          const float* addend, float* out, double* bn_stats, void* stream) {
-    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, out, bn_stats, static_cast<cudaStream_t>(stream));
+    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, out, bn_stats, BnBwdFuse{}, static_cast<cudaStream_t>(stream));
 }
 
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
-                       const float* addend, float* din, void* stream) {
-    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, din, nullptr, static_cast<cudaStream_t>(stream));
+                       const float* addend, float* din, const avid_bn_backward_fuse_t* fuse, void* stream) {
+    BnBwdFuse f;
+    if (fuse) {
+        f.z = fuse->z;  f.mean = fuse->mean;  f.invstd = fuse->invstd;  f.gamma = fuse->gamma;  f.beta = fuse->beta;  f.sums = fuse->sums;
+        AVID_REQUIRE(f.z, "conv_dgrad_tc: fuse->z is NULL");
+    }
+    // a class no filter tap reaches is zero-filled, not computed: its rows would be missing from the fused sums
+    AVID_REQUIRE(!fuse || (s && s->kt >= s->st && s->kh >= s->sh && s->kw >= s->sw), "conv_dgrad_tc: BatchNorm fusion needs filter >= stride");
+    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, din, nullptr, f, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -12,11 +12,16 @@ whose channel counts are multiples of 64 (all but the two stems) on the tcgen05 
 activations and gradients handed from layer to layer as bf16 (hi, lo) planes written by the
 BatchNorm+ReLU kernels.  Strided input gradients run as one tcgen05 launch per stride-parity class.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 from ..ops import Act
+
+
+FUSE_MIN_K = int(os.environ.get('AVID_FUSE_BN_BWD_MIN_K', '2304'))   # contraction length (co * taps) from which dgrad also reduces BN backward
 
 
 def _triple(v, fill=1):
@@ -73,9 +78,19 @@ class ConvOp:
             dw = ops.conv_wgrad(self.shape, x.f32, dz.f32, ci_real=self.ci_real)
         return ops.filter_from_tapmajor(dw, self.conv.weight)
 
-    def dgrad(self, dz, addend=None):
+    def can_fuse_bn_backward(self):
+        """The tensor-core input gradient can also reduce the previous layer's BatchNorm backward (every input pixel must be
+        written by a computed tile: filter >= stride)."""
+        # Measured on B200: the extra epilogue work (z tile, BatchNorm constants, two column reductions) is hidden behind the next
+        # tile's TMA / MMA only when that main loop is long; with short loops (64-channel layers, temporal taps) it made the
+        # input-gradient kernels epilogue-bound (5.3 -> 9.7 ms per step), so the fusion is used from K >= FUSE_MIN_K on.
+        k_total = self.conv.out_channels * self.k[0] * self.k[1] * self.k[2]
+        return self.tc and all(k >= s for k, s in zip(self.k, self.s)) and k_total >= FUSE_MIN_K
+
+    def dgrad(self, dz, addend=None, bn_fuse=None):
         if self.tc:
-            return ops.conv_dgrad_tc(self.shape, dz.hi, dz.lo, self.wd_hi, self.wd_lo, addend=addend)
+            return ops.conv_dgrad_tc(self.shape, dz.hi, dz.lo, self.wd_hi, self.wd_lo, addend=addend, bn_fuse=bn_fuse)
+        assert bn_fuse is None
         return ops.conv_dgrad(self.shape, dz.f32, self.w_tap_t, addend=addend)
 
 
@@ -141,9 +156,14 @@ class ConvBNReLU:
         return y, (op, x, z, st, bn)
 
     @staticmethod
-    def backward(dy, saved, grads, need_dx=True, dx_addend=None, dz_f32=False):
+    def backward(dy, saved, grads, need_dx=True, dx_addend=None, dz_f32=False, sums=None, below=None):
         """dy: fp32 gradient at the ReLU output.  Returns (dx fp32 or None, dz: Act at the conv output, i.e. after
-        the residual sum)."""
+        the residual sum, sums_below).
+
+        `below`: the saved record of the conv-BN-ReLU layer whose output is this layer's input.  When given (and this layer's
+        input gradient runs on the tensor cores) the dgrad epilogue also reduces THAT layer's BatchNorm backward; the (2, c)
+        sums are returned as `sums_below` and must be passed as `sums` to that layer's backward, which then skips its own
+        reduction pass over dy and z."""
         op, x, z, st, bn = saved[:5]
         want_f32 = dz_f32 or not op.tc or (need_dx and op.needs_f32_dz())
         if len(saved) > 5:      # pooled layer: dy is the gradient at the pooled output
@@ -151,11 +171,18 @@ class ConvBNReLU:
                                                                  want_f32=want_f32, want_planes=op.tc, x3=op.x3)
         else:
             dz, dgamma, dbeta = ops.bn_relu_backward_act(z, dy, st, bn.weight.detach(), bn.bias.detach(), want_f32=want_f32,
-                                                         want_planes=op.tc, x3=op.x3)
+                                                         want_planes=op.tc, x3=op.x3, sums=sums)
         grads[bn.weight], grads[bn.bias] = dgamma, dbeta
         grads[op.conv.weight] = op.wgrad(x, dz)
-        dx = op.dgrad(dz, addend=dx_addend) if need_dx else None
-        return dx, dz
+        dx, sums_below = None, None
+        if need_dx:
+            fuse = None
+            if below is not None and len(below) == 5 and getattr(op, 'can_fuse_bn_backward', lambda: False)():
+                _, _, z_b, st_b, bn_b = below
+                sums_below = ops.bn_backward_sums(z_b.shape[-1], z_b.device)
+                fuse = (z_b, st_b, bn_b.weight.detach(), bn_b.bias.detach(), sums_below)
+            dx = op.dgrad(dz, addend=dx_addend, bn_fuse=fuse) if fuse is not None else op.dgrad(dz, addend=dx_addend)
+        return dx, dz, sums_below
 
 
 class Basic2DBlock(nn.Module):
@@ -174,11 +201,18 @@ class Basic2DBlock(nn.Module):
         y2, s2 = ConvBNReLU.forward(y1, self.conv2, self.bn2, training, math, out_f32=True)
         return y2, (s1, s2)
 
-    def _bwd(self, dy, saved, grads, need_dx=True):
+    def _bwd(self, dy, saved, grads, need_dx=True, sums=None, below=None):
+        """`sums`: BatchNorm-backward sums of bn2 already reduced by the block above; `below`: record of the layer feeding this
+        block.  Returns (dx, sums for `below`)."""
         s1, s2 = saved
-        d1, _ = ConvBNReLU.backward(dy, s2, grads)
-        dx, _ = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx)
-        return dx
+        d1, _, sums1 = ConvBNReLU.backward(dy, s2, grads, sums=sums, below=s1)
+        dx, _, sums_below = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx, sums=sums1, below=below)
+        return dx, sums_below
+
+    @staticmethod
+    def top_record(saved):
+        """The record of the block's last conv-BN-ReLU (the layer a block above may reduce the BatchNorm backward of)."""
+        return saved[1]
 
 
 class BasicR2P1DBlock(nn.Module):
@@ -219,16 +253,24 @@ class BasicR2P1DBlock(nn.Module):
         y4, s4 = ConvBNReLU.forward(y3, self.tmp_conv2, self.out_bn, training, math, addend=r, out_f32=True)
         return y4, (s1, s2, s3, s4, rop, x)
 
-    def _bwd(self, dy, saved, grads, need_dx=True):
+    def _bwd(self, dy, saved, grads, need_dx=True, sums=None, below=None):
+        """`sums`: BatchNorm-backward sums of out_bn already reduced by the block above; `below`: record of the layer feeding
+        this block.  Returns (dx, sums for `below`)."""
         s1, s2, s3, s4, rop, x = saved
         # d_sum (gradient at x_main + x_res) flows to tmp_conv2 and to the residual branch
-        d3, d_sum = ConvBNReLU.backward(dy, s4, grads, dz_f32=(not self.res) or rop.needs_f32_dz())
-        d2, _ = ConvBNReLU.backward(d3, s3, grads)
-        d1, _ = ConvBNReLU.backward(d2, s2, grads)
+        d3, d_sum, sums3 = ConvBNReLU.backward(dy, s4, grads, dz_f32=(not self.res) or rop.needs_f32_dz(), sums=sums, below=s3)
+        d2, _, sums2 = ConvBNReLU.backward(d3, s3, grads, sums=sums3, below=s2)
+        d1, _, sums1 = ConvBNReLU.backward(d2, s2, grads, sums=sums2, below=s1)
         if self.res:
             grads[self.res_conv.weight] = rop.wgrad(x, d_sum)
             d_res = rop.dgrad(d_sum) if need_dx else None
         else:
             d_res = d_sum.f32
-        dx, _ = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx, dx_addend=d_res)
-        return dx
+        # the block's input gradient = spt_conv1's input gradient + the residual branch's (fused as the epilogue addend), so the
+        # epilogue sees the complete gradient and can reduce the BatchNorm backward of the layer below
+        dx, _, sums_below = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx, dx_addend=d_res, sums=sums1, below=below)
+        return dx, sums_below
+
+    @staticmethod
+    def top_record(saved):
+        return saved[3]

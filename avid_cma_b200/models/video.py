@@ -70,6 +70,10 @@ class R2Plus1D(TowerMixin, nn.Module):
     def _bwd(self, dpooled, saved, grads, math):
         s_stem, saved_blocks, argmax, hshape = saved
         d = ops.global_maxpool_backward(dpooled, argmax, hshape)
-        for blk, sb in reversed(saved_blocks):
-            d = blk._bwd(d, sb, grads)
+        sums = None
+        for i in range(len(saved_blocks) - 1, -1, -1):
+            blk, sb = saved_blocks[i]
+            # the layer below block i: the last conv-BN-ReLU of block i-1, or the stem
+            below = saved_blocks[i - 1][0].top_record(saved_blocks[i - 1][1]) if i > 0 else s_stem
+            d, sums = blk._bwd(d, sb, grads, sums=sums, below=below)
         ConvBNReLU.backward(d, s_stem, grads, need_dx=False)

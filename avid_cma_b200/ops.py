@@ -278,13 +278,26 @@ def conv_forward_tc(s, x_hi, x_lo, w_hi, w_lo, addend=None, out=None, ci_real=No
     return out
 
 
-def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None):
-    """tcgen05 input gradient (any stride); d_* planes [n,to,ho,wo,co] bf16, w_* planes [taps,ci,co] bf16."""
+def bn_backward_sums(c, device):
+    """(2, c) fp64 zeros for the BatchNorm-backward sums a fused input-gradient launch accumulates."""
+    return _zeros((2, c), torch.float64, device)
+
+
+def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None, bn_fuse=None):
+    """tcgen05 input gradient (any stride); d_* planes [n,to,ho,wo,co] bf16, w_* planes [taps,ci,co] bf16.
+    bn_fuse = (z, BNState, gamma, beta, sums): also accumulate the BatchNorm-backward sums of the layer that produced this
+    convolution's input (z: its conv output) -- see avid_bn_backward_fuse_t."""
     if out is None:
         out = torch.empty(s.n, s.ti, s.hi, s.wi, s.ci, dtype=torch.float32, device=d_hi.device)
+    fuse = None
+    if bn_fuse is not None:
+        z, st, gamma, beta, sums = bn_fuse
+        assert z.numel() == out.numel()
+        fuse = _lib.BnBackwardFuse(_p(z), _p(st.mean), _p(st.invstd), _p(gamma), _p(beta), _p(sums, torch.float64))
     e0 = _t0()
     check(_lib.lib().avid_conv_dgrad_tc(C.byref(s), _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
-                                        _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out), _stream()))
+                                        _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out),
+                                        C.byref(fuse) if fuse is not None else None, _stream()))
     _t1(e0, "conv_dgrad_tc", _conv_flops(s))
     return out
 
@@ -465,18 +478,22 @@ def bn_relu_backward(x, dy, s, gamma, beta, dx=None):
     return act.f32, dgamma, dbeta
 
 
-def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=None):
-    """Backward of y = relu(bn_train(x)); the gradient w.r.t. x as an Act (fp32 and / or bf16 planes)."""
+def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=None, sums=None):
+    """Backward of y = relu(bn_train(x)); the gradient w.r.t. x as an Act (fp32 and / or bf16 planes).  `sums`: the reduction
+    was already done by the epilogue of the input-gradient launch that produced dy (conv_dgrad_tc(bn_fuse=...))."""
     c = x.shape[-1]
     rows = x.numel() // c
-    sums = _zeros((2, c), torch.float64, x.device)
+    have_sums = sums is not None
+    if not have_sums:
+        sums = _zeros((2, c), torch.float64, x.device)
     if want_f32 and dx is None:
         dx = torch.empty_like(x)
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes else None
     lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes and x3 else None
     dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
     L = _lib.lib()
-    check(L.avid_bn_relu_backward_reduce(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), rows, c, _p(sums, torch.float64), _stream()))
+    if not have_sums:
+        check(L.avid_bn_relu_backward_reduce(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), rows, c, _p(sums, torch.float64), _stream()))
     check(L.avid_bn_relu_backward_apply_ex(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), _p(sums, torch.float64), rows, c,
                                            _p(dx, optional=True), _p(hi, torch.bfloat16, optional=True), _p(lo, torch.bfloat16, optional=True),
                                            _p(dgamma), _p(dbeta), _stream()))

@@ -202,8 +202,20 @@ int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const floa
 int avid_split_bf16(const float* x, void* hi, void* lo /* may be NULL */, int64_t n, void* stream);
 int avid_conv_forward_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
                          const float* addend, float* out, double* bn_stats, void* stream);
+/* Optional fusion for avid_conv_dgrad_tc: `din` (+ addend) is the gradient at the ReLU output of the PREVIOUS conv-BN-ReLU
+ * layer; with this struct the epilogue also accumulates that layer's BatchNorm-backward sums
+ * (sums[0][c] += sum g, sums[1][c] += sum g * xhat, g = din * relu'(bn(z)), xhat = (z - mean) * invstd) so that
+ * avid_bn_relu_backward_apply can follow without the separate avid_bn_relu_backward_reduce pass over din and z. */
+typedef struct avid_bn_backward_fuse {
+    const float* z;        /* previous layer's conv output, same shape as din */
+    const float* mean;     /* (ci) saved batch mean / inverse std / affine parameters of that layer's BatchNorm */
+    const float* invstd;
+    const float* gamma;
+    const float* beta;
+    double*      sums;     /* (2, ci) doubles, zeroed by the caller */
+} avid_bn_backward_fuse_t;
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
-                       const float* addend, float* din, void* stream);
+                       const float* addend, float* din, const avid_bn_backward_fuse_t* fuse_host /* may be NULL */, void* stream);
 /*   wgrad  : in planes [n,ti,hi,wi,ci], dout planes [n,to,ho,wo,co] -> dfilt fp32 tap-major [taps][ci][co], zeroed by the
  *            caller (split over pixels, accumulated with fp32 vector atomics); any stride                               */
 int avid_conv_wgrad_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* dout_hi, const void* dout_lo,
