@@ -128,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);      // two accumulator buffers x (hi | lo filter-plane halves)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -166,6 +166,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+        // bf16x3 as TWO MMAs per k-step instead of three: the hi and lo filter planes are adjacent K-major tiles, i.e. ONE
+        // operand of 2*BN rows, so A_hi x [B_hi ; B_lo] is a single N = 2*BN MMA whose two column halves (hi*hi | hi*lo) the
+        // epilogue adds; A_lo x B_hi (N = BN) accumulates into the first half.  An M128 MMA fetches (128 + N) x 32 B of
+        // operands at ~64 B/clk (measured), so fewer, wider MMAs cut the operand traffic per product by 22 % (BN = 64).
+        constexpr uint32_t idesc2 = make_idesc_bf16(kBM, 2 * BN, 0, 0);
         // K-major SW128 tiles: 8-row groups are 1024 bytes apart; a K=16 slice is 32 bytes into the swizzle row.  Descriptors
         // differ only in the start-address field (bytes >> 4): encode once and add offsets, so that the single issuing thread
         // spends a couple of instructions per MMA (an N = 64 MMA is only 32 tensor-pipe cycles).
@@ -176,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int buf = it & 1;
             mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t acc = tmem_base + buf * BN;
+            const uint32_t acc = tmem_base + buf * 2 * BN;
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
@@ -185,9 +190,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (x3) {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
-                        umma_bf16(acc, a_hi + 2 * k, b_hi + (uint32_t)(S::kBBytes >> 4) + 2 * k, idesc, 1);
-                        umma_bf16(acc, a_hi + (uint32_t)(S::kABytes >> 4) + 2 * k, b_hi + 2 * k, idesc, 1);
+                        umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kb | k) != 0);                               // hi*hi | hi*lo
+                        umma_bf16(acc, a_hi + (uint32_t)(S::kABytes >> 4) + 2 * k, b_hi + 2 * k, idesc, 1);              // + lo*hi
                     }
                 } else {
 #pragma unroll
@@ -226,8 +230,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + j * 32, r);
+                uint32_t r[32], r2[32];
+                const uint32_t taddr = tmem_base + buf * 2 * BN + ((uint32_t)(q * 32) << 16) + j * 32;
+                tmem_ld_32x32b_x32(taddr, r);
+                if (p.x3) tmem_ld_32x32b_x32(taddr + BN, r2);       // the hi*lo half of the bf16x3 accumulator
                 tmem_ld_wait();
                 if (j == BN / 32 - 1) {             // the whole accumulator is in registers: hand the TMEM buffer back
                     tc_fence_before();
@@ -236,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
                 float o[32];
 #pragma unroll
-                for (int v = 0; v < 32; ++v) o[v] = __uint_as_float(r[v]);
+                for (int v = 0; v < 32; ++v) o[v] = p.x3 ? __uint_as_float(r[v]) + __uint_as_float(r2[v]) : __uint_as_float(r[v]);
                 if (m < p.M) {
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
@@ -294,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 4 * BN);
 }
 
 // ---- filter gradient ---------------------------------------------------------------------------------
