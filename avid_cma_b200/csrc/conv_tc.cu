@@ -47,6 +47,7 @@ constexpr int kBK = 64;         // channels per k-block: 64 bf16 = one 128-byte 
 constexpr int kTcThreads = 192; // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
 
 constexpr int kMaxTaps = 32;
+constexpr int kStgLd = 36;      // row pitch (floats) of the epilogue staging tiles: 16-byte aligned, conflict-free for float4 rows
 
 struct TcConvParams {
     int M;                          // destination pixels of this launch, enumerated ((n * tq + t) * hq + h) * wq + w
@@ -82,7 +83,8 @@ struct TcSmem {
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kStages = BN <= 64 ? 4 : 3;
     static constexpr int kStatBytes = 4 * 2 * BN * 4 + BN * 16; // [4 epilogue warps][2 sums][BN] floats + [BN] float4 BatchNorm constants
-    static constexpr int kBytes = kStages * kStageBytes + kStatBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kStgBytes = 4 * 32 * kStgLd * 4;       // [4 epilogue warps][32 rows][kStgLd] floats: transpose staging
+    static constexpr int kBytes = kStages * kStageBytes + kStatBytes + kStgBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 // Persistent: CTA i works on tiles i, i + gridDim.x, ...; a tile is (128 destination pixels) x (BN destination channels), tiles
@@ -99,7 +101,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* s_stat = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
     float4* s_par = reinterpret_cast<float4*>(s_stat + 4 * 2 * BN);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kStatBytes);
+    float* s_stage = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kStatBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kStatBytes + S::kStgBytes);
     uint64_t* empty_bar = full_bar + S::kStages;
     uint64_t* tmem_full = empty_bar + S::kStages;     // [2]
     uint64_t* tmem_empty = tmem_full + 2;             // [2]
@@ -203,8 +206,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             umma_commit(&tmem_full[buf]);           // accumulator complete
         }
     } else if (warp >= 2) {
-        // ===== epilogue: TMEM -> registers -> global (one output pixel per thread), optional BatchNorm statistics =====
+        // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> coalesced global rows, optional BatchNorm statistics =====
+        // tcgen05.ld hands every thread one output pixel (row).  Storing rows from that layout makes each warp store instruction
+        // touch 32 different rows (32 sectors in 32 lines); with short contractions (temporal taps, 64 channels) those stores, not
+        // the MMAs, paced the kernel.  Each warp therefore transposes 32 x 32 chunks through a padded staging tile and writes /
+        // reads global memory with 8 lanes per row: one instruction covers 4 rows x 128 contiguous bytes.  The residual addend,
+        // the z tile of the fused BatchNorm backward and the per-channel sums all use that layout (column sums = 8 in-lane adds
+        // + 2 shuffles instead of a 31-shuffle butterfly).
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        float* const stg = s_stage + q * (32 * kStgLd);
+        const int r4 = lane >> 3, c4 = (lane & 7) * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -219,7 +230,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int n_i = r / p.tq;
                 pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
             }
-            const size_t row = pix * p.cd + n0;
+            const unsigned long long my_row = m < p.M ? (unsigned long long)(pix * p.cd + n0) : ~0ull;
+            unsigned long long rows8[8];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rows8[i] = __shfl_sync(0xffffffffu, my_row, i * 4 + r4);
             double* const acc_out = stats ? stats : fuse.sums;       // which per-channel sums this launch accumulates, if any
             if (fuse.z) {       // BatchNorm constants of this tile's channels (the previous tile's readers passed the barrier below)
                 const int t = threadIdx.x - 64;
@@ -234,55 +248,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const uint32_t taddr = tmem_base + buf * 2 * BN + ((uint32_t)(q * 32) << 16) + j * 32;
                 tmem_ld_32x32b_x32(taddr, r);
                 if (p.x3) tmem_ld_32x32b_x32(taddr + BN, r2);       // the hi*lo half of the bf16x3 accumulator
+                // global operands of this chunk are requested while the TMEM loads are in flight
+                float4 ad[8], zz[8];
+                if (addend) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        ad[i] = rows8[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows8[i] + j * 32 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (fuse.z) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        zz[i] = rows8[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows8[i] + j * 32 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 tmem_ld_wait();
                 if (j == BN / 32 - 1) {             // the whole accumulator is in registers: hand the TMEM buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
-                float o[32];
+                float4* const srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-                for (int v = 0; v < 32; ++v) o[v] = p.x3 ? __uint_as_float(r[v]) + __uint_as_float(r2[v]) : __uint_as_float(r[v]);
-                if (m < p.M) {
+                for (int v = 0; v < 8; ++v) {
+                    float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    if (p.x3) {
+                        o.x += __uint_as_float(r2[4 * v]); o.y += __uint_as_float(r2[4 * v + 1]);
+                        o.z += __uint_as_float(r2[4 * v + 2]); o.w += __uint_as_float(r2[4 * v + 3]);
+                    }
+                    srow[v] = o;
+                }
+                __syncwarp();
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 par[4];
+                if (fuse.z) {
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        if (addend) {
-                            const float4 ad = __ldg(reinterpret_cast<const float4*>(addend + row + j * 32) + v);
-                            o[4 * v] += ad.x; o[4 * v + 1] += ad.y; o[4 * v + 2] += ad.z; o[4 * v + 3] += ad.w;
+                    for (int t = 0; t < 4; ++t) par[t] = s_par[j * 32 + c4 + t];      // mean, invstd, gamma, beta
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + r4) * kStgLd + c4);
+                    if (rows8[i] == ~0ull) continue;
+                    if (addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
+                    *reinterpret_cast<float4*>(out + rows8[i] + j * 32 + c4) = o;
+                    if (acc_out) {
+                        // per-channel sums over the tile's rows: fp32 within the tile, fp64 atomics across tiles.
+                        //   forward (stats):      sum(o), sum(o^2) of the stored output -> BatchNorm statistics
+                        //   input gradient (fuse): sum(g), sum(g * xhat) with g = o * relu'(bn(z)) -> the next BatchNorm backward
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+                        if (fuse.z) {
+                            const float zv[4] = {zz[i].x, zz[i].y, zz[i].z, zz[i].w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float xh = (zv[t] - par[t].x) * par[t].y;
+                                const float g = fmaf(xh, par[t].z, par[t].w) > 0.f ? ov[t] : 0.f;
+                                s1[t] += g;
+                                s2[t] = fmaf(g, xh, s2[t]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                s1[t] += ov[t];
+                                s2[t] = fmaf(ov[t], ov[t], s2[t]);
+                            }
                         }
-                        reinterpret_cast<float4*>(out + row + j * 32)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
                     }
                 }
+                __syncwarp();                       // the staging tile is rewritten by the next chunk
                 if (acc_out) {
-                    // per-channel sums over the tile's rows: fp32 within the tile, fp64 atomics across tiles.
-                    //   forward (stats):      sum(o), sum(o^2) of the stored output -> BatchNorm statistics
-                    //   input gradient (fuse): sum(g), sum(g * xhat) with g = o * relu'(bn(z)) -> the next BatchNorm backward
-                    float second[32];
-                    if (fuse.z) {
-                        float zr[32];
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) {
-                            const float4 zz = m < p.M ? __ldg(reinterpret_cast<const float4*>(fuse.z + row + j * 32) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            zr[4 * v] = zz.x; zr[4 * v + 1] = zz.y; zr[4 * v + 2] = zz.z; zr[4 * v + 3] = zz.w;
-                        }
-#pragma unroll
-                        for (int v = 0; v < 32; ++v) {
-                            const float4 par = s_par[j * 32 + v];           // mean, invstd, gamma, beta (warp-wide broadcast)
-                            const float xh = (zr[v] - par.x) * par.y;
-                            const float g = (m < p.M && fmaf(xh, par.z, par.w) > 0.f) ? o[v] : 0.f;
-                            o[v] = g;
-                            second[v] = g * xh;
-                        }
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < 32; ++v) {
-                            if (m >= p.M) o[v] = 0.f;
-                            second[v] = o[v] * o[v];
-                        }
+                    for (int t = 0; t < 4; ++t) {
+                        s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], 8);
+                        s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], 16);
+                        s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], 8);
+                        s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], 16);
                     }
-                    const float cs = warp_column_sums(o, lane), cq = warp_column_sums(second, lane);
-                    s_stat[(q * 2 + 0) * BN + j * 32 + lane] = cs;
-                    s_stat[(q * 2 + 1) * BN + j * 32 + lane] = cq;
+                    if (lane < 8) {
+                        *reinterpret_cast<float4*>(s_stat + (q * 2 + 0) * BN + j * 32 + c4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+                        *reinterpret_cast<float4*>(s_stat + (q * 2 + 1) * BN + j * 32 + c4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+                    }
                 }
             }
             if (acc_out) {
