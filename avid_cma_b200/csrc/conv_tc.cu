@@ -368,8 +368,12 @@ template <int BN>
 struct TcWgSmem {
     static constexpr int kABytes = 2 * kSubTile;            // two (tap, 64-channel) groups
     static constexpr int kBBytes = (BN / 64) * kSubTile;
-    static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
+    static constexpr int kStageBytes = 2 * (kABytes + kBBytes);             // [A hi | A lo | B hi | B lo]
     static constexpr int kStages = BN <= 64 ? 4 : (BN <= 128 ? 3 : 2);
+    // bf16x3 with BN <= 128: X_hi x [dZ_hi | dZ_lo] is ONE MMA of N = 2 * BN (the lo plane's 64-channel groups follow the hi
+    // plane's at the same 8 KB pitch), its two column halves are summed in the epilogue; X_lo x dZ_hi adds into the first half.
+    static constexpr bool kWide = BN <= 128;
+    static constexpr int kTmemCols = kWide ? 2 * BN : BN;
     static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -408,7 +412,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tmem_alloc(tmem_slot, S::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -443,19 +447,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             for (int pl = 0; pl < planes; ++pl) {
                 const CUtensorMap* mx = pl ? &map_x_lo : &map_x_hi;
                 const CUtensorMap* md = pl ? &map_d_lo : &map_d_hi;
-                uint8_t* a = st + pl * (S::kABytes + S::kBBytes);
+                uint8_t* a = st + pl * S::kABytes;
+                uint8_t* b = st + 2 * S::kABytes + pl * S::kBBytes;
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
                     tma_load_im2col_5d(a + i * kSubTile, mx, &full_bar[stage], gc0[i], bw, bh, bt, n_i, (uint16_t)gc[i], (uint16_t)gb[i], (uint16_t)ga[i]);
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                    tma_load_2d(a + S::kABytes + j * kSubTile, md, &full_bar[stage], n0 + j * 64, (kb0 + kb) * kWgKB);
+                    tma_load_2d(b + j * kSubTile, md, &full_bar[stage], n0 + j * 64, (kb0 + kb) * kWgKB);
             }
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        constexpr uint32_t idesc2 = make_idesc_bf16(128, S::kWide ? 2 * BN : BN, 1, 1);
         const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), kSubTile, 1024);
         const bool x3 = p.x3 != 0;
         int stage = 0, phase = 0;
@@ -463,14 +469,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
-            const uint64_t b_hi = a_hi + (uint32_t)(S::kABytes >> 4);
-            constexpr uint32_t kLo = (uint32_t)((S::kABytes + S::kBBytes) >> 4);      // hi -> lo plane of the same operand
+            const uint64_t b_hi = a_hi + (uint32_t)((2 * S::kABytes) >> 4);
+            constexpr uint32_t kLoA = (uint32_t)(S::kABytes >> 4), kLoB = (uint32_t)(S::kBBytes >> 4);      // hi -> lo plane of an operand
             if (x3) {
 #pragma unroll
                 for (int k = 0; k < kWgKB / 16; ++k) {          // a K = 16 step advances 2 KB = 128 encoded units
-                    umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
-                    umma_bf16(tmem_base, a_hi + 128 * k, b_hi + kLo + 128 * k, idesc, 1);
-                    umma_bf16(tmem_base, a_hi + kLo + 128 * k, b_hi + 128 * k, idesc, 1);
+                    if (S::kWide) {
+                        umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc2, (kb | k) != 0);       // hi*hi | hi*lo
+                        umma_bf16(tmem_base, a_hi + kLoA + 128 * k, b_hi + 128 * k, idesc, 1);             // + lo*hi
+                    } else {
+                        umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base, a_hi + 128 * k, b_hi + kLoB + 128 * k, idesc, 1);
+                        umma_bf16(tmem_base, a_hi + kLoA + 128 * k, b_hi + 128 * k, idesc, 1);
+                    }
                 }
             } else {
 #pragma unroll
@@ -492,20 +503,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         float* dst = dfilt + ((size_t)tap * p.cs + ci) * p.cd + n0;
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) {
-            uint32_t r[32];
+            uint32_t r[32], r2[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, r);
+            const bool wide = S::kWide && p.x3;
+            if (wide) tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + BN + j * 32, r2);     // the hi*lo half
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    red_add_v4(dst + j * 32 + 4 * v, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                               __uint_as_float(r[4 * v + 3]));
+                for (int v = 0; v < 8; ++v) {
+                    float o[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) o[t] = wide ? __uint_as_float(r[4 * v + t]) + __uint_as_float(r2[4 * v + t]) : __uint_as_float(r[4 * v + t]);
+                    red_add_v4(dst + j * 32 + 4 * v, o[0], o[1], o[2], o[3]);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, S::kTmemCols);
 }
 
 // fp32 -> (bf16 hi, bf16 lo) planes: hi = rn(x), lo = rn(x - hi)
@@ -732,9 +748,18 @@ int wgrad_tc_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo,
     const int bn = s->co % 256 == 0 ? 256 : (s->co % 128 == 0 ? 128 : 64);
     const int tiles = ((p.groups + 1) / 2) * (s->co / bn);
     const int total_kb = (p.M + kWgKB - 1) / kWgKB;
-    int splits = (2 * kNumSMs + tiles - 1) / tiles;
-    if (splits > (total_kb + 3) / 4) splits = (total_kb + 3) / 4;     // at least 4 k-blocks per CTA
-    if (splits < 1) splits = 1;
+    // one CTA per SM (the stages fill shared memory): pick the pixel split that minimises waves x (k-blocks per CTA + the fixed
+    // prologue / atomic-epilogue cost, ~8 k-blocks) -- a grid of 300 CTAs on 148 SMs would run a third wave for 4 CTAs.
+    int splits = 1;
+    {
+        const int max_splits = total_kb >= 4 ? (total_kb + 3) / 4 : 1;       // at least 4 k-blocks per CTA
+        long best = -1;
+        for (int sp = 1; sp <= max_splits && (long)sp * tiles <= 4L * kNumSMs; ++sp) {
+            const long waves = ((long)sp * tiles + kNumSMs - 1) / kNumSMs;
+            const long cost = waves * ((total_kb + sp - 1) / sp + 8);
+            if (best < 0 || cost < best) { best = cost; splits = sp; }
+        }
+    }
     p.kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
     const int lower[3] = {-s->pw, -s->ph, -s->pt};

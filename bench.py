@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end timed region")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event table of the timed region (mean over steps, launch order) to this file")
     ap.add_argument("--bank-mode", default="auto", choices=["auto", "replicated", "sharded"],
                     help="memory-bank layout for N > 1: sharded = row-partitioned over the ranks (default), replicated = the reference's")
     return ap.parse_args()
@@ -235,6 +236,14 @@ def run_ours(a):
         return
 
     clips = B * world * a.steps
+    if a.dump_launches and len(prof) % a.steps == 0:
+        per = len(prof) // a.steps
+        with open(a.dump_launches, "w") as f:
+            for i in range(per):
+                durs = [prof[s_ * per + i][2] for s_ in range(a.steps)]
+                name, work = prof[i][0], prof[i][1]
+                mean = sum(durs) / len(durs)
+                f.write("%3d %-18s %9.1f us  work %10.3e  rate %8.1f (TFLOP/s or GB/s)\n" % (i, name, mean * 1e3, work, work / (mean * 1e-3) / (1e9 if name.startswith("nce") else 1e12)))
     # roofline of the dominant kernel, from CUDA events recorded around every launch of the timed region.  Families are the
     # instrumented entry points of ops.py; conv_forward_tc and conv_dgrad_tc are the same kernel (conv_tc_kernel) and are merged.
     fam = {}
