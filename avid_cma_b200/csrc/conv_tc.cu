@@ -19,6 +19,7 @@
 //   both operands are MN-major (the reduction index is the row index of the channels-last tensors);
 //   X tiles by im2col TMA, dZ tiles by tiled TMA, split over pixel ranges, fp32 atomics into dW.
 #include <mutex>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -62,6 +63,8 @@ struct TcConvParams {
     // destination addressing: enumerated pixel (n, t, h, w) -> ((n * Td + t * ot + rt) * Hd + h * oh + rh) * Wd + w * ow + rw
     int strided_out;
     int Td, Hd, Wd, ot, oh, ow, rt, rh, rw;
+    int debug;                      // AVID_TC_DEBUG probe bits (scripts/probe_conv.py; 0 in production): 1 no global stores, 2 no
+                                    // statistics, 4 epilogue only hands the accumulator back, 8 no MMAs, 64 no per-tile atomics
 };
 
 // Optional fusion of the NEXT BatchNorm backward's reduction into an input-gradient launch: the tensor this launch writes is
@@ -98,7 +101,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats, const BnBwdFuse fuse) {
     using S = TcSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a pointer -> integer -> pointer round trip would make
+    // every later access a generic LD / ST instead of LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s_stat = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
     float4* s_par = reinterpret_cast<float4*>(s_stat + 4 * 2 * BN);
     float* s_stage = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kStatBytes);
@@ -190,7 +195,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 tc_fence_after();
                 const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
                 const uint64_t b_hi = a_hi + (uint32_t)((2 * S::kABytes) >> 4);
-                if (x3) {
+                if (p.debug & 8) {
+                } else if (x3) {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kb | k) != 0);                               // hi*hi | hi*lo
@@ -242,6 +248,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
+            if (p.debug & 4) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) {
                 uint32_t r[32], r2[32];
@@ -288,8 +300,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + r4) * kStgLd + c4);
                     if (rows8[i] == ~0ull) continue;
                     if (addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
-                    *reinterpret_cast<float4*>(out + rows8[i] + j * 32 + c4) = o;
-                    if (acc_out) {
+                    if (!(p.debug & 1)) *reinterpret_cast<float4*>(out + rows8[i] + j * 32 + c4) = o;
+                    if (acc_out && !(p.debug & 2)) {
                         // per-channel sums over the tile's rows: fp32 within the tile, fp64 atomics across tiles.
                         //   forward (stats):      sum(o), sum(o^2) of the stored output -> BatchNorm statistics
                         //   input gradient (fuse): sum(g), sum(g * xhat) with g = o * relu'(bn(z)) -> the next BatchNorm backward
@@ -327,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 }
             }
-            if (acc_out) {
+            if (acc_out && !(p.debug & 64)) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
                 const int t = threadIdx.x - 64;                      // 0..127
                 for (int i = t; i < 2 * BN; i += 128) {
@@ -692,6 +704,10 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                             p.taps[p.ntaps++] = (uint32_t)d[0].off[c] | ((uint32_t)d[1].off[b] << 8) | ((uint32_t)d[2].off[a] << 16) | (ftap << 24);
                         }
                 p.x3 = x3;
+                {
+                    const char* dbg = getenv("AVID_TC_DEBUG");
+                    p.debug = dbg ? atoi(dbg) : 0;
+                }
                 p.strided_out = dgrad && (ss[0] > 1 || ss[1] > 1 || ss[2] > 1);
                 p.Wd = dst[0];  p.Hd = dst[1];  p.Td = dst[2];
                 p.ow = d[0].ostride;  p.oh = d[1].ostride;  p.ot = d[2].ostride;

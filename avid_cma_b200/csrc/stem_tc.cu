@@ -60,7 +60,9 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const StemParams p,
                     float* __restrict__ out, double* __restrict__ stats) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a pointer -> integer -> pointer round trip would make
+    // every later access a generic LD / ST instead of LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int chunks = p.kt * p.kh, planes = p.x3 ? 2 : 1;
     uint8_t* w_smem = smem;                                          // [plane][chunk][64 co][32 k]
     uint8_t* ring = smem + planes * chunks * kChunkBBytes;           // [stage][11 rows][16 wo][32 k]
@@ -240,7 +242,9 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                   const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, const StemParams p,
                   uint32_t tmem_cols, float* __restrict__ dfilt) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a pointer -> integer -> pointer round trip would make
+    // every later access a generic LD / ST instead of LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int planes = p.x3 ? 2 : 1;
     uint8_t* dz_smem = smem;                                   // [2 buffers][plane][128 pixels][64 co]
     uint8_t* ring = smem + 2 * planes * kDzBytes;
