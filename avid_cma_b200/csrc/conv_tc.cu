@@ -48,7 +48,8 @@ constexpr int kBK = 64;         // channels per k-block: 64 bf16 = one 128-byte 
 constexpr int kTcThreads = 192; // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
 
 constexpr int kMaxTaps = 32;
-constexpr int kStgLd = 36;      // row pitch (floats) of the epilogue staging tiles: 16-byte aligned, conflict-free for float4 rows
+constexpr int kStgLd = 20;      // row pitch (floats) of the 32 x 16 epilogue staging tiles: 16-byte aligned, conflict-free for float4 rows
+constexpr int kConvThreads = 320; // conv_tc_kernel: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-9 epilogue
 
 struct TcConvParams {
     int M;                          // destination pixels of this launch, enumerated ((n * tq + t) * hq + h) * wq + w
@@ -85,8 +86,8 @@ struct TcSmem {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kStages = BN <= 64 ? 4 : 3;
-    static constexpr int kStatBytes = 4 * 2 * BN * 4 + BN * 16; // [4 epilogue warps][2 sums][BN] floats + [BN] float4 BatchNorm constants
-    static constexpr int kStgBytes = 4 * 32 * kStgLd * 4;       // [4 epilogue warps][32 rows][kStgLd] floats: transpose staging
+    static constexpr int kStatBytes = BN * 16;                  // [BN] float4 BatchNorm constants of a fused BatchNorm backward
+    static constexpr int kStgBytes = 8 * 32 * kStgLd * 4;       // [8 epilogue warps][32 rows][kStgLd] floats: transpose staging
     static constexpr int kBytes = kStages * kStageBytes + kStatBytes + kStgBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -95,7 +96,7 @@ struct TcSmem {
 // TMEM (2 x BN columns): the epilogue of tile k (TMEM -> registers -> global, BatchNorm statistics) overlaps the TMA / MMA of
 // tile k + 1.
 template <int BN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcConvParams p,
                const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats, const BnBwdFuse fuse) {
@@ -104,8 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (a pointer -> integer -> pointer round trip would make
     // every later access a generic LD / ST instead of LDS / STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* s_stat = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
-    float4* s_par = reinterpret_cast<float4*>(s_stat + 4 * 2 * BN);
+    float4* s_par = reinterpret_cast<float4*>(smem + S::kStages * S::kStageBytes);
     float* s_stage = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kStatBytes);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kStatBytes + S::kStgBytes);
     uint64_t* empty_bar = full_bar + S::kStages;
@@ -132,7 +132,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 4);      // one arrive per epilogue warp
+            mbar_init(&tmem_empty[b], 8);      // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -213,19 +213,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else if (warp >= 2) {
         // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> coalesced global rows, optional BatchNorm statistics =====
-        // tcgen05.ld hands every thread one output pixel (row).  Storing rows from that layout makes each warp store instruction
-        // touch 32 different rows (32 sectors in 32 lines); with short contractions (temporal taps, 64 channels) those stores, not
-        // the MMAs, paced the kernel.  Each warp therefore transposes 32 x 32 chunks through a padded staging tile and writes /
-        // reads global memory with 8 lanes per row: one instruction covers 4 rows x 128 contiguous bytes.  The residual addend,
-        // the z tile of the fused BatchNorm backward and the per-channel sums all use that layout (column sums = 8 in-lane adds
-        // + 2 shuffles instead of a 31-shuffle butterfly).
+        // EIGHT warps: the per-tile chain (tcgen05.ld -> staging -> stores) is latency-bound with one warp per scheduler, and with
+        // short contractions (temporal taps, 64 channels) it -- not the MMAs -- paced the kernel.  Warp w may access TMEM lanes
+        // 32 * (w % 4) .. + 31, so each lane quarter is served by two warps that split the tile's 32-column chunks.
+        // tcgen05.ld hands every thread one output pixel (row); storing rows from that layout would make each warp store touch 32
+        // different lines.  Each warp therefore transposes 32 x 16 half-chunks through a padded staging tile and accesses global
+        // memory with 4 lanes per row (64 contiguous bytes = 2 full sectors per row, 8 rows per instruction).  The residual addend
+        // and the z tile of the fused BatchNorm backward use the same layout.  Per-channel sums are kept in registers across the
+        // CTA's tiles (all tiles of a CTA have the same channel block: gridDim.x is a multiple of the channel-block count) and
+        // leave the CTA once, as fp64 atomics.
+        constexpr int kChunks = BN / 64;            // 32-column chunks per warp
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
-        float* const stg = s_stage + q * (32 * kStgLd);
-        const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+        const int hsel = (warp - 2) >> 2;           // which half of the tile's columns
+        float* const stg = s_stage + (warp - 2) * (32 * kStgLd);
+        const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+        const int n0 = (blockIdx.x % nblocks) * BN; // constant per CTA
+        double* const acc_out = stats ? stats : fuse.sums;       // which per-channel sums this launch accumulates, if any
+        if (fuse.z) {       // BatchNorm constants of this CTA's channels
+            const int t = threadIdx.x - 64;
+            if (t < BN) s_par[t] = make_float4(__ldg(fuse.mean + n0 + t), __ldg(fuse.invstd + n0 + t), __ldg(fuse.gamma + n0 + t), __ldg(fuse.beta + n0 + t));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        float run1[kChunks][2][4], run2[kChunks][2][4];      // running column sums: [chunk][half][4 columns of this lane]
+#pragma unroll
+        for (int a = 0; a < kChunks; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) run1[a][b][t] = run2[a][b][t] = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            const int n0 = (tile % nblocks) * BN;
             const int m = (tile / nblocks) * kBM + q * 32 + lane;
             size_t pix = (size_t)m;
             if (p.strided_out) {        // one stride-parity class of a strided input gradient: scatter rows to their pixels
@@ -237,16 +255,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
             }
             const unsigned long long my_row = m < p.M ? (unsigned long long)(pix * p.cd + n0) : ~0ull;
-            unsigned long long rows8[8];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
+            unsigned long long rows4[4];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rows8[i] = __shfl_sync(0xffffffffu, my_row, i * 4 + r4);
-            double* const acc_out = stats ? stats : fuse.sums;       // which per-channel sums this launch accumulates, if any
-            if (fuse.z) {       // BatchNorm constants of this tile's channels (the previous tile's readers passed the barrier below)
-                const int t = threadIdx.x - 64;
-                if (t < BN) s_par[t] = make_float4(__ldg(fuse.mean + n0 + t), __ldg(fuse.invstd + n0 + t), __ldg(fuse.gamma + n0 + t), __ldg(fuse.beta + n0 + t));
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            for (int i = 0; i < 4; ++i) rows4[i] = __shfl_sync(0xffffffffu, my_row, i * 8 + r8);
+            mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
             if (p.debug & 4) {
                 tc_fence_before();
@@ -255,32 +267,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 continue;
             }
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) {
-                uint32_t r[32], r2[32];
-                const uint32_t taddr = tmem_base + buf * 2 * BN + ((uint32_t)(q * 32) << 16) + j * 32;
-                tmem_ld_32x32b_x32(taddr, r);
-                if (p.x3) tmem_ld_32x32b_x32(taddr + BN, r2);       // the hi*lo half of the bf16x3 accumulator
-                // global operands of this chunk are requested while the TMEM loads are in flight
-                float4 ad[8], zz[8];
+            for (int hc = 0; hc < 2 * kChunks; ++hc) {      // 16-column half-chunks of this warp
+                const int jj = hc >> 1, hh = hc & 1;
+                const int col = (hsel * kChunks + jj) * 32 + hh * 16;       // first column of the half-chunk inside the tile
+                uint32_t r[16], r2[16];
+                const uint32_t taddr = tmem_base + buf * 2 * BN + ((uint32_t)(q * 32) << 16) + col;
+                tmem_ld_32x32b_x16(taddr, r);
+                if (p.x3) tmem_ld_32x32b_x16(taddr + BN, r2);       // the hi*lo half of the bf16x3 accumulator
+                // global operands of this half-chunk are requested while the TMEM loads are in flight
+                float4 ad[4], zz[4];
                 if (addend) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        ad[i] = rows8[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows8[i] + j * 32 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 4; ++i)
+                        ad[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (fuse.z) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        zz[i] = rows8[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows8[i] + j * 32 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 4; ++i)
+                        zz[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 tmem_ld_wait();
-                if (j == BN / 32 - 1) {             // the whole accumulator is in registers: hand the TMEM buffer back
+                if (hc == 2 * kChunks - 1) {        // this warp's part of the accumulator is in registers: hand the TMEM buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
                 float4* const srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
+                for (int v = 0; v < 4; ++v) {
                     float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                     if (p.x3) {
                         o.x += __uint_as_float(r2[4 * v]); o.y += __uint_as_float(r2[4 * v + 1]);
@@ -289,20 +303,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     srow[v] = o;
                 }
                 __syncwarp();
-                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
                 float4 par[4];
                 if (fuse.z) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) par[t] = s_par[j * 32 + c4 + t];      // mean, invstd, gamma, beta
+                    for (int t = 0; t < 4; ++t) par[t] = s_par[col + c4 + t];      // mean, invstd, gamma, beta
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + r4) * kStgLd + c4);
-                    if (rows8[i] == ~0ull) continue;
+                for (int i = 0; i < 4; ++i) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (i * 8 + r8) * kStgLd + c4);
+                    if (rows4[i] == ~0ull) continue;
                     if (addend) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
-                    if (!(p.debug & 1)) *reinterpret_cast<float4*>(out + rows8[i] + j * 32 + c4) = o;
+                    if (!(p.debug & 1)) *reinterpret_cast<float4*>(out + rows4[i] + col + c4) = o;
                     if (acc_out && !(p.debug & 2)) {
-                        // per-channel sums over the tile's rows: fp32 within the tile, fp64 atomics across tiles.
+                        // per-channel sums:
                         //   forward (stats):      sum(o), sum(o^2) of the stored output -> BatchNorm statistics
                         //   input gradient (fuse): sum(g), sum(g * xhat) with g = o * relu'(bn(z)) -> the next BatchNorm backward
                         const float ov[4] = {o.x, o.y, o.z, o.w};
@@ -312,43 +325,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             for (int t = 0; t < 4; ++t) {
                                 const float xh = (zv[t] - par[t].x) * par[t].y;
                                 const float g = fmaf(xh, par[t].z, par[t].w) > 0.f ? ov[t] : 0.f;
-                                s1[t] += g;
-                                s2[t] = fmaf(g, xh, s2[t]);
+                                run1[jj][hh][t] += g;
+                                run2[jj][hh][t] = fmaf(g, xh, run2[jj][hh][t]);
                             }
                         } else {
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                s1[t] += ov[t];
-                                s2[t] = fmaf(ov[t], ov[t], s2[t]);
+                                run1[jj][hh][t] += ov[t];
+                                run2[jj][hh][t] = fmaf(ov[t], ov[t], run2[jj][hh][t]);
                             }
                         }
                     }
                 }
-                __syncwarp();                       // the staging tile is rewritten by the next chunk
-                if (acc_out) {
+                __syncwarp();                       // the staging tile is rewritten by the next half-chunk
+            }
+        }
+        if (acc_out && !(p.debug & 64)) {
+            // lanes with equal (lane & 3) hold partial sums of the same 4 columns: reduce over the 8 row groups of the warp, over the
+            // 4 lane quarters through shared memory (the staging tiles are free now), then ONE fp64 atomic per column and CTA --
+            // all CTAs finish together, and atomics on the same address serialise in L2
+            float* const s_red = s_stage;           // [4 quarters][2 sums][BN]
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // every epilogue warp is done with its staging tile
+#pragma unroll
+            for (int jj = 0; jj < kChunks; ++jj)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], 8);
-                        s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], 16);
-                        s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], 8);
-                        s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], 16);
+                        float a = run1[jj][hh][t], b = run2[jj][hh][t];
+#pragma unroll
+                        for (int o = 4; o <= 16; o <<= 1) {
+                            a += __shfl_xor_sync(0xffffffffu, a, o);
+                            b += __shfl_xor_sync(0xffffffffu, b, o);
+                        }
+                        if (lane < 4) {
+                            const int col = (hsel * kChunks + jj) * 32 + hh * 16 + c4 + t;
+                            s_red[(q * 2 + 0) * BN + col] = a;
+                            s_red[(q * 2 + 1) * BN + col] = b;
+                        }
                     }
-                    if (lane < 8) {
-                        *reinterpret_cast<float4*>(s_stat + (q * 2 + 0) * BN + j * 32 + c4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-                        *reinterpret_cast<float4*>(s_stat + (q * 2 + 1) * BN + j * 32 + c4) = make_float4(s2[0], s2[1], s2[2], s2[3]);
-                    }
-                }
-            }
-            if (acc_out && !(p.debug & 64)) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-                const int t = threadIdx.x - 64;                      // 0..127
-                for (int i = t; i < 2 * BN; i += 128) {
-                    const int which = i / BN, ch = i - which * BN;
-                    const float tot = s_stat[(0 * 2 + which) * BN + ch] + s_stat[(1 * 2 + which) * BN + ch] + s_stat[(2 * 2 + which) * BN + ch] +
-                                      s_stat[(3 * 2 + which) * BN + ch];
-                    atomicAdd(acc_out + (size_t)which * p.cd + n0 + ch, (double)tot);
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // s_stat / s_par are rewritten by the next tile
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int t = threadIdx.x - 64;         // 0..255 = (which sum, column)
+            if (t < 2 * BN) {
+                const int which = t / BN, col = t - which * BN;
+                const float tot = s_red[(0 * 2 + which) * BN + col] + s_red[(1 * 2 + which) * BN + col] + s_red[(2 * 2 + which) * BN + col] +
+                                  s_red[(3 * 2 + which) * BN + col];
+                atomicAdd(acc_out + (size_t)which * p.cd + n0 + col, (double)tot);
             }
         }
     }
@@ -594,9 +616,12 @@ static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const 
         if (e != cudaSuccess) { set_error("conv_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
         configured = true;
     }
-    const int tiles = ((p.M + kBM - 1) / kBM) * (p.cd / BN);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    conv_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
+    const int nblocks = p.cd / BN;
+    const int tiles = ((p.M + kBM - 1) / kBM) * nblocks;
+    // a multiple of the channel-block count, so that every tile of a CTA has the same channel block (running statistics)
+    const int grid = tiles < kNumSMs ? tiles : (kNumSMs / nblocks) * nblocks;
+    AVID_REQUIRE(grid > 0, "conv_tc: %d channel blocks exceed the SM count", nblocks);
+    conv_tc_kernel<BN><<<grid, kConvThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
     return check_launch("conv_tc_kernel");
 }
 
