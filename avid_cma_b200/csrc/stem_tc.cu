@@ -64,7 +64,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     // every later access a generic LD / ST instead of LDS / STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int chunks = p.kt * p.kh, planes = p.x3 ? 2 : 1;
-    uint8_t* w_smem = smem;                                          // [plane][chunk][64 co][32 k]
+    uint8_t* w_smem = smem;                                          // [chunk][plane][64 co][32 k]: hi | lo of a chunk = one 128-row operand
     uint8_t* ring = smem + planes * chunks * kChunkBBytes;           // [stage][11 rows][16 wo][32 k]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.stages * kSlotBytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
@@ -88,7 +88,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);     // two 64-column accumulators
+    if (warp == 1) tmem_alloc(tmem_slot, X3 ? 256 : 128);     // two accumulators of 64 (bf16x3: 128 = hi*hi | hi*lo) columns
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -99,7 +99,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         mbar_expect_tx(w_bar, (uint32_t)(planes * chunks * kChunkBBytes));
         for (int pl = 0; pl < planes; ++pl)
             for (int c = 0; c < chunks; ++c)
-                tma_load_2d(w_smem + (pl * chunks + c) * kChunkBBytes, pl ? &map_w_lo : &map_w_hi, w_bar, c * 32, 0);
+                tma_load_2d(w_smem + (c * planes + pl) * kChunkBBytes, pl ? &map_w_lo : &map_w_hi, w_bar, c * 32, 0);
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             int n_i, t_o, h0, w0;
@@ -117,22 +117,25 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 0, 0);
+        // bf16x3: x_hi x [w_hi ; w_lo] is ONE MMA of N = 128 (the planes of a chunk are adjacent in shared memory), its column
+        // halves are summed in the epilogue; x_lo x w_hi adds into the first half: 14 KB instead of 18 KB of operand fetch per k-step
+        constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * kStemCo, 0, 0);
+        constexpr int kPl = X3 ? 2 : 1;
         mbar_wait(w_bar, 0);
         // descriptors differ only in the 14-bit start-address field (bytes >> 4): encode once, then add offsets
         const uint64_t desc0 = make_smem_desc_sw64(0, 16, 512);
         const uint64_t w_desc = desc0 + (smem_u32(w_smem) >> 4);
         const uint64_t ring_desc = desc0 + (smem_u32(ring) >> 4);
         const int kh_n = KH > 0 ? KH : p.kh;
-        const uint32_t lo_off = (uint32_t)(chunks * kChunkBBytes) >> 4;      // hi -> lo filter plane
         int stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t acc = tmem_base + buf * kStemCo;
+            const uint32_t acc = tmem_base + buf * (kPl * kStemCo);
             uint32_t accumulate = 0;
             for (int a = 0; a < p.kt; ++a) {
-                const uint64_t w_a = w_desc + (uint32_t)((a * kh_n * kChunkBBytes) >> 4);
+                const uint64_t w_a = w_desc + (uint32_t)((a * kh_n * kPl * kChunkBBytes) >> 4);
 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
                     if (par >= kh_n) break;
@@ -147,11 +150,10 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
                                 const uint64_t da = slot + (uint32_t)(((kh >> 1) * kRowBytes + ks * 32) >> 4);
-                                const uint64_t db_hi = w_a + (uint32_t)((kh * kChunkBBytes + ks * 32) >> 4);
+                                const uint64_t db_hi = w_a + (uint32_t)((kh * kPl * kChunkBBytes + ks * 32) >> 4);
                                 if (pl == 0) {
-                                    umma_bf16(acc, da, db_hi, idesc, accumulate);
+                                    umma_bf16(acc, da, db_hi, X3 ? idesc2 : idesc, accumulate);
                                     accumulate = 1;
-                                    if (X3) umma_bf16(acc, da, db_hi + lo_off, idesc, 1);
                                 } else {
                                     umma_bf16(acc, da, db_hi, idesc, 1);
                                 }
@@ -177,10 +179,24 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
             uint32_t v0[32], v1[32];
-            const uint32_t taddr = tmem_base + buf * kStemCo + ((uint32_t)(q * 32) << 16);
-            tmem_ld_32x32b_x32(taddr, v0);
-            tmem_ld_32x32b_x32(taddr + 32, v1);
-            tmem_ld_wait();
+            const uint32_t taddr = tmem_base + buf * ((X3 ? 2 : 1) * kStemCo) + ((uint32_t)(q * 32) << 16);
+            if (X3) {
+                uint32_t t0[32];
+                tmem_ld_32x32b_x32(taddr, v0);
+                tmem_ld_32x32b_x32(taddr + kStemCo, t0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int v = 0; v < 32; ++v) v0[v] = __float_as_uint(__uint_as_float(v0[v]) + __uint_as_float(t0[v]));
+                tmem_ld_32x32b_x32(taddr + 32, v1);
+                tmem_ld_32x32b_x32(taddr + kStemCo + 32, t0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int v = 0; v < 32; ++v) v1[v] = __float_as_uint(__uint_as_float(v1[v]) + __uint_as_float(t0[v]));
+            } else {
+                tmem_ld_32x32b_x32(taddr, v0);
+                tmem_ld_32x32b_x32(taddr + 32, v1);
+                tmem_ld_wait();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);     // the accumulator is in registers: the next tile may start
@@ -228,7 +244,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 128);
+    if (warp == 1) tmem_dealloc(tmem_base, X3 ? 256 : 128);
 }
 
 // ---- filter gradient -------------------------------------------------------------------------------------------------
