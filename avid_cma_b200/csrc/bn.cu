@@ -290,6 +290,103 @@ __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float
     }
 }
 
+// Backward apply of the pooled stem layer on 2 x 2 blocks of unpooled pixels: the block (rows 2a, 2a+1; columns 2b, 2b+1) is
+// covered by the four pooling windows (a..a+1, b..b+1) only, so one thread loads 4 argmax entries + 4 pooled gradients (all
+// independent, no data-dependent branches) for 4 output pixels instead of walking up to 4 windows per pixel.  Window (oh, ow)
+// holds pixel (ih, iw) at position (ih - 2 oh + 1) * 3 + (iw - 2 ow + 1).
+__global__ void __launch_bounds__(256) bn_relu_pool_backward_apply_kernel(const float* __restrict__ z, const uint8_t* __restrict__ argmax,
+                                                                          const float* __restrict__ dyp, const float* __restrict__ mean,
+                                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                          const float* __restrict__ beta, const double* __restrict__ sums,
+                                                                          int nt, int h, int w, int c, int ho, int wo, float* __restrict__ dx,
+                                                                          __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo,
+                                                                          float* dgamma, float* dbeta) {
+    const int c4 = c >> 2;
+    const uint32_t hb = (uint32_t)(h + 1) >> 1, wb = (uint32_t)(w + 1) >> 1;
+    const uint32_t total = (uint32_t)nt * hb * wb * (uint32_t)c4;
+    const float inv_n = 1.0f / ((float)nt * (float)h * (float)w);
+    if (blockIdx.x == 0)
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            if (dbeta) dbeta[ch] = (float)sums[ch];
+            if (dgamma) dgamma[ch] = (float)sums[c + ch];
+        }
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;      // stride is a multiple of c4
+    const int cc = (int)(i0 % (uint32_t)c4);
+    float mu[4], is[4], ga[4], be[4], kk[4], sg[4], sgx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = cc * 4 + j;
+        mu[j] = mean[ch];  is[j] = invstd[ch];  ga[j] = gamma[ch];  be[j] = beta[ch];
+        kk[j] = ga[j] * is[j];
+        sg[j] = (float)sums[ch] * inv_n;
+        sgx[j] = (float)sums[c + ch] * inv_n;
+    }
+    for (uint32_t i = i0; i < total; i += stride) {
+        uint32_t r = i / (uint32_t)c4;
+        const uint32_t b = r % wb;  r /= wb;
+        const uint32_t a = r % hb;
+        const uint32_t img = r / hb;
+        // the four windows: [dh][dw] = (a + dh, b + dw)
+        uchar4 am[2][2];
+        float4 d[2][2];
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const uint32_t oh = a + dh, ow = b + dw;
+                am[dh][dw] = make_uchar4(255, 255, 255, 255);
+                d[dh][dw] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (oh < (uint32_t)ho && ow < (uint32_t)wo) {
+                    const uint32_t oi = ((img * (uint32_t)ho + oh) * (uint32_t)wo + ow) * (uint32_t)c4 + cc;
+                    am[dh][dw] = __ldg(reinterpret_cast<const uchar4*>(argmax) + oi);
+                    d[dh][dw] = __ldg(reinterpret_cast<const float4*>(dyp) + oi);
+                }
+            }
+        float4 zv[2][2];
+        uint32_t pi[2][2];
+        bool ok[2][2];
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const uint32_t ih = 2 * a + py, iw = 2 * b + px;
+                ok[py][px] = ih < (uint32_t)h && iw < (uint32_t)w;
+                pi[py][px] = ((img * (uint32_t)h + ih) * (uint32_t)w + iw) * (uint32_t)c4 + cc;
+                zv[py][px] = ok[py][px] ? __ldg(reinterpret_cast<const float4*>(z) + pi[py][px]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                if (!ok[py][px]) continue;
+                // gradient at the ReLU output of this pixel: pooled gradients of the windows whose argmax is this pixel
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int dh = 0; dh <= py; ++dh)
+#pragma unroll
+                    for (int dw = 0; dw <= px; ++dw) {
+                        const unsigned pos = (unsigned)((py - 2 * dh + 1) * 3 + (px - 2 * dw + 1));
+                        const uchar4 m = am[dh][dw];
+                        const float4 dd = d[dh][dw];
+                        if (m.x == pos) g[0] += dd.x;
+                        if (m.y == pos) g[1] += dd.y;
+                        if (m.z == pos) g[2] += dd.z;
+                        if (m.w == pos) g[3] += dd.w;
+                    }
+                const float xv[4] = {zv[py][px].x, zv[py][px].y, zv[py][px].z, zv[py][px].w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (xv[j] - mu[j]) * is[j];
+                    const float gg = (xh * ga[j] + be[j]) > 0.f ? g[j] : 0.f;
+                    o[j] = kk[j] * (gg - sg[j] - xh * sgx[j]);
+                }
+                if (dx) reinterpret_cast<float4*>(dx)[pi[py][px]] = make_float4(o[0], o[1], o[2], o[3]);
+                if (dx_hi) store_planes(dx_hi, dx_lo, (int64_t)pi[py][px], o);
+            }
+    }
+}
+
 static int check_bn_shape(int64_t rows, int c) {
     AVID_REQUIRE(rows > 0, "bn: rows must be positive");
     AVID_REQUIRE(c >= 4 && c <= 1024 && (c & (c - 1)) == 0, "bn: c=%d must be a power of two in [4,1024]", c);
@@ -414,11 +511,11 @@ int avid_bn_relu_maxpool_backward_apply(const float* z, const uint8_t* argmax, c
     if (rc) return rc;
     AVID_REQUIRE(z && argmax && dyp && mean && invstd && gamma && beta && sums && (dz || dz_hi), "bn_relu_maxpool_backward_apply: NULL pointer");
     AVID_REQUIRE(dz_hi || !dz_lo, "bn_relu_maxpool_backward_apply: a lo plane needs the hi plane");
-    const int64_t rows = (int64_t)nt * h * w;
-    bn_relu_backward_apply_kernel<<<ew_grid(rows * (c >> 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        z, nullptr, mean, invstd, gamma, beta, sums, rows, c, dz, static_cast<__nv_bfloat16*>(dz_hi), static_cast<__nv_bfloat16*>(dz_lo), dgamma,
-        dbeta, PoolGather{argmax, dyp, h, w, ho, wo, z});
-    return check_launch("bn_relu_backward_apply_kernel(pool)");
+    const int64_t blocks4 = (int64_t)nt * ((h + 1) / 2) * ((w + 1) / 2) * (c >> 2);
+    bn_relu_pool_backward_apply_kernel<<<ew_grid(blocks4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, argmax, dyp, mean, invstd, gamma, beta, sums, nt, h, w, c, ho, wo, dz, static_cast<__nv_bfloat16*>(dz_hi),
+        static_cast<__nv_bfloat16*>(dz_lo), dgamma, dbeta);
+    return check_launch("bn_relu_pool_backward_apply_kernel");
 }
 
 int avid_bn_relu_backward_apply(const float* x, const float* dy, const float* mean, const float* invstd,
