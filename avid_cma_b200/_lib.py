@@ -61,6 +61,10 @@ _SIGNATURES = {
     "avid_cma_topk_begin": (C.c_int, [_L, _P, _Z, _P]),
     "avid_cma_topk_scan": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _I, _P, _Z, _P]),
     "avid_cma_topk_finish": (C.c_int, [_L, _I, _P, _P, _Z, _P]),
+    "avid_cma_to_half": (C.c_int, [_P, _P, _L, _P]),
+    "avid_cma_topk_scan_tc": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _P, _Z, _P]),
+    "avid_cma_topk_rescore": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _P, _Z, _P]),
+    "avid_cma_topk_certify": (C.c_int, [_L, _I, _F, _P, _Z, _P, _P, _P]),
     "avid_conv_forward": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _I, _P]),
     "avid_conv_dgrad": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _I, _P]),
     "avid_conv_wgrad": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _I, _P]),

@@ -85,6 +85,13 @@ class AVIDSimilarityPositiveExpansion(AVIDSimilarityMemoryBank):
             dist.broadcast(ca, r)
             yield cv, ca, lo
 
+    def _any_rank(self, flag):
+        """OR of a boolean over the ranks (the shard stream of a sharded bank is collective: every rank must walk it again
+        if any rank has queries to re-mine)."""
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.view1_mem.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+
     def find_correspondences(self):
         """avid_cma.py:211-229: every rank mines the positives of N/W queries against all N candidates; the slices are
         all-gathered (the reference mines everything on rank 0 and broadcasts)."""
@@ -102,7 +109,8 @@ class AVIDSimilarityPositiveExpansion(AVIDSimilarityMemoryBank):
         else:
             qv, qa = self.view1_mem[lo:hi], self.view2_mem[lo:hi]
         if hi > lo or self.sharded:
-            res = ops.cma_topk(qv, qa, self._candidate_shards(), pos_k, self.sampling_args['type'])
+            res = ops.cma_topk(qv, qa, self._candidate_shards, pos_k, self.sampling_args['type'],
+                               any_rank=self._any_rank if self.sharded else None)
             mine[:hi - lo] = res
         if self.distributed:
             full = torch.empty(world * per, pos_k, dtype=torch.int32, device=dev)

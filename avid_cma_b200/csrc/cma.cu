@@ -133,10 +133,11 @@ __global__ void __launch_bounds__(256, 1) cma_scan_kernel(const float* q_video, 
         }
 }
 
-__global__ void cma_begin_kernel(float* top_val, int* top_idx, size_t n) {
+__global__ void cma_begin_kernel(float* top_val, int* top_idx, float* top_exact, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         top_val[i] = -INFINITY;
         top_idx[i] = -1;
+        top_exact[i] = -INFINITY;
     }
 }
 
@@ -174,7 +175,8 @@ using namespace avid;
 extern "C" {
 
 size_t avid_cma_topk_workspace_bytes(int64_t num_queries) {
-    return num_queries > 0 ? (size_t)num_queries * kSlots * (sizeof(float) + sizeof(int)) : 0;
+    // running top lists: similarity, candidate row and -- for the tensor-core path (cma_tc.cu) -- the exact fp32 similarity
+    return num_queries > 0 ? (size_t)num_queries * kSlots * (2 * sizeof(float) + sizeof(int)) : 0;
 }
 
 static int cma_split(int64_t num_queries, void* workspace, size_t bytes, float** val, int** idx) {
@@ -192,7 +194,8 @@ int avid_cma_topk_begin(int64_t num_queries, void* workspace, size_t workspace_b
     float* val; int* idx;
     int rc = cma_split(num_queries, workspace, workspace_bytes, &val, &idx);
     if (rc) return rc;
-    cma_begin_kernel<<<4 * kNumSMs, 256, 0, static_cast<cudaStream_t>(stream)>>>(val, idx, (size_t)num_queries * kSlots);
+    cma_begin_kernel<<<4 * kNumSMs, 256, 0, static_cast<cudaStream_t>(stream)>>>(val, idx, reinterpret_cast<float*>(idx + (size_t)num_queries * kSlots),
+                                                                                 (size_t)num_queries * kSlots);
     return check_launch("cma_begin_kernel");
 }
 

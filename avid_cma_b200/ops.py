@@ -5,6 +5,8 @@ libavid_b200.so.  All tensors must be contiguous CUDA tensors on the current dev
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -204,19 +206,84 @@ def sample_negatives(y, num_neg, num_rows, seed, offset, positive_set=None):
 CMA_MODES = {"consensus": 0, "union": 1, "video": 2, "audio": 3}
 
 
-def cma_topk(q_video, q_audio, cand_shards, pos_k, mode="consensus"):
-    """cand_shards: iterable of (cand_video, cand_audio, cand_begin).  Returns (Q, pos_k) int32 sorted positives."""
-    if mode not in CMA_MODES:
-        raise ValueError(mode)
+CMA_EPS = 1.0e-3      # rigorous bound of |fp16-input similarity - exact similarity| for unit rows (2^-10 + fp32 accumulation slack)
+
+
+def _cma_to_half(x):
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    check(_lib.lib().avid_cma_to_half(_p(x), _p(out, torch.float16), x.numel(), _stream()))
+    return out
+
+
+def _shard_iter(cand_shards):
+    return cand_shards() if callable(cand_shards) else cand_shards
+
+
+def _cma_topk_exact(q_video, q_audio, cand_shards, pos_k, mode, run=True):
+    """fp32 CUDA-core search (csrc/cma.cu).  run=False only walks the shards (a rank without queries to re-mine must still
+    take part in the collectives that stream them)."""
     L = _lib.lib()
-    nq = q_video.shape[0]
-    ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(nq)), dtype=torch.uint8, device=q_video.device)
-    wp, wn = _p(ws, torch.uint8), ws.numel()
-    check(L.avid_cma_topk_begin(nq, wp, wn, _stream()))
-    for cv, ca, begin in cand_shards:
-        check(L.avid_cma_topk_scan(_p(q_video), _p(q_audio), nq, _p(cv), _p(ca), begin, cv.shape[0], CMA_MODES[mode], pos_k, wp, wn, _stream()))
+    nq = q_video.shape[0] if run else 0
+    if run:
+        ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(nq)), dtype=torch.uint8, device=q_video.device)
+        wp, wn = _p(ws, torch.uint8), ws.numel()
+        check(L.avid_cma_topk_begin(nq, wp, wn, _stream()))
+    for cv, ca, begin in _shard_iter(cand_shards):
+        if run:
+            check(L.avid_cma_topk_scan(_p(q_video), _p(q_audio), nq, _p(cv), _p(ca), begin, cv.shape[0], CMA_MODES[mode], pos_k, wp, wn, _stream()))
+    if not run:
+        return None
     out = torch.empty(nq, pos_k, dtype=torch.int32, device=q_video.device)
     check(L.avid_cma_topk_finish(nq, pos_k, _p(out, torch.int32), wp, wn, _stream()))
+    return out
+
+
+def cma_topk(q_video, q_audio, cand_shards, pos_k, mode="consensus", exact=None, any_rank=None, eps=CMA_EPS, stats=None):
+    """CMASampler.sample_instance for all query rows (avid_cma.py:42-73).  cand_shards: a list of (cand_video, cand_audio,
+    cand_begin), or a callable returning a fresh iterator of them (sharded runs stream the shards through collectives).
+    Returns (Q, pos_k) int32 sorted positives.
+
+    Default: tensor-core candidate generation + exact re-scoring + certificate (csrc/cma_tc.cu); queries without a certificate
+    are re-mined with the fp32 kernel, which needs a second walk over the shards -- `any_rank(flag) -> flag` must OR the flag
+    over the ranks when the shard iterator contains collectives.  exact=True (or AVID_CMA_EXACT=1): fp32 kernel only."""
+    if mode not in CMA_MODES:
+        raise ValueError(mode)
+    if exact is None:
+        exact = os.environ.get("AVID_CMA_EXACT", "0") == "1"
+    if exact:
+        return _cma_topk_exact(q_video, q_audio, cand_shards, pos_k, mode)
+    L = _lib.lib()
+    nq, dev = q_video.shape[0], q_video.device
+    ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(nq)), dtype=torch.uint8, device=dev)
+    wp, wn = _p(ws, torch.uint8), ws.numel()
+    check(L.avid_cma_topk_begin(nq, wp, wn, _stream()))
+    qv_h, qa_h = _cma_to_half(q_video), _cma_to_half(q_audio)
+    m = CMA_MODES[mode]
+    for cv, ca, begin in _shard_iter(cand_shards):
+        same = cv.data_ptr() == q_video.data_ptr() and cv.shape[0] == nq
+        cv_h, ca_h = (qv_h, qa_h) if same else (_cma_to_half(cv), _cma_to_half(ca))
+        check(L.avid_cma_topk_scan_tc(_p(qv_h, torch.float16), _p(qa_h, torch.float16), nq, _p(cv_h, torch.float16), _p(ca_h, torch.float16),
+                                      begin, cv.shape[0], m, wp, wn, _stream()))
+        check(L.avid_cma_topk_rescore(_p(q_video), _p(q_audio), nq, _p(cv), _p(ca), begin, cv.shape[0], m, wp, wn, _stream()))
+    fail_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    fail_list = torch.empty(nq, dtype=torch.int32, device=dev)
+    check(L.avid_cma_topk_certify(nq, pos_k, float(eps), wp, wn, _p(fail_count, torch.int32), _p(fail_list, torch.int32), _stream()))
+    out = torch.empty(nq, pos_k, dtype=torch.int32, device=dev)
+    check(L.avid_cma_topk_finish(nq, pos_k, _p(out, torch.int32), wp, wn, _stream()))
+    n_fail = int(fail_count.item())
+    if stats is not None:
+        stats["uncertified"] = n_fail
+    again = n_fail > 0
+    if any_rank is not None:
+        again = bool(any_rank(again))
+    if again:
+        if not (callable(cand_shards) or isinstance(cand_shards, (list, tuple))):
+            raise RuntimeError("cma_topk: re-mining needs a re-iterable shard source (pass a list or a callable)")
+        if n_fail > 0:
+            rows = fail_list[:n_fail].long()
+            out[rows] = _cma_topk_exact(q_video[rows].contiguous(), q_audio[rows].contiguous(), cand_shards, pos_k, mode)
+        else:
+            _cma_topk_exact(None, None, cand_shards, pos_k, mode, run=False)
     return out
 
 

@@ -156,6 +156,25 @@ int avid_cma_topk_scan(const float* q_video, const float* q_audio, int64_t num_q
 int avid_cma_topk_finish(int64_t num_queries, int32_t pos_k, int32_t* positive_set_out /* (num_queries, pos_k) */,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same search (avid_cma.py:52-70: mm, mm, min/max, topk) with the N x N similarity work on the tensor cores
+ * (csrc/cma_tc.cu): avid_cma_topk_scan_tc keeps an APPROXIMATE top-64 per query from fp16 inputs (tcgen05, fp32
+ * accumulation; *_h are fp16 copies of the rows made by avid_cma_to_half), avid_cma_topk_rescore replaces the scores of
+ * the listed candidates of the current shard by exact fp32 dot products, and -- after the last shard --
+ * avid_cma_topk_certify proves per query that the exact top-(pos_k+1) lies inside the list (every outside candidate
+ * has exact similarity <= list minimum + eps; eps = 1e-3 bounds the fp16 rounding of a dot product of unit rows) and
+ * moves it to the front for avid_cma_topk_finish.  Queries without a certificate are counted in *fail_count and
+ * listed in fail_list (num_queries entries); the caller re-mines them with avid_cma_topk_scan.  Same workspace,
+ * same begin / finish calls, same shard protocol as the fp32 path. */
+int avid_cma_to_half(const float* x, void* out_f16, int64_t n, void* stream);
+int avid_cma_topk_scan_tc(const void* q_video_h, const void* q_audio_h, int64_t num_queries,
+                          const void* cand_video_h, const void* cand_audio_h, int64_t cand_begin, int64_t num_cand,
+                          int32_t mode, void* workspace, size_t workspace_bytes, void* stream);
+int avid_cma_topk_rescore(const float* q_video, const float* q_audio, int64_t num_queries,
+                          const float* cand_video, const float* cand_audio, int64_t cand_begin, int64_t num_cand,
+                          int32_t mode, void* workspace, size_t workspace_bytes, void* stream);
+int avid_cma_topk_certify(int64_t num_queries, int32_t pos_k, float eps, void* workspace, size_t workspace_bytes,
+                          int32_t* fail_count, int32_t* fail_list, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Encoders: (2+1)D / 2D convolution stacks, train-mode BatchNorm, pools, heads */
 /* ------------------------------------------------------------------------- */

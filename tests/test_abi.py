@@ -34,7 +34,7 @@ def test_struct_layout_matches_header(lib):
 def test_workspace_queries_are_host_only(lib):
     assert lib.avid_nce_workspace_bytes(64, 1024, 0, 2) > 64 * 128 * 4 * 2
     assert lib.avid_nce_workspace_bytes(0, 1024, 0, 2) == 0
-    assert lib.avid_cma_topk_workspace_bytes(1000) == 1000 * 64 * 8
+    assert lib.avid_cma_topk_workspace_bytes(1000) == 1000 * 64 * 12
 
 
 def test_invalid_arguments_report_einval(lib):

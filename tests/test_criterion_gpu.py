@@ -278,3 +278,34 @@ def test_cma_topk_vs_oracle(mode):
     assert mism.mean() < 0.01, mism.mean()
     sub = ops.cma_topk(gv[500:563].contiguous(), ga[500:563].contiguous(), [(gv, ga, 0)], pos_k, mode).cpu().numpy()
     assert (sub == got[500:563]).all()
+
+
+@pytest.mark.parametrize("mode", ["consensus", "union", "video", "audio"])
+def test_cma_tensor_core_path_equals_fp32_path(mode):
+    """Tensor-core candidate generation + exact re-scoring + certificate (csrc/cma_tc.cu) returns the positive sets of the
+    fp32 kernel (csrc/cma.cu); every query is certified at the rigorous eps, and when the certificate is made to fail
+    (huge eps) the re-mining fallback returns the same sets."""
+    from avid_cma_b200 import ops
+    N, pos_k = 2000 + 77, 32
+    bv, ba = synth.bank(N, seed=62, tag="bank_v").to(DEV), synth.bank(N, seed=62, tag="bank_a").to(DEV)
+    cut = 1000 + 13
+    shards = [(bv[:cut].contiguous(), ba[:cut].contiguous(), 0), (bv[cut:].contiguous(), ba[cut:].contiguous(), cut)]
+    exact = ops.cma_topk(bv, ba, shards, pos_k, mode, exact=True)
+    st = {}
+    tc = ops.cma_topk(bv, ba, shards, pos_k, mode, exact=False, stats=st)
+    assert st["uncertified"] == 0
+    mism = (tc != exact).any(1).float().mean()
+    assert float(mism) < 0.005, float(mism)          # summation order differs in the last bit: only exact ties at the boundary may swap
+    st2 = {}
+    fb = ops.cma_topk(bv, ba, shards, pos_k, mode, exact=False, eps=10.0, stats=st2)
+    assert st2["uncertified"] == N
+    assert torch.equal(fb, exact)
+    # planted near-duplicates: rows 5 and 1500 almost equal -> each is the other's best positive
+    bv2, ba2 = bv.clone(), ba.clone()
+    bv2[1500] = torch.nn.functional.normalize(bv2[5] + 1e-3 * bv2[1500], dim=0)
+    ba2[1500] = torch.nn.functional.normalize(ba2[5] + 1e-3 * ba2[1500], dim=0)
+    tc2 = ops.cma_topk(bv2, ba2, [(bv2, ba2, 0)], pos_k, mode, exact=False)
+    ex2 = ops.cma_topk(bv2, ba2, [(bv2, ba2, 0)], pos_k, mode, exact=True)
+    assert float((tc2 != ex2).any(1).float().mean()) < 0.005
+    assert 1500 in tc2[5].tolist() or 5 in tc2[5].tolist()
+
