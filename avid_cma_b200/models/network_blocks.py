@@ -21,7 +21,7 @@ from .. import ops
 from ..ops import Act
 
 
-FUSE_MIN_K = int(os.environ.get('AVID_FUSE_BN_BWD_MIN_K', '2304'))   # contraction length (co * taps) from which dgrad also reduces BN backward
+FUSE_MIN_K = int(os.environ.get('AVID_FUSE_BN_BWD_MIN_K', '192'))    # contraction length (co * taps) from which dgrad also reduces BN backward
 
 
 def _triple(v, fill=1):
@@ -81,9 +81,10 @@ class ConvOp:
     def can_fuse_bn_backward(self):
         """The tensor-core input gradient can also reduce the previous layer's BatchNorm backward (every input pixel must be
         written by a computed tile: filter >= stride)."""
-        # Measured on B200: the extra epilogue work (z tile, BatchNorm constants, two column reductions) is hidden behind the next
-        # tile's TMA / MMA only when that main loop is long; with short loops (64-channel layers, temporal taps) it made the
-        # input-gradient kernels epilogue-bound (5.3 -> 9.7 ms per step), so the fusion is used from K >= FUSE_MIN_K on.
+        # Measured on B200 (scripts/gpu_fuse_sweep.sh): with the 8-warp epilogue of conv_tc_kernel the fusion pays for every layer
+        # with K >= 192 (input-gradient launches 4.8 -> 5.7 ms per step, but 1.9 ms of separate reduction passes disappear:
+        # 2123 -> 2176 clips/s); only the 1x1x1 residual convolutions (K = 64..256 with one tap) stay unfused.  With the earlier
+        # 4-warp epilogue the same fusion made the 64-channel launches epilogue-bound (5.3 -> 9.7 ms) and was limited to K >= 2304.
         k_total = self.conv.out_channels * self.k[0] * self.k[1] * self.k[2]
         return self.tc and all(k >= s for k, s in zip(self.k, self.s)) and k_total >= FUSE_MIN_K
 

@@ -6,6 +6,6 @@ timeout 600 python bench.py --steps 10 --warmup 3 --math ${MATH:-bf16x3} --no-cp
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_quick.json"))
-print({k:d[k] for k in ("value","ms_per_step","gpu_launches","last_loss")}, d["e2e"]["value"])
+print({k:d[k] for k in ("value","ms_per_step","gpu_launches","last_loss","clocks")}, d["e2e"]["value"])
 for k,v in d["roofline"]["families"].items(): print(k, {a:round(b,3) for a,b in v.items()})
 PY
