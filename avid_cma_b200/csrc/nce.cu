@@ -8,9 +8,11 @@
 //           groups of 8 lanes own one row each (16 columns per lane, 128-byte coalesced group loads), 2 x 4 rows x
 //           2 banks in flight per warp; dot product = 16 FMAs + 3 shuffles, the NCE math runs per group, the
 //           gradient axpy needs no broadcast.  Partial (grad_hat, loss) per split go to the workspace.
-// Kernel 2  nce_reduce_finalize_kernel  grid (B) x 256 threads: fixed-order sum over splits
-//           (deterministic), backward of F.normalize, and -- in the last CTA to finish -- the
-//           batch means and the coefficient mix.
+//           The LAST split CTA of a query (ticket counter) sums the partials in a fixed order (deterministic) and applies
+//           the backward of F.normalize; the last query forms the batch means and the coefficient mix: one launch per step.
+//           The B + 1 ticket counters live at the start of the workspace, must be zero on entry and are left zero.
+// Kernel 2  nce_reduce_finalize_kernel  grid (B) x 256 threads: the same tail as a separate launch, for the sharded
+//           protocol (avid_nce_finalize runs after the all-reduce of the partials).
 #include <math.h>
 #include "common.cuh"
 
@@ -46,9 +48,17 @@ struct NceParams {
     float* scores;      // optional [num_keys][B][1 + pos_k_stride + K]
     int score_pos_k;    // pos_k used for the score layout
     int64_t* neg_idx_out;
-    unsigned int* counter;
+    unsigned int* counter;      // [B + 1] tickets: splits done per query, queries done; zero on entry, left zero
     bool need[2][2];    // need[bank][ctx]: some key scores this bank against this context
     bool bank_used[2];
+    // tail of the fused kernel: the last split of a query reduces it, the last query forms the batch means
+    float* grad_hat[2];         // optional (B,128): reduced gradient w.r.t. the normalised embedding (sharded protocol)
+    float* loss_part;           // (num_keys, B) per-query loss terms
+    float* grad[2];             // (B,128) gradient w.r.t. the raw embedding (do_finalize)
+    float* loss_keys;
+    float* loss_total;
+    float weights[AVID_MAX_KEYS];
+    int do_finalize;
 };
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -97,7 +107,6 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     const int b = blockIdx.x, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, l8 = lane & 7;
-    if (b == 0 && split == 0 && threadIdx.x == 0 && p.counter) *p.counter = 0u;
 
     float4 e_ctx[2][4];
     load_normalized(p.emb[0], b, l8, e_ctx[0]);
@@ -290,6 +299,75 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
         for (int w = 0; w < kGatherWarps; ++w) t += s_loss[w][k];
         p.part_loss[((size_t)split * p.num_keys + k) * p.B + b] = t;
     }
+
+    // ---- the last split CTA of this query reduces it (fixed order over splits: deterministic) ----
+    __shared__ unsigned int s_ticket;
+    __shared__ float s_red[8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.counter + b, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(p.splits - 1)) return;
+    __threadfence();
+    const int e = threadIdx.x;          // 0..127: one embedding column, both contexts
+    float g[2];
+#pragma unroll
+    for (int ctx = 0; ctx < 2; ++ctx) {
+        float a = 0.f;
+        for (int s = 0; s < p.splits; ++s) a += __ldcg(p.part_grad + ((size_t)(s * 2 + ctx) * p.B + b) * kD + e);
+        g[ctx] = a;
+        if (p.grad_hat[ctx]) p.grad_hat[ctx][(size_t)b * kD + e] = a;
+    }
+    if (e < p.num_keys) {
+        float l = 0.f;
+        for (int s = 0; s < p.splits; ++s) l += __ldcg(p.part_loss + ((size_t)s * p.num_keys + e) * p.B + b);
+        p.loss_part[(size_t)e * p.B + b] = l;
+    }
+    if (e == 0) p.counter[b] = 0u;      // ready for the next launch
+    if (!p.do_finalize) return;
+
+    // backward of x -> x / max(||x||, eps):  (g - ehat <ehat, g>) / ||x||   (g / eps when clamped)
+#pragma unroll
+    for (int ctx = 0; ctx < 2; ++ctx) {
+        const float x = p.emb[ctx][(size_t)b * kD + e];
+        const float xx = warp_sum(x * x);
+        __syncthreads();
+        if (lane == 0) s_red[warp] = xx;
+        __syncthreads();
+        const float n = sqrtf(s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+        const bool clamped = !(n > 1e-12f);
+        const float eh = clamped ? 0.f : x / n;
+        const float pg = warp_sum(eh * g[ctx]);
+        if (lane == 0) s_red[4 + warp] = pg;
+        __syncthreads();
+        const float dotp = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+        p.grad[ctx][(size_t)b * kD + e] = clamped ? g[ctx] / 1e-12f : (g[ctx] - eh * dotp) / n;
+    }
+
+    // ---- the last query: batch means + coefficient mix (avid.py:216-233 / avid_cma.py:338-359) ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.counter + p.B, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(p.B - 1)) return;
+    __threadfence();
+    __shared__ float s_keyloss[AVID_MAX_KEYS];
+    for (int k = warp; k < p.num_keys; k += kGatherWarps) {
+        float sum = 0.f;
+        for (int i = lane; i < p.B; i += 32) sum += __ldcg(p.loss_part + (size_t)k * p.B + i);
+        sum = warp_sum(sum) * p.inv_mean_batch;
+        if (lane == 0) {
+            s_keyloss[k] = sum;
+            p.loss_keys[k] = sum;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int k = 0; k < p.num_keys; ++k) tot += p.weights[k] * s_keyloss[k];
+        *p.loss_total = tot;
+        p.counter[p.B] = 0u;
+    }
 }
 
 struct FinalizeParams {
@@ -369,6 +447,7 @@ __global__ void __launch_bounds__(256) nce_reduce_finalize_kernel(const Finalize
         float tot = 0.f;
         for (int k = 0; k < p.num_keys; ++k) tot += p.weights[k] * s_keyloss[k];
         *p.loss_total = tot;
+        *p.counter = 0u;        // the ticket counters of the workspace are left zero (nce_gather_kernel relies on it)
     }
 }
 
@@ -444,7 +523,7 @@ static Workspace carve(void* base, int B, int K, int pos_k, int num_keys, bool w
         off += (nbytes + 255) & ~size_t(255);
         return r;
     };
-    w.counter = reinterpret_cast<unsigned int*>(take(256));
+    w.counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * (size_t)(B + 1)));      // zero on entry, left zero
     w.part_grad = reinterpret_cast<float*>(take(sizeof(float) * (size_t)splits * 2 * B * kD));
     w.part_loss = reinterpret_cast<float*>(take(sizeof(float) * (size_t)splits * AVID_MAX_KEYS * B));
     w.grad_hat[0] = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * kD));
@@ -525,25 +604,14 @@ int avid_nce_forward_backward(const avid_nce_args_t* a, void* workspace, size_t 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     p.part_grad = w.part_grad;  p.part_loss = w.part_loss;  p.counter = w.counter;
+    p.grad_hat[0] = a->grad_hat_video;  p.grad_hat[1] = a->grad_hat_audio;
+    p.loss_part = a->loss_part ? a->loss_part : w.loss_part;
+    p.grad[0] = a->grad_video;  p.grad[1] = a->grad_audio;
+    p.loss_keys = a->loss_keys;  p.loss_total = a->loss_total;
+    for (int k = 0; k < AVID_MAX_KEYS; ++k) p.weights[k] = k < a->num_keys ? a->keys[k].weight : 0.f;
+    p.do_finalize = sharded ? 0 : 1;
     nce_gather_kernel<<<dim3(a->batch, p.splits), kGatherThreads, 0, st>>>(p);
-    if ((rc = check_launch("nce_gather_kernel"))) return rc;
-
-    FinalizeParams f;
-    f.emb[0] = a->emb_video;  f.emb[1] = a->emb_audio;
-    f.B = a->batch;  f.num_keys = a->num_keys;  f.splits = p.splits;
-    f.inv_mean_batch = p.inv_mean_batch;
-    for (int k = 0; k < AVID_MAX_KEYS; ++k) f.weights[k] = k < a->num_keys ? a->keys[k].weight : 0.f;
-    f.part_grad = w.part_grad;  f.part_loss = w.part_loss;
-    f.grad_hat[0] = a->grad_hat_video ? a->grad_hat_video : w.grad_hat[0];
-    f.grad_hat[1] = a->grad_hat_audio ? a->grad_hat_audio : w.grad_hat[1];
-    f.loss_part = a->loss_part ? a->loss_part : w.loss_part;
-    f.grad[0] = a->grad_video;  f.grad[1] = a->grad_audio;
-    f.loss_keys = a->loss_keys;  f.loss_total = a->loss_total;
-    f.counter = w.counter;
-    f.do_reduce = 1;
-    f.do_finalize = sharded ? 0 : 1;
-    nce_reduce_finalize_kernel<<<a->batch, 256, 0, st>>>(f);
-    return check_launch("nce_reduce_finalize_kernel");
+    return check_launch("nce_gather_kernel");
 }
 
 int avid_nce_finalize(const avid_nce_args_t* a, void* workspace, size_t workspace_bytes, void* stream) {

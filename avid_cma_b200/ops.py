@@ -127,7 +127,7 @@ def reset_launch_count():
 
 def nce_workspace(batch, num_neg, pos_k, num_keys, device):
     n = int(_lib.lib().avid_nce_workspace_bytes(batch, num_neg, max(pos_k, 0), num_keys))
-    return torch.empty(n, dtype=torch.uint8, device=device)
+    return torch.zeros(n, dtype=torch.uint8, device=device)     # the ticket counters at its start must be zero before the first call
 
 
 def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows=None, row_begin=0, row_end=None,

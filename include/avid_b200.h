@@ -107,13 +107,17 @@ typedef struct avid_nce_args {
     float*         loss_part;      /* (num_keys, B) per-instance loss terms (before the batch mean) */
 } avid_nce_args_t;
 
+/* Scratch of the criterion kernels.  Its first 4 * (batch + 1) bytes are ticket counters (splits done per query, queries
+ * done) that MUST BE ZERO before the first call with a given workspace; every call leaves them zero again, so a
+ * workspace zeroed once at allocation can be reused for the life of the criterion. */
 size_t avid_nce_workspace_bytes(int32_t batch, int32_t num_neg, int32_t pos_k, int32_t num_keys);
 
 /* Fused replacement for: F.normalize (avid.py:52-53), positive/negative gathers
  * (avid.py:57-62 / avid_cma.py:158-165,196-209), bmm/T scores (avid.py:65-75),
  * NCECriterion.forward (nce.py:38-58) for every key, the coefficient mix
  * (avid.py:216-233 / avid_cma.py:338-359) AND the backward of all of those
- * w.r.t. the embeddings, in one pass over the gathered rows.                      */
+ * w.r.t. the embeddings, in one pass over the gathered rows and ONE kernel launch:
+ * the last CTA of a query reduces it, the last query forms the batch means.       */
 int avid_nce_forward_backward(const avid_nce_args_t* args_host, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Second half of the sharded protocol: given (all-reduced) grad_hat_* and loss_part,
