@@ -1,6 +1,7 @@
 // Projection heads (models/av_wrapper.py:17-33): y = x W^T + b (+ReLU) and its backward, W in the
 // PyTorch [out, in] layout.  The heads are 0.01 % of the step's FLOPs; these are
 // plain fp32 kernels sized for rows <= a few hundred, in/out <= 1024.
+#include <stdint.h>
 #include "common.cuh"
 
 namespace avid {
@@ -15,15 +16,35 @@ namespace avid {
 // 45-80 us per layer on shuffles and dependent loads: 0.75 ms per step for 0.003 % of its FLOPs.)
 constexpr int kLT = 32;
 
-__device__ __forceinline__ void load_tile32(float (*dst)[kLT + 1], const float* __restrict__ src, int rows_total, int k_total, int r0, int k0,
-                                            long s_r, long s_k, int tid) {
-    // dst[k][r] = src[(r0 + r) * s_r + (k0 + k) * s_k]
-    for (int e = tid; e < kLT * kLT; e += 256) {
-        const int fast = e & 31, slow = e >> 5;
-        const int r = s_k == 1 ? slow : fast, k = s_k == 1 ? fast : slow;
-        float v = 0.f;
-        if (r0 + r < rows_total && k0 + k < k_total) v = __ldg(src + (long)(r0 + r) * s_r + (long)(k0 + k) * s_k);
-        dst[k][r] = v;
+// one float4 of a 32 x 32 tile per thread, along whichever index is contiguous in memory (s_k == 1: along k, else along r);
+// tiles that cross the matrix edge fall back to guarded scalar loads
+struct TileFrag {
+    float v[4];
+};
+__device__ __forceinline__ TileFrag fetch_frag(const float* __restrict__ src, int rows_total, int k_total, int r0, int k0, long s_r, long s_k, int tid) {
+    const int c = (tid & 7) * 4, o = tid >> 3;
+    const int r = s_k == 1 ? o : c, k = s_k == 1 ? c : o;
+    TileFrag f;
+    const bool full = s_k == 1 ? (r0 + r < rows_total && k0 + k + 3 < k_total) : (r0 + r + 3 < rows_total && k0 + k < k_total);
+    const float* ptr = src + (long)(r0 + r) * s_r + (long)(k0 + k) * s_k;
+    if (full && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(ptr));
+        f.v[0] = q.x; f.v[1] = q.y; f.v[2] = q.z; f.v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = s_k == 1 ? r : r + j, kk = s_k == 1 ? k + j : k;
+            f.v[j] = (r0 + rr < rows_total && k0 + kk < k_total) ? __ldg(src + (long)(r0 + rr) * s_r + (long)(k0 + kk) * s_k) : 0.f;
+        }
+    }
+    return f;
+}
+__device__ __forceinline__ void store_frag(float (*dst)[kLT + 1], const TileFrag& f, long s_k, int tid) {
+    const int c = (tid & 7) * 4, o = tid >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (s_k == 1) dst[c + j][o] = f.v[j];      // dst[k][r]
+        else dst[o][c + j] = f.v[j];
     }
 }
 
@@ -35,10 +56,17 @@ __global__ void __launch_bounds__(256) linear_gemm_kernel(const float* __restric
     const int m0 = blockIdx.y * kLT, n0 = blockIdx.x * kLT;
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     float asum[2] = {0.f, 0.f};
+    // the next k-block is fetched into registers while the current one is multiplied: the layers are tiny (one partial wave), so
+    // the kernel is a latency chain and every un-overlapped global load shows
+    TileFrag fa = fetch_frag(A, M, K, m0, 0, a_m, a_k, tid), fb = fetch_frag(B, N, K, n0, 0, b_n, b_k, tid);
     for (int k0 = 0; k0 < K; k0 += kLT) {
-        load_tile32(sa, A, M, K, m0, k0, a_m, a_k, tid);
-        load_tile32(sb, B, N, K, n0, k0, b_n, b_k, tid);
+        store_frag(sa, fa, a_k, tid);
+        store_frag(sb, fb, b_k, tid);
         __syncthreads();
+        if (k0 + kLT < K) {
+            fa = fetch_frag(A, M, K, m0, k0 + kLT, a_m, a_k, tid);
+            fb = fetch_frag(B, N, K, n0, k0 + kLT, b_n, b_k, tid);
+        }
 #pragma unroll
         for (int k = 0; k < kLT; ++k) {
             const float a0 = sa[k][ty], a1 = sa[k][ty + 16], b0 = sb[k][tx], b1 = sb[k][tx + 16];
