@@ -38,9 +38,16 @@ def _p(t, dtype=torch.float32, optional=False):
 _prof = None
 
 
-def profile_begin():
-    global _prof
+_prof_all = False
+
+
+def profile_begin(all_families=None):
+    """Start recording CUDA-event pairs around the tensor-core conv launches and the fused criterion (bench.py roofline).
+    all_families (or AVID_PROFILE_ALL=1): also time the BatchNorm / layout / optimizer wrappers -- ~4x more events per step, for
+    diagnostic runs only (the event records themselves cost about a millisecond per step)."""
+    global _prof, _prof_all
     _prof = []
+    _prof_all = os.environ.get("AVID_PROFILE_ALL", "0") == "1" if all_families is None else bool(all_families)
 
 
 def profile_end():
@@ -64,6 +71,21 @@ def _t1(e0, name, work):
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         _prof.append((name, work, e0, e1))
+
+
+def _timed(name):
+    """Time a wrapper's launches as family `name` when bench.py profiles a step (no algorithmic work attached)."""
+    def deco(fn):
+        def inner(*a, **k):
+            if not _prof_all:
+                return fn(*a, **k)
+            e0 = _t0()
+            r = fn(*a, **k)
+            _t1(e0, name, 0.0)
+            return r
+        inner.__name__, inner.__doc__ = fn.__name__, fn.__doc__
+        return inner
+    return deco
 
 
 class ZeroArena:
@@ -379,6 +401,7 @@ def conv_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo, ci_real=None):
     return dw
 
 
+@_timed("stem_pack")
 def stem_pack(x, wp, pad_left, need_lo=True):
     """(n, c, [t,] h, w) fp32 clip / spectrogram -> bf16 planes [n, t, h, wp, 4] of the stem kernels (c <= 4)."""
     n, c = x.shape[0], x.shape[1]
@@ -421,6 +444,7 @@ def stem_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo):
     return dw
 
 
+@_timed("filter_to_planes")
 def filter_to_planes(w, need_lo=True):
     """PyTorch conv weight (co, ci, *k) -> bf16 planes ((fwd_hi, fwd_lo) [taps, co, ci], (dgrad_hi, dgrad_lo) [taps, ci, co])."""
     co, ci = w.shape[0], w.shape[1]
@@ -444,6 +468,7 @@ def filter_to_tapmajor(w, ci_pad=None, transpose=True):
     return w_tap, w_tap_t
 
 
+@_timed("filter_from_tap")
 def filter_from_tapmajor(dw_tap, like):
     co, ci = like.shape[0], like.shape[1]
     taps, ci_pad = dw_tap.shape[0], dw_tap.shape[1]
@@ -452,6 +477,7 @@ def filter_from_tapmajor(dw_tap, like):
     return out
 
 
+@_timed("layout")
 def nchw_to_nhwc(x, c_pad=None):
     """(n, c, *spatial) -> (n, *spatial, c_pad)."""
     n, c = x.shape[0], x.shape[1]
@@ -482,6 +508,7 @@ class BNState:
         self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
 
 
+@_timed("bn_finalize")
 def bn_train_stats(x, gamma, beta, running_mean, running_var, eps=BN_EPS, momentum=BN_MOMENTUM, state=None):
     """x (..., c) channels-last.  Computes batch statistics, updates running stats, returns BNState.  With `state` given its
     `stats` were already accumulated by the producing convolution's epilogue and only the finalize kernel runs."""
@@ -528,6 +555,7 @@ def bn_relu_forward(x, scale, shift, out=None):
     return out
 
 
+@_timed("bn_relu_fwd")
 def bn_relu_forward_act(x, scale, shift, want_f32, want_planes, x3):
     """relu(x * scale + shift) as an Act with the requested representations, in one pass over x."""
     c = x.shape[-1]
@@ -545,6 +573,7 @@ def bn_relu_backward(x, dy, s, gamma, beta, dx=None):
     return act.f32, dgamma, dbeta
 
 
+@_timed("bn_relu_bwd")
 def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=None, sums=None):
     """Backward of y = relu(bn_train(x)); the gradient w.r.t. x as an Act (fp32 and / or bf16 planes).  `sums`: the reduction
     was already done by the epilogue of the input-gradient launch that produced dy (conv_dgrad_tc(bn_fuse=...))."""
@@ -567,6 +596,7 @@ def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=No
     return Act(dx if want_f32 else None, hi, lo), dgamma, dbeta
 
 
+@_timed("bn_pool_fwd")
 def bn_relu_maxpool_forward(z, scale, shift, want_f32, want_planes, x3):
     """maxpool_1x3x3(relu(z * scale + shift)) without materialising the ReLU output.  z (n, t, h, w, c).
     Returns (Act of the pooled tensor (n, t, ho, wo, c), argmax uint8)."""
@@ -582,6 +612,7 @@ def bn_relu_maxpool_forward(z, scale, shift, want_f32, want_planes, x3):
     return Act(p, hi, lo), am
 
 
+@_timed("bn_pool_bwd")
 def bn_relu_maxpool_backward_act(z, pooled, argmax, dyp, s, gamma, beta, want_f32, want_planes, x3):
     """Backward of pooled = maxpool(relu(bn_train(z))): the gradient w.r.t. z as an Act, dgamma, dbeta."""
     n, t, h, w, c = z.shape
@@ -617,6 +648,7 @@ def maxpool_1x3x3_backward(argmax, dy, in_shape):
     return dx
 
 
+@_timed("global_pool")
 def global_maxpool_forward(x):
     """x (n, ..., c) -> (y (n, c), argmax (n, c) int32)."""
     n, c = x.shape[0], x.shape[-1]
@@ -627,6 +659,7 @@ def global_maxpool_forward(x):
     return y, am
 
 
+@_timed("global_pool")
 def global_maxpool_backward(dy, argmax, shape):
     dx = torch.zeros(shape, dtype=torch.float32, device=dy.device)
     n, c = dy.shape
@@ -634,6 +667,7 @@ def global_maxpool_backward(dy, argmax, shape):
     return dx
 
 
+@_timed("linear")
 def linear_forward(x, w, b, relu):
     rows, in_f = x.shape
     out_f = w.shape[0]
@@ -642,6 +676,7 @@ def linear_forward(x, w, b, relu):
     return y
 
 
+@_timed("linear")
 def linear_backward(x, w, y, dy, relu, need_dx=True):
     """dy is modified in place when relu.  Returns (dx or None, dw, db)."""
     rows, in_f = x.shape
@@ -658,6 +693,7 @@ def add_(a, b):
     return a
 
 
+@_timed("adam")
 def adam_step_multi_(params, grads, exp_avgs, exp_avg_sqs, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
     """One Adam update of many fp32 tensors (32 per kernel launch)."""
     n = len(params)
