@@ -291,12 +291,19 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const bool has_work = (int)blockIdx.x < p.num_tiles;
+    // The temporal taps are split over the CTAs (CTA i works on tap i % kt of the tiles i / kt, i / kt + gridDim.x / kt, ...): a CTA
+    // then needs only two accumulators (row parities), which leaves TMEM room for the wide bf16x3 form x_hi x [dZ_hi | dZ_lo]
+    // (N = 128, the dZ planes are 16 KB apart = the descriptor's leading-dimension offset) + x_lo x dZ_hi: 14 KB instead of
+    // 18 KB of operand fetch per k-step of this fetch-bound kernel.  The kt CTAs of a tile group walk the same tiles, so the
+    // dZ tiles they share come from L2.
+    const int a_only = blockIdx.x % p.kt, cta = blockIdx.x / p.kt, ctas = gridDim.x / p.kt;
+    constexpr int kAccW = X3 ? 2 * kStemCo : kStemCo;      // accumulator columns per (tap, parity)
+    const bool has_work = cta < p.num_tiles;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         int stage = 0, phase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = cta; tile < p.num_tiles; tile += ctas, ++it) {
             int n_i, t_o, h0, w0;
             tile_coords(p, tile, n_i, t_o, h0, w0);
             const int buf = it & 1;
@@ -304,7 +311,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
             mbar_expect_tx(&dz_full[buf], (uint32_t)(planes * kDzBytes));
             for (int pl = 0; pl < planes; ++pl)
                 tma_load_5d(dz_smem + (buf * planes + pl) * kDzBytes, pl ? &map_d_lo : &map_d_hi, &dz_full[buf], 0, w0, h0, t_o, n_i);
-            for (int a = 0; a < p.kt; ++a)
+            for (int a = a_only; a <= a_only; ++a)
                 for (int par = 0; par < 2 && par < p.kh; ++par)
                     for (int pl = 0; pl < planes; ++pl) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -317,17 +324,18 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer: A = x slot (MN-major, 64-byte swizzle, 4 tap atoms one row apart), B = dZ (MN-major, 128-byte swizzle) =====
         constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 1, 1);
+        constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * kStemCo, 1, 1);
         const uint64_t ring_desc = make_smem_desc_sw64(0, kRowBytes, 512) + (smem_u32(ring) >> 4);
-        const uint64_t dz_desc = make_smem_desc_sw128(0, 16, 1024) + (smem_u32(dz_smem) >> 4);
+        const uint64_t dz_desc = make_smem_desc_sw128(0, X3 ? kDzBytes : 16, 1024) + (smem_u32(dz_smem) >> 4);
         int stage = 0, phase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = cta; tile < p.num_tiles; tile += ctas, ++it) {
             const int buf = it & 1;
             mbar_wait(&dz_full[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint64_t dz_hi = dz_desc + (uint32_t)((buf * planes * kDzBytes) >> 4);
-            for (int a = 0; a < p.kt; ++a)
+            for (int a = a_only; a <= a_only; ++a)
                 for (int par = 0; par < 2 && par < p.kh; ++par) {
-                    const uint32_t acc = tmem_base + (a * 2 + par) * kStemCo;
+                    const uint32_t acc = tmem_base + par * kAccW;
 #pragma unroll
                     for (int pl = 0; pl < (X3 ? 2 : 1); ++pl) {
                         mbar_wait(&full_bar[stage], phase);
@@ -338,8 +346,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                             const uint64_t da = slot + (uint32_t)((ks * kRowBytes) >> 4);
                             const uint64_t db_hi = dz_hi + (uint32_t)((ks * 2048) >> 4);
                             if (pl == 0) {
-                                umma_bf16(acc, da, db_hi, idesc, (it | ks) != 0);
-                                if (X3) umma_bf16(acc, da, db_hi + (uint32_t)(kDzBytes >> 4), idesc, 1);
+                                umma_bf16(acc, da, db_hi, X3 ? idesc2 : idesc, (it | ks) != 0);      // x_hi x [dZ_hi | dZ_lo]
                             } else {
                                 umma_bf16(acc, da, db_hi, idesc, 1);
                             }
@@ -358,16 +365,23 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int kwi = (r & 31) >> 2, c = r & 3;
-        for (int a = 0; a < p.kt; ++a)
+        for (int a = a_only; a <= a_only; ++a)
             for (int par = 0; par < 2 && par < p.kh; ++par) {
                 const int kh = par + 2 * (r >> 5);
                 const bool valid = kh < p.kh && kwi < p.kw && c < p.ci;
                 float* dst = dfilt + ((size_t)(((a * p.kh + kh) * p.kw + kwi) * 4 + c)) * kStemCo;
-                const uint32_t taddr = tmem_base + (a * 2 + par) * kStemCo + ((uint32_t)(q * 32) << 16);
+                const uint32_t taddr = tmem_base + par * kAccW + ((uint32_t)(q * 32) << 16);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + j * 32, v);
+                    if (X3) {
+                        uint32_t v2[32];
+                        tmem_ld_32x32b_x32(taddr + kStemCo + j * 32, v2);      // the x_hi x dZ_lo half
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) v[u] = __float_as_uint(__uint_as_float(v[u]) + __uint_as_float(v2[u]));
+                    }
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
@@ -509,7 +523,7 @@ int stem_wgrad_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_l
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     const int smem = 1024 + 2 * planes * kDzBytes + p.stages * kSlotBytes + 256;
     uint32_t cols = 32;
-    while ((int)cols < p.kt * 2 * kStemCo) cols <<= 1;
+    while ((int)cols < 2 * (p.x3 ? 2 : 1) * kStemCo) cols <<= 1;       // two row-parity accumulators per CTA (the kt taps are split over CTAs)
     CUtensorMap mx[2], md[2];
     if ((rc = encode_stem_x(&mx[0], x_hi, s, wp))) return rc;
     mx[1] = mx[0];
@@ -527,7 +541,8 @@ int stem_wgrad_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_l
         if (e != cudaSuccess) { set_error("stem_wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
         configured = true;
     }
-    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    const int groups = kNumSMs / p.kt;                    // CTAs per temporal tap
+    const int grid = (p.num_tiles < groups ? p.num_tiles : groups) * p.kt;
     if (p.x3) stem_wgrad_kernel<true><<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], md[0], md[1], p, cols, dfilt);
     else stem_wgrad_kernel<false><<<grid, kStemThreads, smem, st>>>(mx[0], mx[1], md[0], md[1], p, cols, dfilt);
     return check_launch("stem_wgrad_kernel");
