@@ -398,16 +398,21 @@ struct TcWgradParams {
     int x3;
 };
 
-template <int BN>
+// G = (tap, 64-channel) groups per CTA: 2 (one accumulator of 128 rows), or 3 for layers with exactly three groups (the 64-channel
+// temporal convolutions): a second accumulator takes the third group (its rows 64..127 multiply whatever follows the group in
+// shared memory and are never stored), so the CTA loads dZ ONCE per k-block instead of two CTAs loading it twice -- that
+// launch is HBM-bound (6.7 TB/s) and was reading 1.54 GB for 0.82 GB of operands.
+template <int BN, int G = 2>
 struct TcWgSmem {
-    static constexpr int kABytes = 2 * kSubTile;            // two (tap, 64-channel) groups
+    static constexpr int kABytes = G * kSubTile;            // G (tap, 64-channel) groups
     static constexpr int kBBytes = (BN / 64) * kSubTile;
     static constexpr int kStageBytes = 2 * (kABytes + kBBytes);             // [A hi | A lo | B hi | B lo]
-    static constexpr int kStages = BN <= 64 ? 4 : (BN <= 128 ? 3 : 2);
+    static constexpr int kStages = BN <= 64 ? (G == 3 ? 3 : 4) : (BN <= 128 ? 3 : 2);
     // bf16x3 with BN <= 128: X_hi x [dZ_hi | dZ_lo] is ONE MMA of N = 2 * BN (the lo plane's 64-channel groups follow the hi
     // plane's at the same 8 KB pitch), its two column halves are summed in the epilogue; X_lo x dZ_hi adds into the first half.
     static constexpr bool kWide = BN <= 128;
-    static constexpr int kTmemCols = kWide ? 2 * BN : BN;
+    static constexpr int kAccCols = kWide ? 2 * BN : BN;                    // columns of one accumulator
+    static constexpr int kTmemCols = (G == 3 ? 2 : 1) * kAccCols;
     static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -415,12 +420,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN>
+template <int BN, int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                 const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo, const TcWgradParams p,
                 float* __restrict__ dfilt) {
-    using S = TcWgSmem<BN>;
+    using S = TcWgSmem<BN, G>;
+    constexpr int kAcc = G == 3 ? 2 : 1;                 // accumulators of 128 rows
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
@@ -429,7 +435,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g0 = blockIdx.x * 2;                       // first (tap, channel-block) group of this CTA
+    const int g0 = blockIdx.x * G;                       // first (tap, channel-block) group of this CTA
     const int n0 = blockIdx.y * BN;
     const int cblocks = p.cs / 64;
     const int total_kb = (p.M + kWgKB - 1) / kWgKB;
@@ -454,9 +460,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
-        int gtap[2], gc0[2], ga[2], gb[2], gc[2];
+        int gtap[G], gc0[G], ga[G], gb[G], gc[G];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < G; ++i) {
             const int g = min(g0 + i, p.groups - 1);     // an odd tail group is loaded twice and not stored
             gtap[i] = g / cblocks;
             gc0[i] = (g - gtap[i] * cblocks) * 64;
@@ -467,8 +473,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         }
         const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
         int stage = 0, phase = 0;
+        // Temporal filters: walk the k-blocks frame-fastest (same 64 pixels of consecutive frames back to back), so that the three
+        // reads of an input tile (taps t-1, t, t+1) are 1-2 k-blocks apart and hit L2.  In pixel order they were a whole frame of
+        // the CTA's range apart -- with 148 CTAs streaming concurrently that is ~1 GB of other traffic, and X came from DRAM
+        // three times (1.54 GB read for 0.82 GB of operands, HBM-bound).  Needs k-blocks that do not straddle frames.
+        const int hw_blocks = (p.hd * p.wd) / kWgKB;
+        const bool frame_fastest = p.kt > 1 && (p.hd * p.wd) % kWgKB == 0 && p.td > 1;
         for (int kb = 0; kb < nkb; ++kb) {
-            int m = (kb0 + kb) * kWgKB;
+            int blk = kb0 + kb;
+            if (frame_fastest) {
+                const int per_clip = p.td * hw_blocks;
+                const int n_c = blk / per_clip, rem = blk - n_c * per_clip;
+                const int hb = rem / p.td, t_f = rem - hb * p.td;
+                blk = (n_c * p.td + t_f) * hw_blocks + hb;
+            }
+            int m = blk * kWgKB;
+            const int blk_row = m;
             const int w_o = m % p.wd;  m /= p.wd;
             const int h_o = m % p.hd;  m /= p.hd;
             const int t_o = m % p.td;
@@ -484,11 +504,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 uint8_t* a = st + pl * S::kABytes;
                 uint8_t* b = st + 2 * S::kABytes + pl * S::kBBytes;
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < G; ++i)
                     tma_load_im2col_5d(a + i * kSubTile, mx, &full_bar[stage], gc0[i], bw, bh, bt, n_i, (uint16_t)gc[i], (uint16_t)gb[i], (uint16_t)ga[i]);
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
-                    tma_load_2d(b + j * kSubTile, md, &full_bar[stage], n0 + j * 64, (kb0 + kb) * kWgKB);
+                    tma_load_2d(b + j * kSubTile, md, &full_bar[stage], n0 + j * 64, blk_row);
             }
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
@@ -505,21 +525,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
             const uint64_t b_hi = a_hi + (uint32_t)((2 * S::kABytes) >> 4);
             constexpr uint32_t kLoA = (uint32_t)(S::kABytes >> 4), kLoB = (uint32_t)(S::kBBytes >> 4);      // hi -> lo plane of an operand
-            if (x3) {
 #pragma unroll
-                for (int k = 0; k < kWgKB / 16; ++k) {          // a K = 16 step advances 2 KB = 128 encoded units
-                    if (S::kWide) {
-                        umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc2, (kb | k) != 0);       // hi*hi | hi*lo
-                        umma_bf16(tmem_base, a_hi + kLoA + 128 * k, b_hi + 128 * k, idesc, 1);             // + lo*hi
-                    } else {
-                        umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
-                        umma_bf16(tmem_base, a_hi + 128 * k, b_hi + kLoB + 128 * k, idesc, 1);
-                        umma_bf16(tmem_base, a_hi + kLoA + 128 * k, b_hi + 128 * k, idesc, 1);
+            for (int acc_i = 0; acc_i < kAcc; ++acc_i) {
+                const uint32_t acc = tmem_base + acc_i * S::kAccCols;
+                const uint64_t a_g = a_hi + (uint32_t)((acc_i * 2 * kSubTile) >> 4);       // groups 0,1 | group 2 (+ 8 KB of don't-care rows)
+                if (x3) {
+#pragma unroll
+                    for (int k = 0; k < kWgKB / 16; ++k) {          // a K = 16 step advances 2 KB = 128 encoded units
+                        if (S::kWide) {
+                            umma_bf16(acc, a_g + 128 * k, b_hi + 128 * k, idesc2, (kb | k) != 0);       // hi*hi | hi*lo
+                            umma_bf16(acc, a_g + kLoA + 128 * k, b_hi + 128 * k, idesc, 1);             // + lo*hi
+                        } else {
+                            umma_bf16(acc, a_g + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
+                            umma_bf16(acc, a_g + 128 * k, b_hi + kLoB + 128 * k, idesc, 1);
+                            umma_bf16(acc, a_g + kLoA + 128 * k, b_hi + 128 * k, idesc, 1);
+                        }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int k = 0; k < kWgKB / 16; ++k) umma_bf16(tmem_base, a_hi + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < kWgKB / 16; ++k) umma_bf16(acc, a_g + 128 * k, b_hi + 128 * k, idesc, (kb | k) != 0);
+                }
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }
@@ -531,16 +556,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         tc_fence_after();
         const int q = warp & 3;
         const int row = q * 32 + lane;              // 0..127
-        const int g = g0 + (row >> 6);
-        const bool valid = g < p.groups;
+#pragma unroll
+        for (int acc_i = 0; acc_i < kAcc; ++acc_i) {
+        const int g = g0 + 2 * acc_i + (row >> 6);
+        const bool valid = g < p.groups && g < g0 + G;
         const int tap = g / cblocks, ci = (g - tap * cblocks) * 64 + (row & 63);
         float* dst = dfilt + ((size_t)tap * p.cs + ci) * p.cd + n0;
+        const uint32_t tacc = tmem_base + acc_i * S::kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) {
             uint32_t r[32], r2[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, r);
+            tmem_ld_32x32b_x32(tacc + j * 32, r);
             const bool wide = S::kWide && p.x3;
-            if (wide) tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + BN + j * 32, r2);     // the hi*lo half
+            if (wide) tmem_ld_32x32b_x32(tacc + BN + j * 32, r2);     // the hi*lo half
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
@@ -551,6 +579,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                     red_add_v4(dst + j * 32 + 4 * v, o[0], o[1], o[2], o[3]);
                 }
             }
+        }
         }
     }
     tc_fence_before();
@@ -756,16 +785,16 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     return AVID_OK;
 }
 
-template <int BN>
+template <int BN, int G>
 static int launch_wgrad_tc(const CUtensorMap* maps, const TcWgradParams& p, int splits, float* dfilt, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWgSmem<BN>::kBytes);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWgSmem<BN, G>::kBytes);
         if (e != cudaSuccess) { set_error("wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
         configured = true;
     }
-    dim3 grid((p.groups + 1) / 2, p.cd / BN, splits);
-    wgrad_tc_kernel<BN><<<grid, kTcThreads, TcWgSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, dfilt);
+    dim3 grid((p.groups + G - 1) / G, p.cd / BN, splits);
+    wgrad_tc_kernel<BN, G><<<grid, kTcThreads, TcWgSmem<BN, G>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, dfilt);
     return check_launch("wgrad_tc_kernel");
 }
 
@@ -787,7 +816,8 @@ int wgrad_tc_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo,
     const int taps = s->kt * s->kh * s->kw;
     p.groups = taps * (s->ci / 64);
     const int bn = s->co % 256 == 0 ? 256 : (s->co % 128 == 0 ? 128 : 64);
-    const int tiles = ((p.groups + 1) / 2) * (s->co / bn);
+    const bool three = p.groups == 3 && bn == 64;          // one CTA takes all three groups (see TcWgSmem)
+    const int tiles = three ? 1 : ((p.groups + 1) / 2) * (s->co / bn);
     const int total_kb = (p.M + kWgKB - 1) / kWgKB;
     // one CTA per SM (the stages fill shared memory): pick the pixel split that minimises waves x (k-blocks per CTA + the fixed
     // prologue / atomic-epilogue cost, ~8 k-blocks) -- a grid of 300 CTAs on 148 SMs would run a third wave for 4 CTAs.
@@ -816,9 +846,10 @@ int wgrad_tc_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo,
         if ((rc = encode_im2col(&maps[1], x_lo, s->n, s->ti, s->hi, s->wi, s->ci, lower, upper, stride, kWgKB))) return rc;
         if ((rc = encode_tiled_2d(&maps[3], d_lo, (uint64_t)M, s->co, kWgKB, 64))) return rc;
     }
-    if (bn == 256) return launch_wgrad_tc<256>(maps, p, splits, dfilt, st);
-    if (bn == 128) return launch_wgrad_tc<128>(maps, p, splits, dfilt, st);
-    return launch_wgrad_tc<64>(maps, p, splits, dfilt, st);
+    if (bn == 256) return launch_wgrad_tc<256, 2>(maps, p, splits, dfilt, st);
+    if (bn == 128) return launch_wgrad_tc<128, 2>(maps, p, splits, dfilt, st);
+    if (three) return launch_wgrad_tc<64, 3>(maps, p, splits, dfilt, st);
+    return launch_wgrad_tc<64, 2>(maps, p, splits, dfilt, st);
 }
 
 }  // namespace avid
