@@ -21,6 +21,8 @@ TC_CASES = [
     (2, 64, 64, (1, 25, 33), (1, 3, 3), (1, 2, 2), (0, 1, 1)),     # audio block entry, odd extents (ragged parity classes)
     (2, 64, 128, (3, 7, 9), (3, 3, 3), (2, 2, 2), (1, 1, 1)),      # full 3-D strided filter: 8 parity classes
     (1, 64, 64, (5, 6, 7), (3, 1, 1), (2, 1, 1), (0, 0, 0)),       # unpadded strided temporal (negative tap offsets)
+    (2, 64, 64, (5, 8, 16), (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # temporal, h*w % 64 == 0: frame-fastest k-block order of the filter gradient
+    (2, 128, 128, (3, 8, 8), (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # same with two channel blocks
 ]
 
 
