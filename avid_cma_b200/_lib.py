@@ -61,6 +61,8 @@ _SIGNATURES = {
     "avid_cma_topk_begin": (C.c_int, [_L, _P, _Z, _P]),
     "avid_cma_topk_scan": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _I, _P, _Z, _P]),
     "avid_cma_topk_finish": (C.c_int, [_L, _I, _P, _P, _Z, _P]),
+    "avid_log_spectrogram_workspace_bytes": (c_size_t, [_I]),
+    "avid_log_spectrogram": (C.c_int, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "avid_cma_to_half": (C.c_int, [_P, _P, _L, _P]),
     "avid_cma_topk_scan_tc": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _P, _Z, _P]),
     "avid_cma_topk_rescore": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _P, _Z, _P]),

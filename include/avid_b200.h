@@ -356,6 +356,16 @@ int avid_adam_step_multi(float* const* params_host, const float* const* grads_ho
 /* cudaMemsetAsync(p, 0, bytes): one call zeroes the per-step arena of accumulators (filter gradients, BatchNorm sums) */
 int avid_zero_bytes(void* p, size_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Input side: LogSpectrogram.__call__ of datasets/preprocessing.py:158-186 for a batch of mono clips on
+ * the device: |stft(n_fft, hop)|^2 (hann window, centred frames, reflect padding), bin 0 + pair means -> n_fft/4 + 1 bins,
+ * first num_frames frames, power_to_db (amin 1e-10, ref 1, top_db per clip; top_db < 0: no floor), optional per-bin
+ * (x - mean) / (std + 1e-5).  wave (batch, num_samples) fp32 -> out (batch, 1, num_frames, n_fft/4 + 1) fp32. */
+size_t avid_log_spectrogram_workspace_bytes(int32_t batch);
+int avid_log_spectrogram(const float* wave, int32_t batch, int32_t num_samples, int32_t n_fft, int32_t hop, int32_t num_frames,
+                         float top_db, const float* mean, const float* stdv, float* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

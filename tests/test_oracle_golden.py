@@ -102,3 +102,21 @@ def test_full_step_matches_reference(golden):
     oc.bank_update(bv, ba, ve, ae, y, 0.5)
     _close(bv[y], g["rows_v"], 1e-4, 1e-6)
     _close(ba[y], g["rows_a"], 1e-4, 1e-6)
+
+
+def test_audio_oracle_stft_matches_scipy():
+    """oracle/audio.py restates librosa.stft (absent here); cross-check it against scipy's independent STFT with the same
+    conventions (periodic hann window, reflect-padded centred frames) and check the bin pairing / dB floor arithmetic."""
+    import numpy as np
+    import scipy.signal
+    from oracle import audio as oa
+    sig = np.random.default_rng(0).standard_normal(5000)
+    P = oa.stft_power(sig, 1024, 240)
+    _, _, Z = scipy.signal.stft(np.pad(sig, 512, mode="reflect"), window="hann", nperseg=1024, noverlap=1024 - 240, boundary=None,
+                                padded=False, return_onesided=True)
+    Z = Z * scipy.signal.get_window("hann", 1024, fftbins=True).sum()
+    assert P.shape == (513, 1 + 5000 // 240) and np.abs(np.abs(Z) ** 2 - P).max() < 1e-12 * P.max()
+    out = oa.log_spectrogram(sig, 24000, n_fft=512, hop_size=0.01, duration=0.1)
+    assert out.shape == (1, 10, 257) and out.max() - out.min() <= 100.0
+    pair = 0.5 * (P[1:, :10].reshape(256, 2, -1)).sum(1)
+    np.testing.assert_allclose(out[0, :, 1:], 10 * np.log10(np.maximum(pair, 1e-10)).T, rtol=1e-12)
