@@ -241,23 +241,62 @@ def _shard_iter(cand_shards):
     return cand_shards() if callable(cand_shards) else cand_shards
 
 
+class _CmaExactEngine:
+    """fp32 CUDA-core search (csrc/cma.cu): begin / one scan per candidate shard / finish."""
+
+    def __init__(self, q_video, q_audio, pos_k, mode):
+        self.qv, self.qa, self.pos_k, self.mode = q_video, q_audio, pos_k, CMA_MODES[mode]
+        self.nq = q_video.shape[0]
+        L = _lib.lib()
+        self.ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(self.nq)), dtype=torch.uint8, device=q_video.device)
+        check(L.avid_cma_topk_begin(self.nq, _p(self.ws, torch.uint8), self.ws.numel(), _stream()))
+
+    def scan(self, cv, ca, begin):
+        check(_lib.lib().avid_cma_topk_scan(_p(self.qv), _p(self.qa), self.nq, _p(cv), _p(ca), begin, cv.shape[0], self.mode, self.pos_k,
+                                            _p(self.ws, torch.uint8), self.ws.numel(), _stream()))
+
+    def finish(self):
+        out = torch.empty(self.nq, self.pos_k, dtype=torch.int32, device=self.qv.device)
+        check(_lib.lib().avid_cma_topk_finish(self.nq, self.pos_k, _p(out, torch.int32), _p(self.ws, torch.uint8), self.ws.numel(), _stream()))
+        return out
+
+
+class _CmaTensorCoreEngine(_CmaExactEngine):
+    """tcgen05 candidate generation + exact re-scoring per shard, certificate at the end (csrc/cma_tc.cu).
+    finish() -> (positives, rows of the queries without a certificate)."""
+
+    def __init__(self, q_video, q_audio, pos_k, mode, eps):
+        super().__init__(q_video, q_audio, pos_k, mode)
+        self.eps = float(eps)
+        self.qv_h, self.qa_h = _cma_to_half(q_video), _cma_to_half(q_audio)
+
+    def scan(self, cv, ca, begin):
+        L = _lib.lib()
+        same = cv.data_ptr() == self.qv.data_ptr() and cv.shape[0] == self.nq
+        cv_h, ca_h = (self.qv_h, self.qa_h) if same else (_cma_to_half(cv), _cma_to_half(ca))
+        wp, wn = _p(self.ws, torch.uint8), self.ws.numel()
+        check(L.avid_cma_topk_scan_tc(_p(self.qv_h, torch.float16), _p(self.qa_h, torch.float16), self.nq, _p(cv_h, torch.float16),
+                                      _p(ca_h, torch.float16), begin, cv.shape[0], self.mode, wp, wn, _stream()))
+        check(L.avid_cma_topk_rescore(_p(self.qv), _p(self.qa), self.nq, _p(cv), _p(ca), begin, cv.shape[0], self.mode, wp, wn, _stream()))
+
+    def finish(self):
+        dev = self.qv.device
+        fail_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        fail_list = torch.empty(self.nq, dtype=torch.int32, device=dev)
+        check(_lib.lib().avid_cma_topk_certify(self.nq, self.pos_k, self.eps, _p(self.ws, torch.uint8), self.ws.numel(),
+                                               _p(fail_count, torch.int32), _p(fail_list, torch.int32), _stream()))
+        out = super().finish()
+        return out, fail_list[:int(fail_count.item())].long()
+
+
 def _cma_topk_exact(q_video, q_audio, cand_shards, pos_k, mode, run=True):
-    """fp32 CUDA-core search (csrc/cma.cu).  run=False only walks the shards (a rank without queries to re-mine must still
-    take part in the collectives that stream them)."""
-    L = _lib.lib()
-    nq = q_video.shape[0] if run else 0
-    if run:
-        ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(nq)), dtype=torch.uint8, device=q_video.device)
-        wp, wn = _p(ws, torch.uint8), ws.numel()
-        check(L.avid_cma_topk_begin(nq, wp, wn, _stream()))
+    """One walk over the shards with the fp32 engine.  run=False only walks them (a rank without queries to re-mine must still
+    take part in the collectives that stream the shards)."""
+    eng = _CmaExactEngine(q_video, q_audio, pos_k, mode) if run else None
     for cv, ca, begin in _shard_iter(cand_shards):
         if run:
-            check(L.avid_cma_topk_scan(_p(q_video), _p(q_audio), nq, _p(cv), _p(ca), begin, cv.shape[0], CMA_MODES[mode], pos_k, wp, wn, _stream()))
-    if not run:
-        return None
-    out = torch.empty(nq, pos_k, dtype=torch.int32, device=q_video.device)
-    check(L.avid_cma_topk_finish(nq, pos_k, _p(out, torch.int32), wp, wn, _stream()))
-    return out
+            eng.scan(cv, ca, begin)
+    return eng.finish() if run else None
 
 
 def cma_topk(q_video, q_audio, cand_shards, pos_k, mode="consensus", exact=None, any_rank=None, eps=CMA_EPS, stats=None):
@@ -274,25 +313,11 @@ def cma_topk(q_video, q_audio, cand_shards, pos_k, mode="consensus", exact=None,
         exact = os.environ.get("AVID_CMA_EXACT", "0") == "1"
     if exact:
         return _cma_topk_exact(q_video, q_audio, cand_shards, pos_k, mode)
-    L = _lib.lib()
-    nq, dev = q_video.shape[0], q_video.device
-    ws = torch.empty(int(L.avid_cma_topk_workspace_bytes(nq)), dtype=torch.uint8, device=dev)
-    wp, wn = _p(ws, torch.uint8), ws.numel()
-    check(L.avid_cma_topk_begin(nq, wp, wn, _stream()))
-    qv_h, qa_h = _cma_to_half(q_video), _cma_to_half(q_audio)
-    m = CMA_MODES[mode]
+    eng = _CmaTensorCoreEngine(q_video, q_audio, pos_k, mode, eps)
     for cv, ca, begin in _shard_iter(cand_shards):
-        same = cv.data_ptr() == q_video.data_ptr() and cv.shape[0] == nq
-        cv_h, ca_h = (qv_h, qa_h) if same else (_cma_to_half(cv), _cma_to_half(ca))
-        check(L.avid_cma_topk_scan_tc(_p(qv_h, torch.float16), _p(qa_h, torch.float16), nq, _p(cv_h, torch.float16), _p(ca_h, torch.float16),
-                                      begin, cv.shape[0], m, wp, wn, _stream()))
-        check(L.avid_cma_topk_rescore(_p(q_video), _p(q_audio), nq, _p(cv), _p(ca), begin, cv.shape[0], m, wp, wn, _stream()))
-    fail_count = torch.zeros(1, dtype=torch.int32, device=dev)
-    fail_list = torch.empty(nq, dtype=torch.int32, device=dev)
-    check(L.avid_cma_topk_certify(nq, pos_k, float(eps), wp, wn, _p(fail_count, torch.int32), _p(fail_list, torch.int32), _stream()))
-    out = torch.empty(nq, pos_k, dtype=torch.int32, device=dev)
-    check(L.avid_cma_topk_finish(nq, pos_k, _p(out, torch.int32), wp, wn, _stream()))
-    n_fail = int(fail_count.item())
+        eng.scan(cv, ca, begin)
+    out, rows = eng.finish()
+    n_fail = int(rows.numel())
     if stats is not None:
         stats["uncertified"] = n_fail
     again = n_fail > 0
@@ -302,7 +327,6 @@ def cma_topk(q_video, q_audio, cand_shards, pos_k, mode="consensus", exact=None,
         if not (callable(cand_shards) or isinstance(cand_shards, (list, tuple))):
             raise RuntimeError("cma_topk: re-mining needs a re-iterable shard source (pass a list or a callable)")
         if n_fail > 0:
-            rows = fail_list[:n_fail].long()
             out[rows] = _cma_topk_exact(q_video[rows].contiguous(), q_audio[rows].contiguous(), cand_shards, pos_k, mode)
         else:
             _cma_topk_exact(None, None, cand_shards, pos_k, mode, run=False)
