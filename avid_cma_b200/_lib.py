@@ -99,6 +99,8 @@ _SIGNATURES = {
     "avid_linear_forward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "avid_linear_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "avid_filter_to_planes": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "avid_filter_to_planes_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "avid_filter_from_tapmajor_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "avid_adam_step_multi": (C.c_int, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _F, _P]),
     "avid_zero_bytes": (C.c_int, [_P, _Z, _P]),
     "avid_add_inplace": (C.c_int, [_P, _P, _L, _P]),

@@ -113,6 +113,63 @@ __global__ void __launch_bounds__(256) filter_to_planes_kernel(const float* __re
     }
 }
 
+// The same two conversions for MANY filters in one launch (a tower converts ~35 filters per step; as separate launches they cost
+// more in launch latency than in work).  Block b works on a 2048-element chunk of the filter whose block range contains b.
+constexpr int kFilterMax = 48, kFilterChunk = 2048;
+struct FilterBatch {
+    const float* src[kFilterMax];     // to_planes: PyTorch filter [co][ci][taps];  from_tap: tap-major gradient [taps][ci_pad][co]
+    void* dst[4][kFilterMax];         // to_planes: f_hi, f_lo, d_hi, d_lo planes;  from_tap: dst[0] = PyTorch-layout gradient
+    int co[kFilterMax], ci[kFilterMax], taps[kFilterMax], ci_pad[kFilterMax];
+    int block_begin[kFilterMax + 1];
+    int count;
+};
+
+__global__ void __launch_bounds__(256) filter_to_planes_multi_kernel(const FilterBatch b) {
+    int t = 0;
+    while (t + 1 < b.count && (int)blockIdx.x >= b.block_begin[t + 1]) ++t;
+    const int co = b.co[t], ci = b.ci[t], taps = b.taps[t];
+    const float* __restrict__ w = b.src[t];
+    __nv_bfloat16* f_hi = static_cast<__nv_bfloat16*>(b.dst[0][t]);
+    __nv_bfloat16* f_lo = static_cast<__nv_bfloat16*>(b.dst[1][t]);
+    __nv_bfloat16* d_hi = static_cast<__nv_bfloat16*>(b.dst[2][t]);
+    __nv_bfloat16* d_lo = static_cast<__nv_bfloat16*>(b.dst[3][t]);
+    const int total = taps * ci * co;
+    const int base = (blockIdx.x - b.block_begin[t]) * kFilterChunk;
+    const int end = min(total, base + kFilterChunk);
+    for (int i = base + threadIdx.x; i < end; i += 256) {         // forward planes ((t * co + o) * ci + c)
+        const int c = i % ci, r = i / ci;
+        const int o = r % co, tp = r / co;
+        const float v = __ldg(w + ((size_t)o * ci + c) * taps + tp);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        f_hi[i] = h;
+        if (f_lo) f_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    for (int j = base + threadIdx.x; j < end; j += 256) {         // dgrad planes ((t * ci + c) * co + o)
+        const int o = j % co, r = j / co;
+        const int c = r % ci, tp = r / ci;
+        const float v = __ldg(w + ((size_t)o * ci + c) * taps + tp);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        d_hi[j] = h;
+        if (d_lo) d_lo[j] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+__global__ void __launch_bounds__(256) filter_from_tap_multi_kernel(const FilterBatch b) {
+    int t = 0;
+    while (t + 1 < b.count && (int)blockIdx.x >= b.block_begin[t + 1]) ++t;
+    const int co = b.co[t], ci = b.ci[t], taps = b.taps[t], ci_pad = b.ci_pad[t];
+    const float* __restrict__ w_tap = b.src[t];
+    float* __restrict__ w = static_cast<float*>(b.dst[0][t]);
+    const int total = co * ci * taps;
+    const int base = (blockIdx.x - b.block_begin[t]) * kFilterChunk;
+    const int end = min(total, base + kFilterChunk);
+    for (int i = base + threadIdx.x; i < end; i += 256) {
+        const int tp = i % taps, r = i / taps;
+        const int c = r % ci, o = r / ci;
+        w[i] = __ldg(w_tap + ((size_t)tp * ci_pad + c) * co + o);
+    }
+}
+
 // torch.optim.Adam on up to kAdamMaxTensors tensors per launch: block b works on a 4096-element chunk of the tensor whose
 // block range contains b
 constexpr int kAdamMaxTensors = 32, kAdamChunk = 4096;
@@ -224,6 +281,59 @@ int avid_adam_step_multi(float* const* params, const float* const* grads, float*
                                                                                 (float)sqrt(bc2), grad_scale);
         int rc = check_launch("adam_multi_kernel");
         if (rc) return rc;
+    }
+    return AVID_OK;
+}
+
+static int fill_filter_batch(FilterBatch* b, int first, int count, const float* const* src, const int32_t* co, const int32_t* ci, const int32_t* taps,
+                             const int32_t* ci_pad, const char* what) {
+    b->count = count - first < kFilterMax ? count - first : kFilterMax;
+    int blocks = 0;
+    for (int i = 0; i < b->count; ++i) {
+        const int k = first + i;
+        AVID_REQUIRE(src[k] && co[k] > 0 && ci[k] > 0 && taps[k] > 0, "%s: filter %d has a NULL pointer or an empty shape", what, k);
+        const int64_t n = (int64_t)co[k] * ci[k] * taps[k];
+        AVID_REQUIRE(n < ((int64_t)1 << 31), "%s: filter %d too large", what, k);
+        b->src[i] = src[k];  b->co[i] = co[k];  b->ci[i] = ci[k];  b->taps[i] = taps[k];  b->ci_pad[i] = ci_pad ? ci_pad[k] : ci[k];
+        b->block_begin[i] = blocks;
+        blocks += (int)((n + kFilterChunk - 1) / kFilterChunk);
+    }
+    b->block_begin[b->count] = blocks;
+    return AVID_OK;
+}
+
+int avid_filter_to_planes_multi(const float* const* w_oihw, void* const* fwd_hi, void* const* fwd_lo, void* const* dgrad_hi, void* const* dgrad_lo,
+                                const int32_t* co, const int32_t* ci, const int32_t* taps, int32_t count, void* stream) {
+    AVID_REQUIRE(w_oihw && fwd_hi && dgrad_hi && co && ci && taps && count > 0, "filter_to_planes_multi: bad arguments");
+    AVID_REQUIRE((fwd_lo == nullptr) == (dgrad_lo == nullptr), "filter_to_planes_multi: give both lo plane lists or neither");
+    for (int first = 0; first < count; first += kFilterMax) {
+        FilterBatch b;
+        int rc = fill_filter_batch(&b, first, count, w_oihw, co, ci, taps, nullptr, "filter_to_planes_multi");
+        if (rc) return rc;
+        for (int i = 0; i < b.count; ++i) {
+            AVID_REQUIRE(fwd_hi[first + i] && dgrad_hi[first + i], "filter_to_planes_multi: filter %d has a NULL plane", first + i);
+            b.dst[0][i] = fwd_hi[first + i];  b.dst[1][i] = fwd_lo ? fwd_lo[first + i] : nullptr;
+            b.dst[2][i] = dgrad_hi[first + i];  b.dst[3][i] = dgrad_lo ? dgrad_lo[first + i] : nullptr;
+        }
+        filter_to_planes_multi_kernel<<<b.block_begin[b.count], 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+        if ((rc = check_launch("filter_to_planes_multi_kernel"))) return rc;
+    }
+    return AVID_OK;
+}
+
+int avid_filter_from_tapmajor_multi(const float* const* w_tap, float* const* w_oihw, const int32_t* co, const int32_t* ci, const int32_t* taps,
+                                    const int32_t* ci_pad, int32_t count, void* stream) {
+    AVID_REQUIRE(w_tap && w_oihw && co && ci && taps && ci_pad && count > 0, "filter_from_tapmajor_multi: bad arguments");
+    for (int first = 0; first < count; first += kFilterMax) {
+        FilterBatch b;
+        int rc = fill_filter_batch(&b, first, count, w_tap, co, ci, taps, ci_pad, "filter_from_tapmajor_multi");
+        if (rc) return rc;
+        for (int i = 0; i < b.count; ++i) {
+            AVID_REQUIRE(w_oihw[first + i] && ci_pad[first + i] >= ci[first + i], "filter_from_tapmajor_multi: filter %d: bad destination / ci_pad", first + i);
+            b.dst[0][i] = w_oihw[first + i];
+        }
+        filter_from_tap_multi_kernel<<<b.block_begin[b.count], 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+        if ((rc = check_launch("filter_from_tap_multi_kernel"))) return rc;
     }
     return AVID_OK;
 }

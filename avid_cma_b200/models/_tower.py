@@ -13,6 +13,15 @@ def default_math():
     return _MATH[os.environ.get('AVID_MATH', 'fp32')]
 
 
+def prepare_tower_filters(tower):
+    """All tensor-core filters of the tower -> bf16 operand planes in one launch (instead of one launch per layer)."""
+    if tower.math == ops.MATH_FP32:
+        return
+    ws = [m.weight.detach() for m in tower.modules()
+          if isinstance(m, (torch.nn.Conv2d, torch.nn.Conv3d)) and m.in_channels % 64 == 0 and m.out_channels % 64 == 0]
+    ops.prepare_filter_planes(ws, need_lo=tower.math == ops.MATH_BF16X3)
+
+
 class TowerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tower, x, *params):
@@ -20,9 +29,11 @@ class TowerFunction(torch.autograd.Function):
         arena.begin(x.device)
         ops.set_arena(arena)
         try:
+            prepare_tower_filters(tower)
             pooled, saved = tower._fwd(x.detach().contiguous().float(), tower.training, tower.math)
         finally:
             ops.set_arena(None)
+            ops.clear_filter_planes()
         ctx.tower, ctx.saved, ctx.params = tower, saved, params
         return pooled
 
@@ -32,9 +43,12 @@ class TowerFunction(torch.autograd.Function):
         arena = ctx.tower.__dict__.setdefault('_bwd_arena', ops.ZeroArena())
         arena.begin(dpooled.device)
         ops.set_arena(arena)
+        ops.defer_filter_gradients(True)          # every filter gradient is brought to the PyTorch layout by ONE launch at the end
         try:
             ctx.tower._bwd(dpooled.contiguous(), ctx.saved, grads, ctx.tower.math)
+            ops.flush_filter_gradients()
         finally:
+            ops.defer_filter_gradients(False)
             ops.set_arena(None)
         ctx.saved = None
         return (None, None) + tuple(grads.get(p) for p in ctx.params)

@@ -468,9 +468,75 @@ def stem_wgrad_tc(s, x_hi, x_lo, d_hi, d_lo):
     return dw
 
 
+_plane_cache = {}        # weight.data_ptr() -> planes converted ahead of time by prepare_filter_planes (consumed by filter_to_planes)
+_deferred_grads = None   # list of (dw_tap, out, co, ci, taps, ci_pad) while a tower's backward defers its filter-gradient layout conversion
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
+
+
+@_timed("filter_to_planes")
+def prepare_filter_planes(weights, need_lo=True):
+    """Convert MANY PyTorch conv weights (co, ci, *k) to the tensor-core operand planes in ONE launch (avid_filter_to_planes_multi);
+    the planes are handed out by the following filter_to_planes(w) calls.  One bf16 buffer backs all planes of the call."""
+    global _plane_cache
+    _plane_cache = {}
+    weights = [w for w in weights if w is not None]
+    if not weights:
+        return
+    dev = weights[0].device
+    shapes = [(w.shape[0], w.shape[1], w[0, 0].numel()) for w in weights]
+    per = 4 if need_lo else 2
+    sizes = [co * ci * taps for co, ci, taps in shapes]
+    buf = torch.empty(per * sum((n + 63) // 64 * 64 for n in sizes), dtype=torch.bfloat16, device=dev)
+    f_hi, f_lo, d_hi, d_lo, off = [], [], [], [], 0
+    for (co, ci, taps), n in zip(shapes, sizes):
+        step = (n + 63) // 64 * 64
+        views = [buf[off + k * step: off + k * step + n] for k in range(per)]
+        off += per * step
+        f_hi.append(views[0].view(taps, co, ci))
+        d_hi.append(views[1].view(taps, ci, co))
+        f_lo.append(views[2].view(taps, co, ci) if need_lo else None)
+        d_lo.append(views[3].view(taps, ci, co) if need_lo else None)
+    for w in weights:
+        _p(w)
+    ints = lambda vals: (C.c_int32 * len(vals))(*vals)
+    check(_lib.lib().avid_filter_to_planes_multi(_ptr_array(weights), _ptr_array(f_hi), _ptr_array(f_lo) if need_lo else None, _ptr_array(d_hi),
+                                                 _ptr_array(d_lo) if need_lo else None, ints([s_[0] for s_ in shapes]), ints([s_[1] for s_ in shapes]),
+                                                 ints([s_[2] for s_ in shapes]), len(weights), _stream()))
+    for w, a, b, c, d in zip(weights, f_hi, f_lo, d_hi, d_lo):
+        _plane_cache[(w.data_ptr(), need_lo)] = ((a, b), (c, d))
+
+
+def clear_filter_planes():
+    global _plane_cache
+    _plane_cache = {}
+
+
+def defer_filter_gradients(on):
+    """While on, filter_from_tapmajor only records its work; flush_filter_gradients converts every recorded gradient in ONE launch."""
+    global _deferred_grads
+    _deferred_grads = [] if on else None
+
+
+@_timed("filter_from_tap")
+def flush_filter_gradients():
+    global _deferred_grads
+    todo, _deferred_grads = _deferred_grads or [], None
+    if not todo:
+        return
+    ints = lambda k: (C.c_int32 * len(todo))(*[t[k] for t in todo])
+    check(_lib.lib().avid_filter_from_tapmajor_multi(_ptr_array([t[0] for t in todo]), _ptr_array([t[1] for t in todo]), ints(2), ints(3), ints(4),
+                                                     ints(5), len(todo), _stream()))
+
+
 @_timed("filter_to_planes")
 def filter_to_planes(w, need_lo=True):
     """PyTorch conv weight (co, ci, *k) -> bf16 planes ((fwd_hi, fwd_lo) [taps, co, ci], (dgrad_hi, dgrad_lo) [taps, ci, co])."""
+    hit = _plane_cache.pop((w.data_ptr(), need_lo), None)
+    if hit is not None:
+        return hit
     co, ci = w.shape[0], w.shape[1]
     taps = w[0, 0].numel()
     mk = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=w.device)
@@ -497,6 +563,10 @@ def filter_from_tapmajor(dw_tap, like):
     co, ci = like.shape[0], like.shape[1]
     taps, ci_pad = dw_tap.shape[0], dw_tap.shape[1]
     out = torch.empty_like(like)
+    if _deferred_grads is not None:
+        _p(dw_tap)
+        _deferred_grads.append((dw_tap, out, co, ci, taps, ci_pad))      # dw_tap stays alive until the flush
+        return out
     check(_lib.lib().avid_filter_from_tapmajor(_p(dw_tap), _p(out), co, ci, taps, ci_pad, _stream()))
     return out
 

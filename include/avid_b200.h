@@ -272,6 +272,13 @@ int avid_filter_from_tapmajor(const float* w_tap, float* w_oihw, int32_t co, int
  * forward planes [taps][co][ci], dgrad planes [taps][ci][co] (lo planes NULL for single-pass bf16) */
 int avid_filter_to_planes(const float* w_oihw, void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* dgrad_lo, int32_t co, int32_t ci, int32_t taps,
                           void* stream);
+/* The same conversions for many filters in one launch each (arrays of `count` pointers / shapes on the HOST): a tower converts
+ * all its tensor-core filters at the start of a step and all its filter gradients at the end of the backward pass. */
+int avid_filter_to_planes_multi(const float* const* w_oihw, void* const* fwd_hi, void* const* fwd_lo, void* const* dgrad_hi,
+                                void* const* dgrad_lo, const int32_t* co, const int32_t* ci, const int32_t* taps, int32_t count,
+                                void* stream);
+int avid_filter_from_tapmajor_multi(const float* const* w_tap, float* const* w_oihw, const int32_t* co, const int32_t* ci,
+                                    const int32_t* taps, const int32_t* ci_pad, int32_t count, void* stream);
 
 /* [n, c, thw] -> [n, thw, c_pad] (c_pad > c only for c <= 4: the 3-channel clip / 1-channel spectrogram)
  * and back [n, thw, c] -> [n, c, thw] */

@@ -309,3 +309,26 @@ def test_towers_eval_mode_and_return_embs():
         assert taps_a[k].shape == ref_a[k].shape and _rel(taps_a[k], ref_a[k]) < 1e-4, k
     rv, ra = towers.av_forward(video.double(), audio.double(), sd, training=False)
     assert _rel(ve, rv) < 1e-4 and _rel(ae, ra) < 1e-4
+
+
+def test_batched_filter_layout_conversions_equal_single_launches():
+    """avid_filter_to_planes_multi / avid_filter_from_tapmajor_multi (one launch per tower) == the per-filter entry points."""
+    g = torch.Generator().manual_seed(4)
+    shapes = [(64, 64, (1, 3, 3)), (128, 64, (1, 1, 1)), (128, 128, (3, 1, 1)), (512, 256, (3, 3)), (64, 3, (3, 7, 7))]
+    ws = [torch.randn(co, ci, *k, generator=g).to(DEV) for co, ci, k in shapes]
+    for need_lo in (True, False):
+        single = [ops.filter_to_planes(w, need_lo) for w in ws[:4]]
+        ops.prepare_filter_planes(ws[:4], need_lo)
+        for w, want in zip(ws[:4], single):
+            got = ops.filter_to_planes(w, need_lo)
+            for a, b in zip(got[0] + got[1], want[0] + want[1]):
+                assert (a is None and b is None) or torch.equal(a, b)
+        assert not ops._plane_cache
+    dws = [torch.randn(w[0, 0].numel(), 4 if w.shape[1] == 3 else w.shape[1], w.shape[0], generator=g).to(DEV) for w in ws]
+    want = [ops.filter_from_tapmajor(d, w) for d, w in zip(dws, ws)]
+    ops.defer_filter_gradients(True)
+    got = [ops.filter_from_tapmajor(d, w) for d, w in zip(dws, ws)]
+    ops.flush_filter_gradients()
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
