@@ -313,6 +313,7 @@ def test_towers_eval_mode_and_return_embs():
 
 def test_batched_filter_layout_conversions_equal_single_launches():
     """avid_filter_to_planes_multi / avid_filter_from_tapmajor_multi (one launch per tower) == the per-filter entry points."""
+    from avid_cma_b200 import ops
     g = torch.Generator().manual_seed(4)
     shapes = [(64, 64, (1, 3, 3)), (128, 64, (1, 1, 1)), (128, 128, (3, 1, 1)), (512, 256, (3, 3)), (64, 3, (3, 7, 7))]
     ws = [torch.randn(co, ci, *k, generator=g).to(DEV) for co, ci, k in shapes]
