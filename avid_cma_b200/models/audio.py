@@ -3,7 +3,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import Act
-from .network_blocks import Basic2DBlock, ConvBNReLU, StemOp, pad_channels
+from .network_blocks import flush_batch_counters, Basic2DBlock, ConvBNReLU, StemOp, pad_channels
 from ._tower import TowerMixin
 
 __all__ = ['Conv2D']
@@ -41,6 +41,7 @@ class Conv2D(TowerMixin, nn.Module):
             if taps is not None:
                 taps[tag] = h.f32
         pooled, argmax = ops.global_maxpool_forward(h.f32)
+        flush_batch_counters()
         return pooled, (s_stem, saved_blocks, argmax, tuple(h.shape))
 
     def _bwd(self, dpooled, saved, grads, math):

@@ -24,6 +24,17 @@ from ..ops import Act
 FUSE_MIN_K = int(os.environ.get('AVID_FUSE_BN_BWD_MIN_K', '192'))    # contraction length (co * taps) from which dgrad also reduces BN backward
 
 
+_BATCH_COUNTERS = []
+
+
+def flush_batch_counters():
+    """num_batches_tracked += 1 of every BatchNorm the tower just ran in training mode (nn.BatchNorm's bookkeeping), as ONE
+    multi-tensor launch instead of a tiny kernel per layer."""
+    if _BATCH_COUNTERS:
+        torch._foreach_add_(list(_BATCH_COUNTERS), 1)
+        del _BATCH_COUNTERS[:]
+
+
 def _triple(v, fill=1):
     """(t, h, w) view of a Conv2d / Conv3d hyper-parameter; `fill` is the value of the missing t entry
     (1 for kernel_size / stride, 0 for padding)."""
@@ -141,7 +152,7 @@ class ConvBNReLU:
             st = ops.BNState(conv.out_channels, x.device) if op.tc else None
             z = op.forward(x, addend, bn_stats=st.stats) if op.tc else op.forward(x, addend)
             st = ops.bn_train_stats(z, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bn.momentum, state=st)
-            bn.num_batches_tracked += 1
+            _BATCH_COUNTERS.append(bn.num_batches_tracked)       # += 1 for all layers of the tower in one foreach launch
         else:
             z = op.forward(x, addend)
             st = ops.BNState(conv.out_channels, z.device)

@@ -4,7 +4,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import Act
-from .network_blocks import BasicR2P1DBlock, ConvBNReLU, StemOp, pad_channels
+from .network_blocks import flush_batch_counters, BasicR2P1DBlock, ConvBNReLU, StemOp, pad_channels
 from ._tower import TowerFunction, TowerMixin
 
 
@@ -65,6 +65,7 @@ class R2Plus1D(TowerMixin, nn.Module):
             if taps is not None:
                 taps[name] = h.f32
         pooled, argmax = ops.global_maxpool_forward(h.f32)
+        flush_batch_counters()
         return pooled, (s_stem, saved_blocks, argmax, tuple(h.shape))
 
     def _bwd(self, dpooled, saved, grads, math):
