@@ -33,21 +33,26 @@ class _HeadFunction(torch.autograd.Function):
         return (None, d) + tuple(grads.get(p) for p in ctx.params)
 
 
+def _mlp(widths):
+    """[Linear, ReLU, Linear, ..., Linear] over consecutive width pairs: the Linear layers sit at the even positions of the
+    Sequential ('projection.0', 'projection.2', ...), which is the parameter naming of the reference's Head (av_wrapper.py:17-33)."""
+    mods = []
+    for k, (fan_in, fan_out) in enumerate(zip(widths[:-1], widths[1:])):
+        if k:
+            mods.append(nn.ReLU(inplace=True))
+        mods.append(nn.Linear(fan_in, fan_out))
+    return nn.Sequential(*mods)
+
+
 class Head(nn.Module):
-    """Linear(+ReLU) chain (av_wrapper.py:17-33); nn.Linear children hold the parameters, the math is libavid_b200's."""
+    """Projection head: Linear(+ReLU) chain; the nn.Linear children only hold the parameters, the math is libavid_b200's
+    (one autograd.Function for the whole chain)."""
 
     def __init__(self, input_dim, proj_dims):
         super().__init__()
-        if not isinstance(proj_dims, list):
-            proj_dims = [proj_dims]
-        projection = []
-        for i, d in enumerate(proj_dims):
-            projection += [nn.Linear(input_dim, d)]
-            input_dim = d
-            if i < len(proj_dims) - 1:
-                projection += [nn.ReLU(inplace=True)]
-        self.projection = nn.Sequential(*projection)
-        self.out_dim = proj_dims[-1]
+        widths = [input_dim] + (list(proj_dims) if isinstance(proj_dims, (list, tuple)) else [proj_dims])
+        self.projection = _mlp(widths)
+        self.out_dim = widths[-1]
 
     def _linears(self):
         return [m for m in self.projection if isinstance(m, nn.Linear)]
@@ -57,39 +62,38 @@ class Head(nn.Module):
 
 
 class AV_Wrapper(nn.Module):
+    """forward(video, audio) -> (video_emb, audio_emb), both (B, out_dim) (av_wrapper.py:36-61).  proj_dim=None: the pooled
+    512-d tower outputs are returned without heads."""
+
     def __init__(self, video_model, audio_model, proj_dim=128):
         super().__init__()
-        self.video_model = video_model
-        self.audio_model = audio_model
+        self.video_model, self.audio_model = video_model, audio_model
         self.use_linear_proj = proj_dim is not None
-        if proj_dim is not None:
-            self.video_proj = Head(video_model.out_dim, proj_dim)
-            self.audio_proj = Head(audio_model.out_dim, proj_dim)
+        self.out_dim = video_model.out_dim
+        if self.use_linear_proj:
+            self.video_proj, self.audio_proj = Head(video_model.out_dim, proj_dim), Head(audio_model.out_dim, proj_dim)
             self.out_dim = self.video_proj.out_dim
-        else:
-            self.out_dim = video_model.out_dim
+
+    def _embed(self, tower, head_name, x):
+        pooled = tower(x)
+        emb = pooled.view(pooled.shape[0], pooled.shape[1])          # (B, C, 1, 1[, 1]) -> (B, C)
+        return getattr(self, head_name)(emb) if self.use_linear_proj else emb
 
     def forward(self, video, audio):
-        video_emb = self.video_model(video)
-        video_emb = video_emb.view(video_emb.shape[0], video_emb.shape[1])
-        if self.use_linear_proj:
-            video_emb = self.video_proj(video_emb)
-        audio_emb = self.audio_model(audio)
-        audio_emb = audio_emb.view(audio_emb.shape[0], audio_emb.shape[1])
-        if self.use_linear_proj:
-            audio_emb = self.audio_proj(audio_emb)
-        return video_emb, audio_emb
+        return self._embed(self.video_model, 'video_proj', video), self._embed(self.audio_model, 'audio_proj', audio)
 
 
 def av_wrapper(video_backbone, video_backbone_args, audio_backbone, audio_backbone_args, proj_dim=128, checkpoint=None):
-    """Factory with the reference's signature (av_wrapper.py:64-76): backbones are resolved by name in this package."""
+    """Factory with the reference's signature (av_wrapper.py:64-76): backbones are resolved by name in this package; a
+    checkpoint written under DataParallel / DistributedDataParallel (`module.`-prefixed keys) is loaded the same way."""
     from .. import models
-    assert video_backbone in models.__dict__, 'Unknown model architecture'
-    assert audio_backbone in models.__dict__, 'Unknown model architecture'
-    video_model = models.__dict__[video_backbone](**video_backbone_args)
-    audio_model = models.__dict__[audio_backbone](**audio_backbone_args)
-    model = AV_Wrapper(video_model, audio_model, proj_dim=proj_dim)
+    towers = []
+    for name, kwargs in ((video_backbone, video_backbone_args), (audio_backbone, audio_backbone_args)):
+        if name not in models.__dict__:
+            raise AssertionError('Unknown model architecture')
+        towers.append(models.__dict__[name](**kwargs))
+    model = AV_Wrapper(towers[0], towers[1], proj_dim=proj_dim)
     if checkpoint is not None:
-        ckp = torch.load(checkpoint, map_location='cpu', weights_only=False)
-        nn.DataParallel(model).load_state_dict(ckp['model'])   # published checkpoints carry the `module.` prefix
+        state = torch.load(checkpoint, map_location='cpu', weights_only=False)['model']
+        nn.DataParallel(model).load_state_dict(state)
     return model

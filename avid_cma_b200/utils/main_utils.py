@@ -91,29 +91,26 @@ def build_model(cfg, logger=None):
 
 
 def distribute_model_to_cuda(models, args, batch_size, num_workers, ngpus_per_node):
-    """DistributedDataParallel (one process per GPU), plain .cuda(gpu), or single-process DataParallel -- the same three cases,
-    chosen the same way, as main_utils.py:98-138.  The towers' parameters are ordinary nn.Parameters whose .grad is filled by
-    one autograd.Function per tower, so DDP's gradient hooks and bucketed all-reduce work unchanged."""
+    """Placement of the model(s), chosen like main_utils.py:98-138: DistributedDataParallel when the job is distributed (pinned to
+    args.gpu in the one-process-per-GPU case, in which the configured batch size / worker count are per NODE and get divided),
+    plain .cuda(gpu) when a single GPU was requested, single-process DataParallel otherwise.  The towers' parameters are ordinary
+    nn.Parameters whose .grad is filled by one autograd.Function per tower, so DDP's hooks and bucketed all-reduce work unchanged."""
     if ngpus_per_node == 0:
         return models, args, batch_size, num_workers
-    single = not isinstance(models, list)
-    group = [models] if single else models
-    for i, m in enumerate(group):
+    pinned = args.gpu is not None
+    if pinned:
+        torch.cuda.set_device(args.gpu)
+
+    def place(m):
         if args.distributed:
-            if args.gpu is not None:
-                torch.cuda.set_device(args.gpu)
-                group[i] = torch.nn.parallel.DistributedDataParallel(m.cuda(args.gpu), device_ids=[args.gpu])
-            else:
-                group[i] = torch.nn.parallel.DistributedDataParallel(m.cuda())
-        elif args.gpu is not None:
-            torch.cuda.set_device(args.gpu)
-            group[i] = m.cuda(args.gpu)
-        else:
-            group[i] = torch.nn.DataParallel(m).cuda()
-    if args.distributed and args.gpu is not None:      # one GPU per process: the configured batch is the per-node batch
-        batch_size = int(batch_size / ngpus_per_node)
-        num_workers = int((num_workers + ngpus_per_node - 1) / ngpus_per_node)
-    return (group[0] if single else group), args, batch_size, num_workers
+            ddp = torch.nn.parallel.DistributedDataParallel
+            return ddp(m.cuda(args.gpu), device_ids=[args.gpu]) if pinned else ddp(m.cuda())
+        return m.cuda(args.gpu) if pinned else torch.nn.DataParallel(m).cuda()
+
+    placed = [place(m) for m in models] if isinstance(models, list) else place(models)
+    if args.distributed and pinned:
+        batch_size, num_workers = int(batch_size / ngpus_per_node), int((num_workers + ngpus_per_node - 1) / ngpus_per_node)
+    return placed, args, batch_size, num_workers
 
 
 def build_dataloaders(cfg, num_workers, distributed, logger):
@@ -152,21 +149,20 @@ def build_criterion(cfg, logger=None):
 
 
 def build_optimizer(params, cfg, logger=None):
-    params = list(params)
-    if cfg['name'] == 'sgd':
-        optimizer = torch.optim.SGD(params=params, lr=cfg['lr']['base_lr'], momentum=cfg['momentum'], weight_decay=cfg['weight_decay'],
-                                    nesterov=cfg['nesterov'])
-    elif cfg['name'] == 'adam':
-        betas = cfg['betas'] if 'betas' in cfg else [0.9, 0.999]
-        if params and all(p.is_cuda for p in params):
-            from ..optim import Adam           # fused multi-tensor kernel, same rule / state layout as torch.optim.Adam
-            optimizer = Adam(params, lr=cfg['lr']['base_lr'], weight_decay=cfg['weight_decay'], betas=betas)
-        else:
-            optimizer = torch.optim.Adam(params=params, lr=cfg['lr']['base_lr'], weight_decay=cfg['weight_decay'], betas=betas)
+    """SGD / Adam + MultiStepLR from the reference's optimizer config (main_utils.py:240-259).  'adam' on CUDA parameters is the
+    fused multi-tensor kernel (avid_cma_b200.optim.Adam: same update rule and state_dict layout as torch.optim.Adam)."""
+    params, lr = list(params), cfg['lr']
+    kind = cfg['name']
+    if kind == 'sgd':
+        optimizer = torch.optim.SGD(params, lr=lr['base_lr'], momentum=cfg['momentum'], weight_decay=cfg['weight_decay'], nesterov=cfg['nesterov'])
+    elif kind == 'adam':
+        from ..optim import Adam as FusedAdam
+        on_gpu = bool(params) and all(p.is_cuda for p in params)
+        optimizer = (FusedAdam if on_gpu else torch.optim.Adam)(params, lr=lr['base_lr'], weight_decay=cfg['weight_decay'],
+                                                               betas=cfg.get('betas', [0.9, 0.999]))
     else:
         raise ValueError('Unknown optimizer.')
-    scheduler = torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=cfg['lr']['milestones'], gamma=cfg['lr']['gamma'])
-    return optimizer, scheduler
+    return optimizer, torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=lr['milestones'], gamma=lr['gamma'])
 
 
 def reference_state_dict(module):
@@ -182,49 +178,50 @@ def reference_state_dict(module):
 
 class CheckpointManager(object):
     """{'epoch', 'model', 'optimizer', 'train_criterion'} files named like the reference's (main_utils.py:262-315): rank 0
-    writes `checkpoint.pth.tar` (and `model_best.pth.tar`), every rank restores."""
+    writes `checkpoint.pth.tar` (and copies the best one to `model_best.pth.tar`), every rank restores."""
+    FILES = {'last': 'checkpoint.pth.tar', 'best': 'model_best.pth.tar'}
 
     def __init__(self, checkpoint_dir, rank=0):
         self.checkpoint_dir, self.rank, self.best_metric = checkpoint_dir, rank, 0.
 
-    def save(self, epoch, filename=None, eval_metric=0., **kwargs):
-        sharded = any(getattr(getattr(m, 'nce_average', None), 'sharded', False) for m in kwargs.values())
-        if self.rank != 0 and not sharded:
-            return
-        state = {'epoch': epoch}
-        for k, m in kwargs.items():
-            state[k] = reference_state_dict(m) if hasattr(m, 'nce_average') else m.state_dict()
-        if self.rank != 0:
-            return
-        is_best = eval_metric > self.best_metric
-        if is_best:
-            self.best_metric = eval_metric
-        if filename is None:
-            save_checkpoint(state=state, is_best=is_best, model_dir=self.checkpoint_dir)
-        else:
-            save_checkpoint(state=state, is_best=False, filename='{}/{}'.format(self.checkpoint_dir, filename))
+    def _path(self, which):
+        return '{}/{}'.format(self.checkpoint_dir, self.FILES[which])
 
     def last_checkpoint_fn(self):
-        return '{}/checkpoint.pth.tar'.format(self.checkpoint_dir)
+        return self._path('last')
 
     def best_checkpoint_fn(self):
-        return '{}/model_best.pth.tar'.format(self.checkpoint_dir)
+        return self._path('best')
 
     def checkpoint_fn(self, last=False, best=False):
         assert best != last, 'choose exactly one of last / best'
-        return self.last_checkpoint_fn() if last else self.best_checkpoint_fn()
+        return self._path('last' if last else 'best')
 
     def checkpoint_exists(self, last=False, best=False):
         return os.path.isfile(self.checkpoint_fn(last, best))
 
+    def save(self, epoch, filename=None, eval_metric=0., **kwargs):
+        """kwargs: name -> module / optimizer.  A criterion with row-sharded banks makes this call COLLECTIVE (the banks are gathered
+        on every rank); otherwise ranks other than 0 return at once."""
+        gather = any(getattr(getattr(m, 'nce_average', None), 'sharded', False) for m in kwargs.values())
+        if self.rank != 0 and not gather:
+            return
+        state = {name: (reference_state_dict(m) if hasattr(m, 'nce_average') else m.state_dict()) for name, m in kwargs.items()}
+        state['epoch'] = epoch
+        if self.rank != 0:
+            return
+        improved = eval_metric > self.best_metric
+        self.best_metric = max(self.best_metric, eval_metric)
+        if filename is not None:
+            save_checkpoint(state=state, is_best=False, filename='{}/{}'.format(self.checkpoint_dir, filename))
+        else:
+            save_checkpoint(state=state, is_best=improved, model_dir=self.checkpoint_dir)
+
     def restore(self, fn=None, restore_last=False, restore_best=False, **kwargs):
         path = fn if fn is not None else self.checkpoint_fn(restore_last, restore_best)
         ckp = torch.load(path, map_location='cpu', weights_only=False)      # reference checkpoints pickle plain dicts / numpy scalars
-        for k, m in kwargs.items():
-            if k == 'train_criterion':
-                m.load_state_dict(ckp[k], strict=False)
-            else:
-                m.load_state_dict(ckp[k])
+        for name, m in kwargs.items():
+            m.load_state_dict(ckp[name], **({'strict': False} if name == 'train_criterion' else {}))
         return ckp['epoch']
 
 
