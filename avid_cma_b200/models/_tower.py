@@ -63,6 +63,11 @@ class TowerMixin:
             self.math = default_math()
         if not x.is_cuda:
             raise RuntimeError('avid_cma_b200 encoders run on CUDA tensors only (no CPU fallback)')
+        if getattr(self, '_is_replica', False):
+            # nn.DataParallel over several GPUs runs its replicas in threads of ONE process; the launch bookkeeping of this package
+            # (zero arena, deferred layout conversions) is per process by design: one process per GPU
+            raise RuntimeError('avid_cma_b200 runs one process per GPU: use --multiprocessing-distributed / torchrun (DistributedDataParallel) '
+                               'instead of multi-GPU nn.DataParallel')
         if return_embs:
             # feature taps for evaluation (utils/eval_utils.py:208,324,343): forward only, reference NC(D)HW layout
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:

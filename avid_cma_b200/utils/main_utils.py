@@ -105,7 +105,11 @@ def distribute_model_to_cuda(models, args, batch_size, num_workers, ngpus_per_no
         if args.distributed:
             ddp = torch.nn.parallel.DistributedDataParallel
             return ddp(m.cuda(args.gpu), device_ids=[args.gpu]) if pinned else ddp(m.cuda())
-        return m.cuda(args.gpu) if pinned else torch.nn.DataParallel(m).cuda()
+        if pinned:
+            return m.cuda(args.gpu)
+        # the reference wraps in DataParallel over ALL visible GPUs here; this package runs one process per GPU, so the wrap
+        # (kept for `model.module`, main-avid.py:100) is pinned to the current device -- use --multiprocessing-distributed for more
+        return torch.nn.DataParallel(m, device_ids=[torch.cuda.current_device()]).cuda()
 
     placed = [place(m) for m in models] if isinstance(models, list) else place(models)
     if args.distributed and pinned:
