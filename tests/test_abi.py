@@ -72,3 +72,43 @@ def test_model_state_dict_matches_reference_layout():
     assert list(sd.keys()) == list(ref.keys())
     assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
     assert m.out_dim == 128 and m.video_model.out_dim == 512 and m.audio_model.out_dim == 512
+
+
+def test_new_entry_points_validate_arguments_on_the_host(lib):
+    """Argument checks of the entry points added for CMA mining, the input side and the batched layout conversions happen before
+    any launch, so they can be exercised without a GPU."""
+    p16 = C.c_void_p(16)
+    rc = lib.avid_log_spectrogram(p16, 2, 48000, 1000, 240, 200, 100.0, None, None, p16, p16, 64, None)      # n_fft not a power of two
+    assert rc == 1 and b"power of two" in lib.avid_last_error()
+    rc = lib.avid_log_spectrogram(p16, 2, 48000, 1024, 240, 500, 100.0, None, None, p16, p16, 64, None)      # more frames than the clip has
+    assert rc == 1 and b"frames requested" in lib.avid_last_error()
+    rc = lib.avid_log_spectrogram(p16, 2, 48000, 1024, 240, 200, 100.0, p16, None, p16, p16, 64, None)       # mean without std
+    assert rc == 1
+    assert lib.avid_log_spectrogram_workspace_bytes(7) == 28 and lib.avid_log_spectrogram_workspace_bytes(0) == 0
+    ws = lib.avid_cma_topk_workspace_bytes(10)
+    rc = lib.avid_cma_topk_certify(10, 64, 1e-3, p16, ws, None, None, None)                                    # pos_k must be < 64
+    assert rc == 1 and b"certify" in lib.avid_last_error()
+    rc = lib.avid_cma_topk_scan_tc(p16, p16, 10, p16, p16, 0, 100, 9, p16, ws, None)                           # unknown mode
+    assert rc == 1 and b"mode" in lib.avid_last_error()
+    rc = lib.avid_cma_topk_rescore(p16, p16, 10, p16, p16, 0, 100, 0, p16, ws - 1, None)                       # workspace one byte short
+    assert rc == 2
+    rc = lib.avid_filter_to_planes_multi(None, None, None, None, None, None, None, None, 3, None)
+    assert rc == 1 and b"filter_to_planes_multi" in lib.avid_last_error()
+    rc = lib.avid_cma_to_half(p16, p16, 6, None)                                                               # n must be a multiple of 4
+    assert rc == 1
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under avid_cma_b200/ (nor the launcher) may import it, and bench.py only in its CPU legs."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    for base, _, files in os.walk(os.path.join(root, "avid_cma_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pat.search(open(os.path.join(base, f)).read()), os.path.join(base, f)
+    assert not pat.search(open(os.path.join(root, "main_avid.py")).read())
+    bench = open(os.path.join(root, "bench.py")).read()
+    body = bench[bench.index("def run_ours"):bench.index("if __name__")]
+    calls = [m.start() for m in pat.finditer(body)]
+    assert not calls, "run_ours() must not import the oracle (cpu_baseline goes through cpu_reference())"
