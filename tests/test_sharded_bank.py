@@ -171,6 +171,15 @@ def _worker(rank, world, port, backend, q):
             worst = max(worst, max(errs))
         fv, fa = bank.full_banks()
         worst = max(worst, rel(fv, full_v), rel(fa, full_a))
+        # checkpoint layout: every rank takes part in the gather, the dict holds the reference's full (N,128) banks;
+        # loading such a checkpoint into a sharded criterion keeps only the rows the rank owns
+        from avid_cma_b200.utils import main_utils as MU
+        sd = MU.reference_state_dict(crit)
+        assert tuple(sd['nce_average.view1_mem'].shape) == (N, 128) and not sd['nce_average.view1_mem'].is_cuda
+        worst = max(worst, rel(sd['nce_average.view1_mem'], full_v), rel(sd['nce_average.view2_mem'], full_a))
+        shuffled = {k: (v.flip(0) if k.endswith('_mem') else v) for k, v in sd.items()}
+        crit.load_state_dict(shuffled, strict=False)
+        worst = max(worst, rel(bank.view1_mem, full_v.flip(0)[bank.row_begin:bank.row_end]))
         q.put((rank, worst, None))
     except Exception as e:   # noqa: BLE001
         import traceback
