@@ -125,6 +125,19 @@ def cma_case(tag, N, B, K, Kw, pos_k, mode, seed):
     print("cma", tag, float(loss), {k: float(v) for k, v in log.items()})
 
 
+def cma_mining_case(tag, N, pos_k, mode, seed):
+    """Positive mining only (reference CMASampler.sample_instance, avid_cma.py:42-73) for the single-modality sampling types."""
+    torch.manual_seed(seed)
+    crit = criterions.AVID_CMA(num_data=N, embedding_dim=128, num_negatives=16, num_negatives_within=8, momentum=0.5,
+                               sampling_args={"type": mode, "pos_k": pos_k}, device=0)
+    crit.nce_average.view1_mem.copy_(synth.bank(N, seed=seed, tag="bank_v"))
+    crit.nce_average.view2_mem.copy_(synth.bank(N, seed=seed, tag="bank_a"))
+    crit.nce_average.find_correspondences()
+    np.savez_compressed(os.path.join(HERE, f"cma_mining_{tag}.npz"), N=N, pos_k=pos_k, seed=seed,
+                        positive_set=np_(crit.nce_average.positive_set))
+    print("cma mining", tag, tuple(crit.nce_average.positive_set.shape))
+
+
 def step_case(tag="config1", B=4, N=64, K=1024, size=112, spec=(100, 129), seed=0):
     """BASELINE config 1: full forward + AVID criterion + backward through both towers."""
     model = models.av_wrapper("R2Plus1D", {"depth": 18}, "Conv2D", {"depth": 10}, proj_dim=[512, 512, 128])
@@ -192,4 +205,6 @@ if __name__ == "__main__":
     criterion_case("cfg1", N=64, B=4, K=1024, seed=3, steps=1)
     cma_case("consensus", N=400, B=6, K=96, Kw=16, pos_k=8, mode="consensus", seed=4)
     cma_case("union", N=257, B=4, K=40, Kw=None, pos_k=5, mode="union", seed=5)
+    cma_mining_case("video", N=333, pos_k=6, mode="video", seed=6)
+    cma_mining_case("audio", N=190, pos_k=9, mode="audio", seed=7)
     step_case()

@@ -309,3 +309,15 @@ def test_cma_tensor_core_path_equals_fp32_path(mode):
     assert float((tc2 != ex2).any(1).float().mean()) < 0.005
     assert 1500 in tc2[5].tolist() or 5 in tc2[5].tolist()
 
+
+
+@pytest.mark.parametrize("mode", ["video", "audio"])
+def test_cma_single_modality_mining_matches_reference_golden(golden, mode):
+    """Tensor-core mining with one modality (only that modality's tiles are loaded and multiplied) == the imported reference."""
+    from avid_cma_b200 import ops
+    g = golden("cma_mining_" + mode)
+    N, pos_k, seed = int(g["N"]), int(g["pos_k"]), int(g["seed"])
+    bv, ba = synth.bank(N, seed=seed, tag="bank_v").to(DEV), synth.bank(N, seed=seed, tag="bank_a").to(DEV)
+    got = ops.cma_topk(bv, ba, [(bv, ba, 0)], pos_k, mode).cpu().numpy()
+    mism = (got != g["positive_set"]).any(1).mean()
+    assert mism < 0.01, mism        # set-identical up to fp32 summation-order ties at the k-th boundary

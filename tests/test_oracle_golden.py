@@ -120,3 +120,12 @@ def test_audio_oracle_stft_matches_scipy():
     assert out.shape == (1, 10, 257) and out.max() - out.min() <= 100.0
     pair = 0.5 * (P[1:, :10].reshape(256, 2, -1)).sum(1)
     np.testing.assert_allclose(out[0, :, 1:], 10 * np.log10(np.maximum(pair, 1e-10)).T, rtol=1e-12)
+
+
+@pytest.mark.parametrize("mode", ["video", "audio"])
+def test_cma_single_modality_mining_matches_reference(golden, mode):
+    """sampling type 'video' / 'audio' (avid_cma.py:60-63): positives ranked by one modality's similarity only."""
+    g = golden("cma_mining_" + mode)
+    N, pos_k, seed = int(g["N"]), int(g["pos_k"]), int(g["seed"])
+    bv, ba = synth.bank(N, seed=seed, tag="bank_v"), synth.bank(N, seed=seed, tag="bank_a")
+    assert np.array_equal(oc.cma_topk(bv, ba, pos_k, mode).numpy(), g["positive_set"])
