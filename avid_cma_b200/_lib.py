@@ -33,6 +33,7 @@ class NceArgs(C.Structure):
         ("loss_keys", c_void_p), ("loss_total", c_void_p), ("grad_video", c_void_p), ("grad_audio", c_void_p),
         ("scores", c_void_p), ("neg_idx_out", c_void_p),
         ("grad_hat_video", c_void_p), ("grad_hat_audio", c_void_p), ("loss_part", c_void_p),
+        ("bad_index", c_void_p), ("group_batch", c_int32), ("in_group_stride", c_int64), ("out_group_stride", c_int64),
     ]
 
 
@@ -54,8 +55,9 @@ _SIGNATURES = {
     "avid_nce_forward_backward": (C.c_int, [C.POINTER(NceArgs), _P, _Z, _P]),
     "avid_nce_finalize": (C.c_int, [C.POINTER(NceArgs), _P, _Z, _P]),
     "avid_nce_partition_mean": (C.c_int, [C.POINTER(NceArgs), _I, _P, _P, _Z, _P]),
-    "avid_bank_update": (C.c_int, [_P, _P, _L, _L, _P, _P, _P, _I, _F, _F, _P]),
+    "avid_bank_update": (C.c_int, [_P, _P, _L, _L, _P, _P, _P, _I, _I, _L, _F, _F, _P]),
     "avid_rows_l2_normalize": (C.c_int, [_P, _L, _P]),
+    "avid_bank_init": (C.c_int, [_P, _L, _L, _U, _I, _P]),
     "avid_sample_negatives": (C.c_int, [_P, _I, _I, _L, _P, _I, _U, _U, _P, _P]),
     "avid_cma_topk_workspace_bytes": (c_size_t, [_L]),
     "avid_cma_topk_begin": (C.c_int, [_L, _P, _Z, _P]),

@@ -76,32 +76,58 @@ class AVIDSimilarityMemoryBank(nn.Module):
         self.rows_per_rank = (memory_size + self.world - 1) // self.world if self.sharded else memory_size
         self.row_begin = min(memory_size, self.rank * self.rows_per_rank) if self.sharded else 0
         self.row_end = min(memory_size, self.row_begin + self.rows_per_rank)
-        # counter-based sampler state: (seed, offset) of the Philox stream shared by all ranks' kernels
-        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        # counter-based sampler state: (seed, offset) of the Philox stream shared by ALL ranks' kernels.  The default generator's seed
+        # differs from process to process unless the launcher seeds every worker, and a sharded step is only correct when every
+        # rank draws the same negatives for a gathered query: rank 0's seed is broadcast.
+        self._seed = self._shared_seed()
         self._offset = 0
         self._owner = None           # the AVID module (gives access to the NCECriterion and coefficients)
         self._ws = None
-        self._gathered = None        # (emb_v, emb_a, y) of all ranks, kept from the sharded scoring pass for update_memory
+        self._gathered = None        # packed (emb_v, emb_a, y) of all ranks, kept from the sharded scoring pass for update_memory
+        # raised by the NCE kernel when an instance index is outside [0, N) (the reference raises IndexError, avid.py:57-58); pinned
+        # host memory, polled at the start of the next forward without a device sync
+        self._bad = torch.zeros(1, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self.init_memory(memory_size, embedding_dim)
-        self._register_load_state_dict_pre_hook(self._slice_full_banks)
+        self._register_load_state_dict_pre_hook(self._on_load)
+        self._register_state_dict_hook(self._on_save)
+
+    def _shared_seed(self):
+        seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        if self.distributed:
+            dev = _torch_device(self.device) if dist.get_backend() == 'nccl' else torch.device('cpu')
+            t = torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed], dtype=torch.int64, device=dev)
+            dist.broadcast(t, 0)
+            seed = int(t.item()) & 0xFFFFFFFFFFFFFFFF
+        return seed
+
+    @staticmethod
+    def _on_save(module, state_dict, prefix, local_metadata):
+        """The Philox (seed, offset) travels with the checkpoint so that a resumed run does not replay the negative stream."""
+        seed = module._seed - (1 << 64) if module._seed >= (1 << 63) else module._seed
+        state_dict[prefix + 'sampler_state'] = torch.tensor([seed, module._offset], dtype=torch.int64)
+        return state_dict
 
     # ---- reference API -------------------------------------------------------------------------
     def init_memory(self, num_items, embedding_dim):
-        """avid.py:88-101: N(0,1) rows, L2-normalised, rank 0's copy broadcast to every rank (a sharded rank keeps its rows)."""
+        """avid.py:88-101: N(0,1) rows, L2-normalised, identical on every rank.  The reference draws them on rank 0 and broadcasts
+        2 x (N,128); here row r is a function of (shared seed, bank, r) (avid_bank_init), so every rank -- replicated or owner of
+        a shard -- fills its rows locally: no N x 128 tensor is ever materialised per shard and nothing crosses NVLink."""
         dev = _torch_device(self.device)
-        for name in ('view1_mem', 'view2_mem'):
-            mem = torch.randn(num_items, embedding_dim, device=dev)
-            ops.rows_l2_normalize_(mem)
-            if self.distributed:
-                dist.broadcast(mem, 0)
-            if self.sharded:
-                mem = mem[self.row_begin:self.row_end].clone()
+        rows = self.row_end - self.row_begin
+        for which, name in enumerate(('view1_mem', 'view2_mem')):
+            mem = torch.empty(max(rows, 0), embedding_dim, dtype=torch.float32, device=dev)
+            if rows > 0:
+                ops.bank_init_(mem, self.row_begin, self._seed, which)
             self.register_buffer(name, mem)
         if self.distributed:
             dist.barrier()
 
-    def _slice_full_banks(self, state_dict, prefix, *args):
-        """A checkpoint holds the full (N,128) banks (reference layout); a sharded rank loads its rows."""
+    def _on_load(self, state_dict, prefix, *args):
+        """A checkpoint holds the full (N,128) banks (reference layout): a sharded rank loads its rows.  `sampler_state` (ours, absent
+        from reference checkpoints) restores the Philox stream position."""
+        st = state_dict.pop(prefix + 'sampler_state', None)
+        if st is not None:
+            self._seed, self._offset = int(st[0]) & 0xFFFFFFFFFFFFFFFF, int(st[1])
         if not self.sharded:
             return
         for name in ('view1_mem', 'view2_mem', 'positive_set'):
@@ -129,17 +155,42 @@ class AVIDSimilarityMemoryBank(nn.Module):
         self._offset += self.world * B * K
         return idx
 
+    def _gather_queries(self, emb_v, emb_a, y, neg_idx=None):
+        """ONE all-gather per step (the reference issues three, avid.py:109-111): every rank contributes one packed record
+        [emb_v (B,128) f32 | emb_a (B,128) f32 | y (B) i64 | (injected negatives (B,K) i64)]; returns strided views
+        (W,B,128), (W,B,128), (W,B)[, (W,B,K)] into the gathered buffer, rank-major like _gather_from_all."""
+        B = emb_v.shape[0]
+        nf, ny = B * 128, 2 * B
+        nn_ = 2 * neg_idx.numel() if neg_idx is not None else 0
+        rec = torch.empty(2 * nf + ny + nn_, dtype=torch.float32, device=emb_v.device)
+        rec[:nf].copy_(emb_v.reshape(-1))
+        rec[nf:2 * nf].copy_(emb_a.reshape(-1))
+        rec[2 * nf:2 * nf + ny].view(torch.int64).copy_(y)
+        if neg_idx is not None:
+            rec[2 * nf + ny:].view(torch.int64).copy_(neg_idx.reshape(-1))
+        W = self.world
+        flat = torch.empty(W * rec.numel(), dtype=torch.float32, device=emb_v.device)
+        dist.all_gather_into_tensor(flat, rec)
+        allrec = flat.view(W, rec.numel())
+        out = [allrec[:, :nf].view(W, B, 128), allrec[:, nf:2 * nf].view(W, B, 128), allrec[:, 2 * nf:2 * nf + ny].view(torch.int64)]
+        if neg_idx is not None:
+            out.append(allrec[:, 2 * nf + ny:].view(torch.int64).view(W, B, neg_idx.shape[1]))
+        return out
+
     def update_memory(self, video_emb, audio_emb, y):
         """avid.py:103-129.  Takes the un-normalised embeddings: the kernel normalises them itself."""
         if self._gathered is not None:
             video_emb, audio_emb, y = self._gathered
             self._gathered = None
         elif self.distributed:
-            video_emb = _gather_from_all(video_emb)
-            audio_emb = _gather_from_all(audio_emb)
-            y = _gather_from_all(y)
+            video_emb, audio_emb, y = self._gather_queries(video_emb, audio_emb, y)
         ops.bank_update(self.view1_mem, self.view2_mem, video_emb, audio_emb, y, float(self.momentum[0]), float(self.momentum[1]),
                         row_begin=self.row_begin, row_end=self.row_end)
+
+    def _check_indices(self):
+        if self._bad is not None and int(self._bad[0]) != 0:
+            self._bad.zero_()
+            raise IndexError('an instance index passed to the criterion was outside [0, %d)' % self.memory_size)
 
     # ---- fused path ----------------------------------------------------------------------------
     def keys(self):
@@ -199,7 +250,7 @@ class AVIDSimilarityMemoryBank(nn.Module):
         grad_a = out[1 + len(keys) + B * 128:].view(B, 128)
         args = ops.make_nce_args(emb_v, emb_a, y, self.view1_mem, self.view2_mem, key_tuples, K, crit.avg_exp_score,
                                  neg_idx=neg_idx, seed=seed, offset=offset, positive_set=pos, temperature=self.temperature,
-                                 loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a)
+                                 loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a, bad_index=self._bad)
         if not crit.z_ready():
             # nce.py:21-36: Z <- mean exp(score) over the negatives of the first key of the first batch
             # (mean of the per-rank means when distributed), frozen afterwards.
@@ -213,9 +264,18 @@ class AVIDSimilarityMemoryBank(nn.Module):
         ops.nce_forward_backward(args, ws)
         return loss_total.reshape(()), loss_keys, grad_v, grad_a
 
+    def _reduce_scatter(self, mine, part):
+        """mine (rec) <- sum over ranks of part[rank] (W, rec)."""
+        if dist.get_backend() == 'gloo':        # gloo (CPU protocol tests) has no reduce-scatter
+            dist.all_reduce(part)
+            mine.copy_(part[self.rank])
+        else:
+            dist.reduce_scatter_tensor(mine, part.view(-1))
+
     def _run_sharded(self, emb_v, emb_a, y):
-        """One step of the row-partitioned protocol: gather queries -> score owned rows -> all-reduce partials
-        -> finalize own queries.  Scores / gradients cross NVLink (4 B per negative), bank rows (512 B) never do."""
+        """One step of the row-partitioned protocol: ONE packed all-gather of the queries -> score owned rows
+        -> ONE reduce-scatter of the partials -> finalize own queries.  Scores / gradients cross NVLink (4 B per negative),
+        bank rows (512 B) never do."""
         crit = self._owner.criterion
         keys, key_tuples = self._key_tuples()
         W, B, K, nk = self.world, emb_v.shape[0], int(self.num_negatives), len(keys)
@@ -224,18 +284,21 @@ class AVIDSimilarityMemoryBank(nn.Module):
         pos_k = pos.shape[1] if pos is not None else 0
         neg_idx, seed, offset = self._draw(y)
         # (1) queries of all ranks, rank-major (these are also what update_memory needs: avid.py:109-111)
-        all_v, all_a, all_y = _gather_from_all(emb_v), _gather_from_all(emb_a), _gather_from_all(y)
-        all_neg = _gather_from_all(neg_idx) if neg_idx is not None else None
+        gathered = self._gather_queries(emb_v, emb_a, y, neg_idx)
+        all_v, all_a, all_y = gathered[:3]
+        all_neg = gathered[3] if neg_idx is not None else None
         self._gathered = (all_v, all_a, all_y)
         ws = self._workspace(W * B, K, pos_k, nk, dev)
-        # (2) partial dL/d(normalised embedding) and per-query loss terms over the rows this rank holds
-        part = torch.zeros(2 * W * B * 128 + nk * W * B, dtype=torch.float32, device=dev)
-        gh_v, gh_a = part[:W * B * 128].view(W * B, 128), part[W * B * 128:2 * W * B * 128].view(W * B, 128)
-        loss_part = part[2 * W * B * 128:].view(nk, W * B)
+        # (2) partial dL/d(normalised embedding) and per-query loss terms over the rows this rank holds, written straight into the
+        #     rank-major records the reduce-scatter sends back to the query owners
+        nf = B * 128
+        part = torch.empty(W, 2 * nf + nk * B, dtype=torch.float32, device=dev)
+        gh_v, gh_a = part[:, :nf].view(W, B, 128), part[:, nf:2 * nf].view(W, B, 128)
+        loss_part = part[:, 2 * nf:].view(W, nk, B)
         args = ops.make_nce_args(all_v, all_a, all_y, self.view1_mem, self.view2_mem, key_tuples, K, crit.avg_exp_score,
                                  num_rows=self.memory_size, row_begin=self.row_begin, row_end=self.row_end, neg_idx=all_neg, seed=seed,
                                  offset=offset, positive_set=pos, mean_batch=B, temperature=self.temperature,
-                                 grad_hat_v=gh_v, grad_hat_a=gh_a, loss_part=loss_part)
+                                 grad_hat_v=gh_v, grad_hat_a=gh_a, loss_part=loss_part, bad_index=self._bad)
         if not crit.z_ready():
             # the sharded partition pass returns the SUM of exp(score) over held rows; equal batches make the mean over all
             # W*B*K negatives equal to the reference's mean of per-rank means (nce.py:27-33)
@@ -246,23 +309,24 @@ class AVIDSimilarityMemoryBank(nn.Module):
             crit.avg_exp_score.copy_(z.reshape(()))
             crit.mark_ready()
         ops.nce_forward_backward(args, ws)
-        # (3) sum the partials over the shards
-        dist.all_reduce(part)
+        # (3) sum the partials over the shards; every rank receives the record of its own B queries
+        mine = torch.empty(2 * nf + nk * B, dtype=torch.float32, device=dev)
+        self._reduce_scatter(mine, part)
         # (4) backward of F.normalize, batch means and coefficient mix for this rank's own queries
         out = torch.empty(1 + nk + 2 * B * 128, dtype=torch.float32, device=dev)
         loss_total, loss_keys = out[0:1], out[1:1 + nk]
         grad_v, grad_a = out[1 + nk:1 + nk + B * 128].view(B, 128), out[1 + nk + B * 128:].view(B, 128)
-        lo, hi = self.rank * B, (self.rank + 1) * B
         fin = ops.make_nce_args(emb_v, emb_a, y, self.view1_mem, self.view2_mem, key_tuples, K, crit.avg_exp_score,
                                 num_rows=self.memory_size, row_begin=self.row_begin, row_end=self.row_end, mean_batch=B,
                                 temperature=self.temperature, loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a,
-                                grad_hat_v=gh_v[lo:hi], grad_hat_a=gh_a[lo:hi], loss_part=loss_part[:, lo:hi].contiguous())
+                                grad_hat_v=mine[:nf].view(B, 128), grad_hat_a=mine[nf:2 * nf].view(B, 128), loss_part=mine[2 * nf:].view(nk, B))
         ops.nce_finalize(fin, ws)
         return loss_total.reshape(()), loss_keys, grad_v, grad_a
 
     def forward(self, video_emb, audio_emb, y):
         """Returns (loss_total, {key: loss}) -- the reference returns raw scores here (avid.py:47-80) and leaves
         the loss to NCECriterion; the fused kernel produces both at once, then the bank is updated (avid.py:78)."""
+        self._check_indices()
         loss_total, loss_keys = _FusedNCE.apply(video_emb, audio_emb, self, y)
         with torch.no_grad():
             self.update_memory(video_emb.detach().contiguous().float(), audio_emb.detach().contiguous().float(),

@@ -59,6 +59,11 @@ struct NceParams {
     float* loss_total;
     float weights[AVID_MAX_KEYS];
     int do_finalize;
+    int* bad_index;             // optional: set to 1 when a y[b] lies outside [0, N)
+    // packed per-rank records of a sharded step: query b = (group b / group_batch, row b % group_batch); emb / y / neg_idx of
+    // group g start in_group_stride BYTES after those of group g - 1, grad_hat / loss_part out_group_stride bytes (0: dense)
+    int group_batch;
+    size_t in_group_stride, out_group_stride;
 };
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -101,19 +106,71 @@ __device__ __forceinline__ void load_normalized(const float* emb, int b, int l8,
     for (int j = 0; j < 4; ++j) out[j] = make_float4(out[j].x * inv, out[j].y * inv, out[j].z * inv, out[j].w * inv);
 }
 
-// a warp keeps 2 row quads (4 rows each) per bank in flight: 2 x 4 rows x 2 banks x 512 B = 8 KB
+// ---- bank rows reach the SM as bulk async copies (cp.async.bulk, 512 B per row) into a per-warp shared-memory ring ----
+// The gather is a latency problem, not a bandwidth one (K = 1024: 131 k rows of 512 B per step, ~4 dependent DRAM round trips
+// per warp when the rows in flight are bounded by registers).  With the rows landing in shared memory the data in flight per SM
+// is the ring size (3 CTAs x 4 warps x 16 KB = 192 KB, far above the ~44 KB bandwidth-delay product per SM), independent of
+// registers and occupancy; the arithmetic then reads the rows with conflict-free 128-byte group loads.
+constexpr int kStageItems = 8;                                  // one pass of the quad loop: 2 quads x 4 groups
+constexpr int kRowBytes = kD * 4;                               // 512
+constexpr int kStageBytes = kStageItems * 2 * kRowBytes;        // [item][bank][128] floats = 8 KB
+constexpr int kRing = 2;                                        // stages in flight per warp
+constexpr int kGatherSmem = kGatherWarps * kRing * kStageBytes + kGatherWarps * kRing * 8;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_row(void* dst, const void* src, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "n"(kRowBytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+struct ItemDesc {          // what lane l knows about item l of a 32-item chunk
+    int kind;              // -1 nothing to score here, 0 negative kk, 1 self, 2 positive-set entry kk
+    int kk;
+    int64_t idx;
+};
 
 __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {
+    extern __shared__ __align__(128) uint8_t nce_smem[];
     const int b = blockIdx.x, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, l8 = lane & 7;
+    // gathered queries of a sharded step arrive as one packed record per rank (group): query b = (group g, row bl)
+    const int g_i = p.group_batch > 0 ? b / p.group_batch : 0, bl = p.group_batch > 0 ? b - g_i * p.group_batch : b;
+    const size_t in_off = (size_t)g_i * p.in_group_stride;          // bytes
+    const float* emb0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[0]) + in_off);
+    const float* emb1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[1]) + in_off);
+    const int64_t* negs = p.neg_idx ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg_idx) + in_off) + (size_t)bl * p.K : nullptr;
+
+    float* ring = reinterpret_cast<float*>(nce_smem + (size_t)warp * kRing * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nce_smem + (size_t)kGatherWarps * kRing * kStageBytes) + warp * kRing;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     float4 e_ctx[2][4];
-    load_normalized(p.emb[0], b, l8, e_ctx[0]);
-    load_normalized(p.emb[1], b, l8, e_ctx[1]);
-    const int64_t y = p.y[b];
+    load_normalized(emb0, bl, l8, e_ctx[0]);
+    load_normalized(emb1, bl, l8, e_ctx[1]);
+    int64_t y = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.y) + in_off)[bl];
+    if (y < 0 || y >= p.N) {       // the reference raises IndexError here (avid.py:57-58): report it, score no positive, read nothing
+        if (p.bad_index && threadIdx.x == 0 && split == 0) *p.bad_index = 1;
+        y = -1;
+    }
     const float Z = p.Z ? *p.Z : 1.0f;
-    const int32_t* pos_row = (p.positive_set && p.pos_k > 0) ? p.positive_set + (size_t)y * p.pos_k : nullptr;
+    const int32_t* pos_row = (p.positive_set && p.pos_k > 0 && y >= 0) ? p.positive_set + (size_t)y * p.pos_k : nullptr;
 
     // item stream of this CTA: [self, positives...] (split 0 only) then negatives [k_begin, k_end)
     const int npos = (split == 0) ? 1 + (pos_row ? p.pos_k : 0) : 0;
@@ -129,57 +186,87 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     float loss_acc[2] = {0.f, 0.f};
     const int key_passes = (p.num_keys + 3) >> 2;
     const int u_sel = l8 >> 2;
+    const uint32_t row_bytes = (p.bank_used[0] ? kRowBytes : 0) + (p.bank_used[1] ? kRowBytes : 0);
 
-    for (int c0 = warp * 32; c0 < n_items; c0 += kGatherWarps * 32) {
-        // each lane describes one item of the chunk: kind 0 = negative k, 1 = self, 2 = positive-set entry
+    // lane l describes item c0 + l: kind, slot, bank row (Philox draw or the injected index)
+    auto describe = [&](int c0) {
+        ItemDesc d{-1, 0, -1};
         const int item = c0 + lane;
-        int kind = -1, kk = 0;
-        int64_t idx = -1;
         if (item < n_items) {
             if (item < npos) {
-                kind = item == 0 ? 1 : 2;
-                kk = item - 1;
-                idx = item == 0 ? y : (int64_t)pos_row[item - 1];
+                d.kind = item == 0 ? 1 : 2;
+                d.kk = item - 1;
+                d.idx = item == 0 ? y : (int64_t)pos_row[item - 1];
             } else {
-                kind = 0;
-                kk = k_begin + (item - npos);
-                idx = p.neg_idx ? p.neg_idx[(size_t)b * p.K + kk]
-                                : draw_negative(p.seed, p.offset, b, kk, p.K, p.N, y, pos_row, p.pos_k);
-                if (p.neg_idx_out) p.neg_idx_out[(size_t)b * p.K + kk] = idx;
+                d.kind = 0;
+                d.kk = k_begin + (item - npos);
+                d.idx = negs ? negs[d.kk] : draw_negative(p.seed, p.offset, b, d.kk, p.K, p.N, y, pos_row, p.pos_k);
+                if (p.neg_idx_out) p.neg_idx_out[(size_t)b * p.K + d.kk] = d.idx;
             }
         }
-        if (!(idx >= p.row_begin && idx < p.row_end)) kind = -1;      // rows another shard holds are scored there
-        const int n_chunk = min(32, n_items - c0);
+        if (!(d.idx >= p.row_begin && d.idx < p.row_end)) d.kind = -1;      // rows another shard holds are scored there
+        return d;
+    };
+    // the 8 lanes describing stage `st` of a chunk start the copies of their rows into ring slot `slot`
+    auto issue = [&](const ItemDesc& d, int st, int slot) {
+        const bool mine = (lane >> 3) == st && d.kind >= 0;
+        const uint32_t n = __popc(__ballot_sync(0xffffffffu, mine));
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bars[slot])), "r"(n * row_bytes) : "memory");
+        __syncwarp();
+        if (mine) {
+            const size_t off = (size_t)(d.idx - p.row_begin) * kD;
+            float* dst = ring + (size_t)slot * (kStageBytes / 4) + (lane & 7) * (2 * kD);
+            if (p.bank_used[0]) bulk_row(dst, p.bank[0] + off, &bars[slot]);
+            if (p.bank_used[1]) bulk_row(dst + kD, p.bank[1] + off, &bars[slot]);
+        }
+    };
 
-        for (int j0 = 0; j0 < n_chunk; j0 += 8) {
+    const int first = warp * 32;
+    const int n_chunks = first < n_items ? (n_items - first + kGatherWarps * 32 - 1) / (kGatherWarps * 32) : 0;
+    ItemDesc cur = describe(first), nxt = cur;
+    if (n_chunks > 0) {
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) issue(cur, s, s);
+    }
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int c0 = first + ci * kGatherWarps * 32;
+        const bool has_next = ci + 1 < n_chunks;
+        if (has_next) nxt = describe(c0 + kGatherWarps * 32);
+        const int n_chunk = min(32, n_items - c0);
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            const int t = ci * 4 + st, slot = t % kRing;
+            bar_wait(&bars[slot], (uint32_t)((t / kRing) & 1));
+            const float* stage = ring + (size_t)slot * (kStageBytes / 4);
             float4 rv[2][4], ra[2][4];
             int kind_u[2], kk_u[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int src = (j0 + 4 * u + grp) & 31;          // the item this group scores in quad u
-                const int64_t idx_u = __shfl_sync(0xffffffffu, idx, src);
-                kind_u[u] = __shfl_sync(0xffffffffu, kind, src);
-                kk_u[u] = __shfl_sync(0xffffffffu, kk, src);
-                if (j0 + 4 * u + grp >= n_chunk) kind_u[u] = -1;
+                const int src = st * 8 + 4 * u + grp;          // the item this group scores in quad u
+                kind_u[u] = __shfl_sync(0xffffffffu, cur.kind, src);
+                kk_u[u] = __shfl_sync(0xffffffffu, cur.kk, src);
+                if (src >= n_chunk) kind_u[u] = -1;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     rv[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     ra[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (kind_u[u] >= 0) {
-                    const size_t off = (size_t)(idx_u - p.row_begin) * kD;
+                    const float4* r = reinterpret_cast<const float4*>(stage + (4 * u + grp) * (2 * kD)) + l8;
                     if (p.bank_used[0]) {
-                        const float4* r = reinterpret_cast<const float4*>(p.bank[0] + off) + l8;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) rv[u][j] = ld_stream(r + 8 * j);
+                        for (int j = 0; j < 4; ++j) rv[u][j] = r[8 * j];
                     }
                     if (p.bank_used[1]) {
-                        const float4* r = reinterpret_cast<const float4*>(p.bank[1] + off) + l8;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ra[u][j] = ld_stream(r + 8 * j);
+                        for (int j = 0; j < 4; ++j) ra[u][j] = r[kD / 4 + 8 * j];
                     }
                 }
             }
+            // every lane has its rows in registers: the slot can take the stage kRing steps ahead
+            __syncwarp();
+            if (st + kRing < 4) issue(cur, st + kRing, slot);
+            else if (has_next) issue(nxt, st + kRing - 4, slot);
             // d[u][bank][ctx] of this group's two rows, on all 8 lanes of the group
             float d[2][2][2];
 #pragma unroll
@@ -206,8 +293,8 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
                         const float d1 = key.bank == 0 ? (key.ctx == 0 ? d[1][0][0] : d[1][0][1]) : (key.ctx == 0 ? d[1][1][0] : d[1][1][1]);
                         const float s = (u_sel ? d1 : d0) * p.inv_T;
                         if (p.scores) {
-                            const int slot = kind_m == 1 ? 0 : (kind_m == 2 ? 1 + kk_m : 1 + p.score_pos_k + kk_m);
-                            p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot] = s;
+                            const int slot_s = kind_m == 1 ? 0 : (kind_m == 2 ? 1 + kk_m : 1 + p.score_pos_k + kk_m);
+                            p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot_s] = s;
                         }
                         if (p.Z) {
                             // nce.py:42-57 with c = K_key * Z
@@ -230,12 +317,12 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
                 const int nk = min(4, p.num_keys - 4 * kp);
                 for (int q = 0; q < nk; ++q) {
                     const int bank = p.keys[q + 4 * kp].bank, ctx = p.keys[q + 4 * kp].ctx;      // uniform
-                    const float c0 = __shfl_sync(0xffffffffu, coef, (lane & 24) | q);
-                    const float c1 = __shfl_sync(0xffffffffu, coef, (lane & 24) | 4 | q);
+                    const float c0q = __shfl_sync(0xffffffffu, coef, (lane & 24) | q);
+                    const float c1q = __shfl_sync(0xffffffffu, coef, (lane & 24) | 4 | q);
                     if (bank == 0) {
-                        if (ctx == 0) { cf[0][0][0] += c0; cf[1][0][0] += c1; } else { cf[0][0][1] += c0; cf[1][0][1] += c1; }
+                        if (ctx == 0) { cf[0][0][0] += c0q; cf[1][0][0] += c1q; } else { cf[0][0][1] += c0q; cf[1][0][1] += c1q; }
                     } else {
-                        if (ctx == 0) { cf[0][1][0] += c0; cf[1][1][0] += c1; } else { cf[0][1][1] += c0; cf[1][1][1] += c1; }
+                        if (ctx == 0) { cf[0][1][0] += c0q; cf[1][1][0] += c1q; } else { cf[0][1][1] += c0q; cf[1][1][1] += c1q; }
                     }
                 }
             }
@@ -254,6 +341,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
                     }
                 }
         }
+        cur = nxt;
     }
     if (!p.Z) return;
 
@@ -310,18 +398,19 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     if (s_ticket != (unsigned)(p.splits - 1)) return;
     __threadfence();
     const int e = threadIdx.x;          // 0..127: one embedding column, both contexts
+    const size_t out_off = (size_t)g_i * p.out_group_stride;
     float g[2];
 #pragma unroll
     for (int ctx = 0; ctx < 2; ++ctx) {
         float a = 0.f;
         for (int s = 0; s < p.splits; ++s) a += __ldcg(p.part_grad + ((size_t)(s * 2 + ctx) * p.B + b) * kD + e);
         g[ctx] = a;
-        if (p.grad_hat[ctx]) p.grad_hat[ctx][(size_t)b * kD + e] = a;
+        if (p.grad_hat[ctx]) reinterpret_cast<float*>(reinterpret_cast<char*>(p.grad_hat[ctx]) + out_off)[(size_t)bl * kD + e] = a;
     }
     if (e < p.num_keys) {
         float l = 0.f;
         for (int s = 0; s < p.splits; ++s) l += __ldcg(p.part_loss + ((size_t)s * p.num_keys + e) * p.B + b);
-        p.loss_part[(size_t)e * p.B + b] = l;
+        reinterpret_cast<float*>(reinterpret_cast<char*>(p.loss_part) + out_off)[(size_t)e * (p.group_batch > 0 ? p.group_batch : p.B) + bl] = l;
     }
     if (e == 0) p.counter[b] = 0u;      // ready for the next launch
     if (!p.do_finalize) return;
@@ -329,7 +418,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     // backward of x -> x / max(||x||, eps):  (g - ehat <ehat, g>) / ||x||   (g / eps when clamped)
 #pragma unroll
     for (int ctx = 0; ctx < 2; ++ctx) {
-        const float x = p.emb[ctx][(size_t)b * kD + e];
+        const float x = (ctx ? emb1 : emb0)[(size_t)bl * kD + e];
         const float xx = warp_sum(x * x);
         __syncthreads();
         if (lane == 0) s_red[warp] = xx;
@@ -535,6 +624,16 @@ static Workspace carve(void* base, int B, int K, int pos_k, int num_keys, bool w
     return w;
 }
 
+static int configure_gather() {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(nce_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem);
+        if (e != cudaSuccess) { set_error("nce: shared-memory attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        configured = true;
+    }
+    return AVID_OK;
+}
+
 static int fill_params(const avid_nce_args_t* a, NceParams* p) {
     AVID_REQUIRE(a != nullptr, "nce: args is NULL");
     AVID_REQUIRE(a->emb_video && a->emb_audio && a->y && a->bank_video && a->bank_audio, "nce: NULL tensor pointer");
@@ -575,6 +674,13 @@ static int fill_params(const avid_nce_args_t* a, NceParams* p) {
     p->scores = a->scores;
     p->score_pos_k = p->pos_k;
     p->neg_idx_out = a->neg_idx_out;
+    p->bad_index = a->bad_index;
+    AVID_REQUIRE(a->group_batch >= 0 && (a->group_batch == 0 || a->batch % a->group_batch == 0), "nce: batch %d is not a multiple of group_batch %d",
+                 a->batch, a->group_batch);
+    AVID_REQUIRE(a->in_group_stride % 16 == 0 && a->out_group_stride % 16 == 0, "nce: group strides must be multiples of 16 bytes");
+    p->group_batch = a->group_batch;
+    p->in_group_stride = a->group_batch > 0 ? (size_t)a->in_group_stride : 0;
+    p->out_group_stride = a->group_batch > 0 ? (size_t)a->out_group_stride : 0;
     return AVID_OK;
 }
 
@@ -610,7 +716,9 @@ int avid_nce_forward_backward(const avid_nce_args_t* a, void* workspace, size_t 
     p.loss_keys = a->loss_keys;  p.loss_total = a->loss_total;
     for (int k = 0; k < AVID_MAX_KEYS; ++k) p.weights[k] = k < a->num_keys ? a->keys[k].weight : 0.f;
     p.do_finalize = sharded ? 0 : 1;
-    nce_gather_kernel<<<dim3(a->batch, p.splits), kGatherThreads, 0, st>>>(p);
+    AVID_REQUIRE(sharded || a->group_batch == 0, "nce: packed per-rank records (group_batch) are for the sharded protocol only");
+    if ((rc = configure_gather())) return rc;
+    nce_gather_kernel<<<dim3(a->batch, p.splits), kGatherThreads, kGatherSmem, st>>>(p);
     return check_launch("nce_gather_kernel");
 }
 
@@ -666,7 +774,8 @@ int avid_nce_partition_mean(const avid_nce_args_t* a, int32_t key, float* out_me
     const size_t n = (size_t)a->batch * stride;
     fill_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(w.scores, n, -INFINITY);
     if ((rc = check_launch("fill_kernel"))) return rc;
-    nce_gather_kernel<<<dim3(a->batch, q.splits), kGatherThreads, 0, st>>>(q);
+    if ((rc = configure_gather())) return rc;
+    nce_gather_kernel<<<dim3(a->batch, q.splits), kGatherThreads, kGatherSmem, st>>>(q);
     if ((rc = check_launch("nce_gather_kernel(scores)"))) return rc;
     const bool sharded = a->row_begin != 0 || a->row_end != a->num_rows;
     const int kn = q.keys[0].num_neg;

@@ -1,4 +1,6 @@
 """Two-tower wrapper + projection heads (reference: models/av_wrapper.py)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -80,6 +82,21 @@ class AV_Wrapper(nn.Module):
         return getattr(self, head_name)(emb) if self.use_linear_proj else emb
 
     def forward(self, video, audio):
+        if os.environ.get('AVID_TOWER_STREAMS', '0') == '1' and video.is_cuda:
+            # the two towers are independent until the criterion: the audio tower (11 % of the FLOPs) runs on a side stream, so
+            # its bandwidth-bound passes overlap the video tower's tensor-bound ones; autograd replays each tower's backward on
+            # the stream of its forward
+            cur = torch.cuda.current_stream()
+            side = self.__dict__.get('_side_stream')
+            if side is None:
+                side = self.__dict__['_side_stream'] = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                audio_emb = self._embed(self.audio_model, 'audio_proj', audio)
+            video_emb = self._embed(self.video_model, 'video_proj', video)
+            cur.wait_stream(side)
+            audio_emb.record_stream(cur)
+            return video_emb, audio_emb
         return self._embed(self.video_model, 'video_proj', video), self._embed(self.audio_model, 'audio_proj', audio)
 
 

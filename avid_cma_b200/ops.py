@@ -152,25 +152,68 @@ def nce_workspace(batch, num_neg, pos_k, num_keys, device):
     return torch.zeros(n, dtype=torch.uint8, device=device)     # the ticket counters at its start must be zero before the first call
 
 
+def _group_layout(name, t, elem_bytes, rows_per_group):
+    """(pointer to record 0, bytes between records) of a packed per-rank tensor (W, rows_per_group, ...) whose records are dense."""
+    if t.shape[1] != rows_per_group or not t[0].is_contiguous():
+        raise ValueError(f"{name}: every rank record must be a dense block of {rows_per_group} rows")
+    return t[0], t.stride(0) * elem_bytes
+
+
 def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows=None, row_begin=0, row_end=None,
                   neg_idx=None, seed=0, offset=0, positive_set=None, mean_batch=0, temperature=0.07,
                   loss_keys=None, loss_total=None, grad_v=None, grad_a=None, scores=None, neg_idx_out=None,
-                  grad_hat_v=None, grad_hat_a=None, loss_part=None):
-    """keys: sequence of (ctx, bank, pos_mode, num_neg, weight)."""
+                  grad_hat_v=None, grad_hat_a=None, loss_part=None, bad_index=None):
+    """keys: sequence of (ctx, bank, pos_mode, num_neg, weight).
+
+    Dense call: emb_* (B,128), y (B), neg_idx (B,K), grad_hat_* (B,128), loss_part (num_keys,B).
+    Packed call (sharded protocol): emb_* (W,B,128), y (W,B), neg_idx (W,B,K) are strided views into the ONE all-gathered
+    buffer of the step (a dense record per rank), grad_hat_* (W,B,128) and loss_part (W,num_keys,B) views into the ONE buffer
+    that is reduce-scattered afterwards: the kernel addresses rank records by stride, nothing is re-packed."""
     a = NceArgs()
-    a.emb_video, a.emb_audio, a.y = _p(emb_v), _p(emb_a), _p(y, torch.int64)
+    grouped = emb_v.dim() == 3
+    views = {}
+    if grouped:
+        W, B = emb_v.shape[0], emb_v.shape[1]
+        ins = [("emb_v", emb_v, 4), ("emb_a", emb_a, 4), ("y", y, 8)] + ([("neg_idx", neg_idx, 8)] if neg_idx is not None else [])
+        strides = set()
+        for name, t, eb in ins:
+            views[name], st = _group_layout(name, t, eb, B)
+            strides.add(st)
+        if len(strides) != 1:
+            raise ValueError("packed inputs must share one record stride")
+        a.group_batch, a.in_group_stride = B, strides.pop()
+        outs = [(n_, t) for n_, t in (("grad_hat_v", grad_hat_v), ("grad_hat_a", grad_hat_a)) if t is not None]
+        strides = set()
+        for name, t in outs:
+            views[name], st = _group_layout(name, t, 4, B)
+            strides.add(st)
+        if loss_part is not None:
+            if tuple(loss_part.shape) != (W, len(keys), B) or not loss_part[0].is_contiguous():
+                raise ValueError("packed loss_part must be (W, num_keys, B) with dense records")
+            views["loss_part"] = loss_part[0]
+            strides.add(loss_part.stride(0) * 4)
+        if len(strides) > 1:
+            raise ValueError("packed outputs must share one record stride")
+        a.out_group_stride = strides.pop() if strides else 0
+        batch = W * B
+        e_v, e_a, y_, n_ = views["emb_v"], views["emb_a"], views["y"], views.get("neg_idx")
+        gh_v, gh_a, lp = views.get("grad_hat_v"), views.get("grad_hat_a"), views.get("loss_part")
+    else:
+        batch = emb_v.shape[0]
+        e_v, e_a, y_, n_, gh_v, gh_a, lp = emb_v, emb_a, y, neg_idx, grad_hat_v, grad_hat_a, loss_part
+        if emb_v.shape != emb_a.shape or emb_v.shape[1] != 128 or y.shape[0] != emb_v.shape[0]:
+            raise ValueError("embeddings must be (B,128) and y (B,)")
+        if neg_idx is not None and tuple(neg_idx.shape) != (batch, num_neg):
+            raise ValueError("neg_idx must be (B,K)")
+    a.emb_video, a.emb_audio, a.y = _p(e_v), _p(e_a), _p(y_, torch.int64)
     a.bank_video, a.bank_audio = _p(bank_v), _p(bank_a)
     a.num_rows = bank_v.shape[0] if num_rows is None else num_rows
     a.row_begin = row_begin
     a.row_end = a.num_rows if row_end is None else row_end
     if bank_v.shape[0] != a.row_end - a.row_begin or bank_a.shape != bank_v.shape or bank_v.shape[1] != 128:
         raise ValueError("bank shapes do not match the row range / embedding width 128")
-    if emb_v.shape != emb_a.shape or emb_v.shape[1] != 128 or y.shape[0] != emb_v.shape[0]:
-        raise ValueError("embeddings must be (B,128) and y (B,)")
-    a.batch, a.mean_batch, a.num_neg = emb_v.shape[0], mean_batch, num_neg
-    if neg_idx is not None and tuple(neg_idx.shape) != (a.batch, num_neg):
-        raise ValueError("neg_idx must be (B,K)")
-    a.neg_idx = _p(neg_idx, torch.int64, optional=True)
+    a.batch, a.mean_batch, a.num_neg = batch, mean_batch, num_neg
+    a.neg_idx = _p(n_, torch.int64, optional=True)
     a.seed, a.offset = seed, offset
     a.positive_set = _p(positive_set, torch.int32, optional=True)
     a.pos_k = positive_set.shape[1] if positive_set is not None else 0
@@ -183,12 +226,14 @@ def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows
     a.grad_video, a.grad_audio = _p(grad_v, optional=True), _p(grad_a, optional=True)
     a.scores = _p(scores, optional=True)
     a.neg_idx_out = _p(neg_idx_out, torch.int64, optional=True)
-    a.grad_hat_video, a.grad_hat_audio = _p(grad_hat_v, optional=True), _p(grad_hat_a, optional=True)
-    a.loss_part = _p(loss_part, optional=True)
+    a.grad_hat_video, a.grad_hat_audio = _p(gh_v, optional=True), _p(gh_a, optional=True)
+    a.loss_part = _p(lp, optional=True)
+    # a pinned host int32 the kernel raises when an instance index is out of range (polled by the criterion without a sync)
+    a.bad_index = C.c_void_p(bad_index.data_ptr()) if bad_index is not None else None
     # the struct only carries raw pointers: keep the tensors alive as long as the args object
     a.tensors = dict(emb_v=emb_v, emb_a=emb_a, y=y, bank_v=bank_v, bank_a=bank_a, neg_idx=neg_idx, positive_set=positive_set, Z=Z,
                      loss_keys=loss_keys, loss_total=loss_total, grad_v=grad_v, grad_a=grad_a, scores=scores, neg_idx_out=neg_idx_out,
-                     grad_hat_v=grad_hat_v, grad_hat_a=grad_hat_a, loss_part=loss_part)
+                     grad_hat_v=grad_hat_v, grad_hat_a=grad_hat_a, loss_part=loss_part, bad_index=bad_index)
     return a
 
 
@@ -208,9 +253,25 @@ def nce_partition_mean(args, key, out, workspace):
 
 
 def bank_update(bank_v, bank_a, emb_v, emb_a, y, mom_v, mom_a, row_begin=0, row_end=None):
+    """emb_* (n,128) and y (n) dense, or the packed views (W,B,128) / (W,B) of the step's all-gathered buffer."""
     row_end = row_begin + bank_v.shape[0] if row_end is None else row_end
+    n, gb, stride = y.shape[0], 0, 0
+    if emb_v.dim() == 3:
+        n, gb = emb_v.shape[0] * emb_v.shape[1], emb_v.shape[1]
+        (emb_v, s0), (emb_a, s1), (y, s2) = (_group_layout("emb_v", emb_v, 4, gb), _group_layout("emb_a", emb_a, 4, gb),
+                                             _group_layout("y", y, 8, gb))
+        if not s0 == s1 == s2:
+            raise ValueError("packed inputs must share one record stride")
+        stride = s0
     check(_lib.lib().avid_bank_update(_p(bank_v), _p(bank_a), row_begin, row_end, _p(emb_v), _p(emb_a), _p(y, torch.int64),
-                                      y.shape[0], float(mom_v), float(mom_a), _stream()))
+                                      n, gb, stride, float(mom_v), float(mom_a), _stream()))
+
+
+def bank_init_(bank, row_begin, seed, which):
+    """init_memory (avid.py:88-96) for the rows [row_begin, row_begin + len(bank)) of bank `which`: L2-normalised N(0,1) rows that
+    depend only on (seed, which, row) -- no broadcast from rank 0 needed."""
+    check(_lib.lib().avid_bank_init(_p(bank), row_begin, bank.shape[0], seed & 0xFFFFFFFFFFFFFFFF, which, _stream()))
+    return bank
 
 
 def rows_l2_normalize_(x):

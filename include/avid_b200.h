@@ -105,6 +105,17 @@ typedef struct avid_nce_args {
     float*         grad_hat_video; /* (B, 128) partial dL/d normalised video embedding; may be NULL when not sharded */
     float*         grad_hat_audio; /* (B, 128) */
     float*         loss_part;      /* (num_keys, B) per-instance loss terms (before the batch mean) */
+    /* Optional int32 the kernel sets to 1 when some y[b] is outside [0, num_rows) (the reference raises IndexError on such an
+     * index, avid.py:57-58).  The offending instance then contributes no positive; nothing is read or written out of bounds.
+     * May live in pinned host memory (the caller polls it without a device sync).  NULL: not reported. */
+    int32_t*       bad_index;
+    /* Sharded mode, packed records (ONE all-gather in, ONE reduce-scatter out).  group_batch > 0: query b of
+     * the `batch` gathered queries is row (b % group_batch) of rank-record (b / group_batch); emb_video / emb_audio / y / neg_idx
+     * point at the fields of record 0 and record g starts in_group_stride BYTES further; grad_hat_* / loss_part (then laid out
+     * (num_keys, group_batch) per record) likewise with out_group_stride.  0: dense (B, ...) arrays. */
+    int32_t        group_batch;
+    int64_t        in_group_stride;
+    int64_t        out_group_stride;
 } avid_nce_args_t;
 
 /* Scratch of the criterion kernels.  Its first 4 * (batch + 1) bytes are ticket counters (splits done per query, queries
@@ -131,10 +142,18 @@ int avid_nce_partition_mean(const avid_nce_args_t* args_host, int32_t key, float
 
 /* AVIDSimilarityMemoryBank.update_memory (avid.py:103-129) after the all-gather:
  * for i < n: if y[i] in [row_begin,row_end): m = bank[y[i]]; m = mom*m + (1-mom)*normalize(emb[i]);
- * bank[y[i]] = normalize(m), for both banks.  Duplicate y: one of the writers wins.  */
+ * bank[y[i]] = normalize(m), for both banks.  Duplicate y: the LAST occurrence in y wins (one complete update per row,
+ * like index_copy_; never a torn row).  group_batch > 0: the n instances come as packed per-rank records of the one
+ * all-gather of the step (instance i = row i % group_batch of record i / group_batch, records group_stride BYTES apart,
+ * emb_video / emb_audio / y point at the fields of record 0); 0: dense arrays.  */
 int avid_bank_update(float* bank_video, float* bank_audio, int64_t row_begin, int64_t row_end,
-                     const float* emb_video, const float* emb_audio, const int64_t* y, int32_t n,
+                     const float* emb_video, const float* emb_audio, const int64_t* y, int32_t n, int32_t group_batch, int64_t group_stride,
                      float momentum_video, float momentum_audio, void* stream);
+
+/* init_memory (avid.py:88-96) without the rank-0 broadcast (avid.py:99-101): rows [row_begin, row_begin + rows) of bank
+ * `which` (0 video / 1 audio) <- L2-normalised N(0,1) rows.  Row r depends only on (seed, which, r) (Philox4x32-10 +
+ * Box-Muller), so every rank of a sharded run fills its own rows and replicated ranks fill identical banks. */
+int avid_bank_init(float* bank, int64_t row_begin, int64_t rows, uint64_t seed, int32_t which, void* stream);
 
 /* In-place row-wise x / max(||x||_2, 1e-12) on (rows, 128): init_memory (avid.py:92,95). */
 int avid_rows_l2_normalize(float* x, int64_t rows, void* stream);

@@ -38,7 +38,7 @@ def test_workspace_queries_are_host_only(lib):
 
 
 def test_invalid_arguments_report_einval(lib):
-    rc = lib.avid_bank_update(None, None, 0, 10, None, None, None, 4, 0.5, 0.5, None)
+    rc = lib.avid_bank_update(None, None, 0, 10, None, None, None, 4, 0, 0, 0.5, 0.5, None)
     assert rc == 1 and b"NULL" in lib.avid_last_error()
     s = _lib.ConvShape(1, 1, 8, 8, 3, 1, 8, 8, 64, 1, 3, 3, 1, 1, 1, 0, 1, 1)   # ci = 3 is not a padded channel count
     rc = lib.avid_conv_forward(C.byref(s), C.c_void_p(16), C.c_void_p(16), None, C.c_void_p(16), 0, None)

@@ -26,12 +26,21 @@ def _normalize(x):
     return x / x.pow(2).sum(1, keepdim=True).sqrt().clamp_min(1e-12)
 
 
+def _dense(t, tail):
+    """Packed per-rank views (W, B, ...) of the step's gathered buffer -> dense (W*B, ...) copies; dense tensors pass through."""
+    return t.reshape((-1,) + tuple(tail)) if t is not None else None
+
+
 def _fake_make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows=None, row_begin=0, row_end=None, neg_idx=None,
-                        seed=0, offset=0, positive_set=None, mean_batch=0, temperature=0.07, **out):
+                        seed=0, offset=0, positive_set=None, mean_batch=0, temperature=0.07, bad_index=None, **out):
     num_rows = bank_v.shape[0] if num_rows is None else num_rows
+    grouped = emb_v.dim() == 3
+    if grouped:       # the kernel addresses the rank records by stride; the stand-in copies them out
+        assert emb_v.stride(0) == emb_a.stride(0) == 2 * y.stride(0) and emb_v[0].is_contiguous() and y[0].is_contiguous()
+    emb_v, emb_a, y, neg_idx = _dense(emb_v, (128,)), _dense(emb_a, (128,)), _dense(y, ()), _dense(neg_idx, (num_neg,))
     return SimpleNamespace(emb=(emb_v, emb_a), y=y, bank=(bank_v, bank_a), keys=keys, K=num_neg, Z=Z, N=num_rows, row_begin=row_begin,
                            row_end=num_rows if row_end is None else row_end, neg_idx=neg_idx, mean_batch=mean_batch or emb_v.shape[0],
-                           T=temperature, out=out)
+                           T=temperature, out=out, grouped=grouped)
 
 
 def _partial_terms(a, with_loss=True):
@@ -65,9 +74,17 @@ def _fake_forward_backward(a, ws):
     sharded = a.row_begin != 0 or a.row_end != a.N
     lp = torch.stack([l.detach() for l in loss_part])
     if sharded:
-        a.out["grad_hat_v"].copy_(ehat[0].grad if ehat[0].grad is not None else torch.zeros_like(ehat[0]))
-        a.out["grad_hat_a"].copy_(ehat[1].grad if ehat[1].grad is not None else torch.zeros_like(ehat[1]))
-        a.out["loss_part"].copy_(lp)
+        gv = ehat[0].grad if ehat[0].grad is not None else torch.zeros_like(ehat[0])
+        ga = ehat[1].grad if ehat[1].grad is not None else torch.zeros_like(ehat[1])
+        if a.grouped:       # outputs are (W, B, 128) / (W, num_keys, B) views into the buffer that is reduce-scattered
+            W, Bq = a.out["grad_hat_v"].shape[:2]
+            a.out["grad_hat_v"].copy_(gv.view(W, Bq, 128))
+            a.out["grad_hat_a"].copy_(ga.view(W, Bq, 128))
+            a.out["loss_part"].copy_(lp.view(len(a.keys), W, Bq).permute(1, 0, 2))
+        else:
+            a.out["grad_hat_v"].copy_(gv)
+            a.out["grad_hat_a"].copy_(ga)
+            a.out["loss_part"].copy_(lp)
     else:
         a.out["grad_hat_v"], a.out["grad_hat_a"], a.out["loss_part"] = ehat[0].grad, ehat[1].grad, lp
         _fake_finalize(a, ws)
@@ -95,6 +112,7 @@ def _fake_partition_mean(a, key, out, ws):
 
 def _fake_bank_update(bank_v, bank_a, emb_v, emb_a, y, mom_v, mom_a, row_begin=0, row_end=None):
     row_end = row_begin + bank_v.shape[0] if row_end is None else row_end
+    emb_v, emb_a, y = _dense(emb_v, (128,)), _dense(emb_a, (128,)), _dense(y, ())
     for bank, emb, m in ((bank_v, emb_v, mom_v), (bank_a, emb_a, mom_a)):
         e = _normalize(emb)
         for i in range(y.shape[0]):
@@ -112,6 +130,11 @@ def _install_cpu_standins():
     ops.bank_update = _fake_bank_update
     ops.nce_workspace = lambda *a: torch.empty(1)
     ops.rows_l2_normalize_ = lambda x: x.copy_(_normalize(x))
+
+    def bank_init_(bank, row_begin, seed, which):      # rows are a function of (seed, which, row), like avid_bank_init
+        full = torch.randn(N, 128, generator=torch.Generator().manual_seed((seed + which) % (2 ** 63)))
+        return bank.copy_(_normalize(full[row_begin:row_begin + bank.shape[0]]))
+    ops.bank_init_ = bank_init_
 
 
 # ---------------------------------------------------------------------------------------------- worker

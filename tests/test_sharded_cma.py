@@ -71,6 +71,8 @@ def _worker(rank, world, port, backend, q):
             ops._CmaExactEngine, ops._CmaTensorCoreEngine = _FakeExact, _FakeTensorCore
             ops.rows_l2_normalize_ = lambda x: x.copy_(torch.nn.functional.normalize(x, dim=1))
             ops.nce_workspace = lambda *a: torch.empty(1)
+            ops.bank_init_ = lambda bank, row_begin, seed, which: bank.copy_(torch.nn.functional.normalize(torch.randn(
+                N, 128, generator=torch.Generator().manual_seed((seed + which) % (2 ** 63)))[row_begin:row_begin + bank.shape[0]], dim=1))
         from avid_cma_b200.criterions import avid_cma
         orig = avid_cma.AVIDSimilarityPositiveExpansion._candidate_shards
 
