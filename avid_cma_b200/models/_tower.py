@@ -10,7 +10,7 @@ _MATH = {'fp32': ops.MATH_FP32, 'bf16x3': ops.MATH_BF16X3, 'bf16': ops.MATH_BF16
 
 
 def default_math():
-    return _MATH[os.environ.get('AVID_MATH', 'fp32')]
+    return _MATH[os.environ.get('AVID_MATH', 'bf16x3')]
 
 
 def prepare_tower_filters(tower):

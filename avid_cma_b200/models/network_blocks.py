@@ -156,6 +156,7 @@ class ConvBNReLU:
         else:
             z = op.forward(x, addend)
             st = ops.BNState(conv.out_channels, z.device)
+            st.frozen = True
             st.invstd.copy_(torch.rsqrt(bn.running_var + bn.eps))
             st.mean.copy_(bn.running_mean)
             st.scale.copy_(bn.weight.detach() * st.invstd)

@@ -655,9 +655,10 @@ def nhwc_to_nchw(x):
 
 class BNState:
     """Per-call buffers of one train-mode BatchNorm: statistics, saved mean/invstd, folded scale/shift."""
-    __slots__ = ("stats", "mean", "invstd", "scale", "shift")
+    __slots__ = ("stats", "mean", "invstd", "scale", "shift", "frozen")
 
     def __init__(self, c, device):
+        self.frozen = False          # True: the layer ran with running statistics (model.eval()): its backward is affine-only
         self.stats = _zeros((2, c), torch.float64, device)
         buf = torch.empty(4, c, dtype=torch.float32, device=device)
         self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
@@ -745,10 +746,20 @@ def bn_relu_backward_act(x, dy, s, gamma, beta, want_f32, want_planes, x3, dx=No
     L = _lib.lib()
     if not have_sums:
         check(L.avid_bn_relu_backward_reduce(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), rows, c, _p(sums, torch.float64), _stream()))
+    sums, dgamma, dbeta = _frozen_sums(s, sums, dgamma, dbeta)
     check(L.avid_bn_relu_backward_apply_ex(_p(x), _p(dy), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta), _p(sums, torch.float64), rows, c,
                                            _p(dx, optional=True), _p(hi, torch.bfloat16, optional=True), _p(lo, torch.bfloat16, optional=True),
-                                           _p(dgamma), _p(dbeta), _stream()))
+                                           _p(dgamma) if not s.frozen else None, _p(dbeta) if not s.frozen else None, _stream()))
     return Act(dx if want_f32 else None, hi, lo), dgamma, dbeta
+
+
+def _frozen_sums(s, sums, dgamma, dbeta):
+    """A layer that ran with its RUNNING statistics (model.eval(), frozen-BatchNorm fine-tuning) is a per-channel affine map: its
+    input gradient is dy * relu' * gamma * invstd without the batch-statistic terms, while dgamma / dbeta are still the reduced
+    sums.  The apply kernels compute k * (g - sums[0]/n - xhat * sums[1]/n): hand them zero sums."""
+    if not s.frozen:
+        return sums, dgamma, dbeta
+    return torch.zeros_like(sums), sums[1].float(), sums[0].float()
 
 
 @_timed("bn_pool_fwd")
@@ -780,9 +791,10 @@ def bn_relu_maxpool_backward_act(z, pooled, argmax, dyp, s, gamma, beta, want_f3
     L = _lib.lib()
     common = (_p(z), _p(argmax, torch.uint8), _p(dyp), _p(s.mean), _p(s.invstd), _p(gamma), _p(beta))
     check(L.avid_bn_relu_maxpool_backward_reduce(_p(z), _p(pooled), *common[1:], n * t, h, w, c, ho, wo, _p(sums, torch.float64), _stream()))
+    sums, dgamma, dbeta = _frozen_sums(s, sums, dgamma, dbeta)
     check(L.avid_bn_relu_maxpool_backward_apply(*common, _p(sums, torch.float64), n * t, h, w, c, ho, wo, _p(dz, optional=True),
                                                 _p(hi, torch.bfloat16, optional=True), _p(lo, torch.bfloat16, optional=True),
-                                                _p(dgamma), _p(dbeta), _stream()))
+                                                _p(dgamma) if not s.frozen else None, _p(dbeta) if not s.frozen else None, _stream()))
     return Act(dz, hi, lo), dgamma, dbeta
 
 

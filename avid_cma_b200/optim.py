@@ -26,7 +26,8 @@ class Adam(torch.optim.Optimizer):
                     st['step'] = 0
                     st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st['step'] += 1
+                # torch.optim.Adam state_dicts store `step` as a tensor: normalise to a python int (dict key, kernel argument)
+                st['step'] = int(st['step']) + 1
                 by_step.setdefault(st['step'], []).append((p.data, p.grad.contiguous(), st['exp_avg'], st['exp_avg_sq']))
             for step, items in by_step.items():      # normally one entry: every parameter has taken the same number of steps
                 ps, gs, ms, vs = zip(*items)

@@ -311,6 +311,36 @@ def test_towers_eval_mode_and_return_embs():
     assert _rel(ve, rv) < 1e-4 and _rel(ae, ra) < 1e-4
 
 
+@pytest.mark.parametrize("math", ["fp32", "bf16x3"])
+def test_eval_mode_backward_matches_frozen_batchnorm(math):
+    """model.eval() with gradients enabled (frozen-BatchNorm fine-tuning): BatchNorm is a per-channel affine map, so the input
+    gradient has no batch-statistic terms while dgamma / dbeta are still the reduced sums (nn.BatchNorm in eval mode)."""
+    model = _load_model(2, math).eval()
+    sd = {k: v.detach().cpu().double().clone() for k, v in model.state_dict().items()}
+    # running statistics away from (0, 1) so that a train-mode backward would be visibly different
+    g = torch.Generator().manual_seed(5)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g, dtype=torch.float64)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g, dtype=torch.float64)
+    model.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
+    keys = towers.param_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    video, audio = synth.clips(2, 4, 32, 11), synth.spectrograms(2, 40, 33, 11)
+    wv, wa = synth.normal((2, 128), 11, "wv").double(), synth.normal((2, 128), 11, "wa").double()
+    rv, ra = towers.av_forward(video.double(), audio.double(), sd, training=False)
+    ((rv * wv).sum() + (ra * wa).sum()).backward()
+    ve, ae = model(video.to(DEV), audio.to(DEV))
+    ((ve * wv.float().to(DEV)).sum() + (ae * wa.float().to(DEV)).sum()).backward()
+    tol = 1e-4 if math == "fp32" else 2e-3
+    assert _rel(ve, rv) < tol and _rel(ae, ra) < tol
+    params = dict(model.named_parameters())
+    worst = max(_rel(params[k].grad, sd[k].grad) for k in keys)
+    assert worst < (1e-3 if math == "fp32" else 2e-2), worst
+
+
 def test_batched_filter_layout_conversions_equal_single_launches():
     """avid_filter_to_planes_multi / avid_filter_from_tapmajor_multi (one launch per tower) == the per-filter entry points."""
     from avid_cma_b200 import ops
