@@ -34,7 +34,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"],
+                    help="ours: this package; reference: the reference's CPU path (oracle port) on the host cores; torch_gpu: DIAGNOSTIC arm, the "
+                         "same reference call sequence through stock torch (cuDNN / cuBLAS / ATen) on cuda:0, TF32 off and on")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--frames", type=int, default=8)
@@ -44,6 +46,9 @@ def parse():
     ap.add_argument("--math", default=os.environ.get("AVID_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch GPU leg (gpu_library_baseline) of the N=1 line")
+    ap.add_argument("--no-subrecords", action="store_true", help="N > 1: skip the config-3 (2 M-row sharded bank) and config-4 (sharded CMA) sub-records")
+    ap.add_argument("--sub-steps", type=int, default=8, help="timed steps of each N > 1 sub-record (after 3 warm-up steps)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end timed region")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event table of the timed region (mean over steps, launch order) to this file")
     ap.add_argument("--bank-mode", default="auto", choices=["auto", "replicated", "sharded"],
@@ -85,10 +90,70 @@ def run_reference(a):
     if rank != 0:
         return
     cb, sec = cpu_reference(a, a.steps, a.warmup, a.cpu_sample_batch)
+    cfg = config_of(a, a.gpus)
+    # this arm is ONE host process stepping a bounded sample of the workload: say so in ITS config (same clip / spectrogram shape,
+    # bank, K and optimizer; clips/s on the CPU is batch-independent to a few per cent)
+    cfg.update({"global_batch": a.cpu_sample_batch, "batch_per_gpu": a.cpu_sample_batch, "parallelism": "1 host process, %d threads" % cb["cores"],
+                "bank_layout": "single", "math": "f32 (torch CPU)",
+                "sample": "%d-clip steps of the workload (the GPU arm steps %d clips per GPU)" % (a.cpu_sample_batch, a.batch)})
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_of(a, a.gpus), "cpu_baseline": cb,
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ stock-torch GPU arm (diagnostic)
+def torch_gpu_baseline(a, steps, warmup, device):
+    """the reference's training step through stock torch 2.11 on the same B200 -- cuDNN conv3d / conv2d,
+    cuBLAS bmm / Linear, the ~150 small ATen launches of the criterion, host-drawn negatives copied each step, torch.optim.Adam --
+    with cudnn.benchmark on (main-avid.py:121), TF32 off (fp32 truth) and on (torch's default for convolutions).  The oracle port
+    is that call sequence as functional torch; here it only runs on `device`.  DIAGNOSTIC: not the driver's reference arm."""
+    from oracle import synth
+    from oracle.step import OracleTrainer
+    out = {}
+    B = a.batch
+    g = torch.Generator().manual_seed(0)
+    video = torch.randn(B, 3, a.frames, a.size, a.size, generator=g).to(device)
+    audio = torch.randn(B, 1, a.spec[0], a.spec[1], generator=g).to(device)
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            tr = OracleTrainer(a.bank, num_negatives=a.negatives, seed=0, device=device)
+            ys = [synth.instance_ids(B, a.bank, seed=i).to(device) for i in range(warmup + steps)]
+            for i in range(warmup):
+                tr.step(video, audio, ys[i])
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                tr.step(video, audio, ys[warmup + i])
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms = e0.elapsed_time(e1) / steps
+            out["tf32_on" if tf32 else "fp32"] = {"clips_per_s": B / (ms * 1e-3), "ms_per_step": ms}
+            del tr
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out.update({"unit": UNIT, "steps": steps, "warmup": warmup, "batch": B,
+                "what": "the reference's step (oracle port = its torch call sequence) on stock torch %s CUDA: cuDNN / cuBLAS / ATen, "
+                        "cudnn.benchmark=True, inputs resident, loss read back every step" % torch.__version__})
+    return out
+
+
+def run_torch_gpu(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    res = torch_gpu_baseline(a, a.steps, a.warmup, dev)
+    line = {"impl": "torch_gpu", "metric": METRIC, "value": res["fp32"]["clips_per_s"], "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": res["fp32"]["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 off)",
+            "data": "synthetic", "config": config_of(a, 1), "gpu_library_baseline": res}
     print(json.dumps(line), flush=True)
 
 
@@ -123,6 +188,150 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _max_over_ranks(vals, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def parity_check(net, video, audio, a, world, rank, local, dev):
+    """N > 1, before anything is timed: ONE gathered batch through the row-sharded criterion (the layout this run times) and through
+    the replicated one (the reference's layout, avid.py:103-129), same Philox stream, same banks (rows are a function of the shared
+    seed).  Loss, d loss / d embeddings and the updated bank rows must agree to fp32 summation order; the run FAILS above 1e-4."""
+    import torch.distributed as dist
+    from avid_cma_b200.criterions import AVID
+    crits = {}
+    for mode in ("sharded", "replicated"):
+        os.environ["AVID_SHARD_BANK"] = "1" if mode == "sharded" else "0"
+        crits[mode] = AVID(num_data=a.bank, embedding_dim=128, num_negatives=a.negatives, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=local)
+    assert crits["sharded"].nce_average.sharded and not crits["replicated"].nce_average.sharded
+    with torch.no_grad():
+        ve, ae = net(video, audio)
+    y = torch.randperm(a.bank, generator=torch.Generator().manual_seed(99))[rank * a.batch:(rank + 1) * a.batch].to(dev)
+    res = {}
+    for mode, crit in crits.items():
+        ev, ea = ve.detach().clone().requires_grad_(True), ae.detach().clone().requires_grad_(True)
+        loss, _ = crit(ev, ea, y)
+        loss.backward()
+        res[mode] = (loss.detach().double(), ev.grad.double(), ea.grad.double())
+    ls, lr = res["sharded"][0], res["replicated"][0]
+    loss_rel = float((ls - lr).abs() / lr.abs())
+    grad_rel = max(float((res["sharded"][i] - res["replicated"][i]).norm() / res["replicated"][i].norm()) for i in (1, 2))
+    bs, br = crits["sharded"].nce_average, crits["replicated"].nce_average
+    bank_rel = max(float((getattr(bs, n).double() - getattr(br, n)[bs.row_begin:bs.row_end].double()).norm() /
+                         getattr(br, n)[bs.row_begin:bs.row_end].double().norm()) for n in ("view1_mem", "view2_mem"))
+    z_rel = abs(float(crits["sharded"].criterion.avg_exp_score) - float(crits["replicated"].criterion.avg_exp_score)) / float(crits["replicated"].criterion.avg_exp_score)
+    loss_rel, grad_rel, bank_rel, z_rel = _max_over_ranks([loss_rel, grad_rel, bank_rel, z_rel], dev, world)
+    out = {"loss_rel": loss_rel, "grad_rel": grad_rel, "bank_rel": bank_rel, "z_rel": z_rel, "tolerance": 1e-4,
+           "what": "step 0 of one gathered batch: row-sharded criterion vs replicated criterion (max over ranks), in-kernel Philox negatives"}
+    del crits
+    torch.cuda.empty_cache()
+    if not max(loss_rel, grad_rel, bank_rel, z_rel) <= 1e-4:
+        raise RuntimeError("sharded criterion != replicated criterion: %s" % json.dumps(out))
+    os.environ["AVID_SHARD_BANK"] = "0" if a.bank_mode == "replicated" else "1"
+    return out
+
+
+def sub_record(name, crit, net, opt, resident, a, world, rank, dev, rows):
+    """3 warm-up + a.sub_steps timed training steps of the SAME towers with another criterion (BASELINE configs 3 and 4)."""
+    import torch.distributed as dist
+    from avid_cma_b200 import ops
+    B = a.batch
+    perm = torch.randperm(rows, generator=torch.Generator().manual_seed(11))
+    n_total = 3 + a.sub_steps
+    ys = [perm[(i * world + rank) * B % (rows - B):][:B].contiguous().to(dev) for i in range(n_total)]
+
+    def step(i):
+        ve, ae = net(*resident[i % len(resident)])
+        loss, _ = crit(ve, ae, ys[i])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(3):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ops.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3, n_total):
+        loss = step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    prof = ops.profile_end()
+    ms, = _max_over_ranks([e0.elapsed_time(e1)], dev, world)
+    nce = [(w, d) for n_, w, d in prof if n_ == "nce_fused"]
+    rec = {"clips_per_s": B * world * a.sub_steps / (ms * 1e-3), "ms_per_step": ms / a.sub_steps, "steps": a.sub_steps, "warmup": 3,
+           "last_loss": float(loss)}
+    if nce:
+        rec["nce_GBps_per_gpu"] = sum(w for w, _ in nce) / (sum(d for _, d in nce) * 1e-3) / 1e9
+        rec["nce_us_per_launch"] = 1e3 * sum(d for _, d in nce) / len(nce)
+        rec["nce_algorithmic_bytes_per_launch"] = nce[0][0]
+    return rec
+
+
+def sub_records(net, opt, resident, a, world, rank, local, dev):
+    """BASELINE.json configs 3 (Audioset-shape 2 M-row bank, row-sharded) and 4 (AVID+CMA, 240 k bank, top-32 consensus mining
+    sharded over the ranks) on the towers this run has just timed."""
+    import torch.distributed as dist
+    from avid_cma_b200.criterions import AVID, AVID_CMA
+    os.environ["AVID_SHARD_BANK"] = "1"
+    out = {}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- config 3: Cross-N1024 AVID, 2 M-entry sharded bank (configs/main/avid/audioset/Cross-N1024.yaml: num_data 1 784 108)
+    N3 = 2000000
+    sync()
+    t0 = time.perf_counter()
+    crit3 = AVID(num_data=N3, embedding_dim=128, num_negatives=a.negatives, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=local)
+    sync()
+    init_s, = _max_over_ranks([time.perf_counter() - t0], dev, world)
+    rec = sub_record("config3", crit3, net, opt, resident, a, world, rank, dev, N3)
+    rec.update({"workload": "Cross-N1024 AVID, 2M-entry sharded memory bank (Audioset-shape), batch=64/GPU, NCCL packed all-gather + reduce-scatter",
+                "bank_rows": N3, "rows_per_gpu": crit3.nce_average.rows_per_rank, "bank_init_s": init_s,
+                "bank_init": "per-rank seeded rows (avid_bank_init), no (N,128) broadcast"})
+    out["config3"] = rec
+    del crit3
+    torch.cuda.empty_cache()
+
+    # ---- config 4: InstX-N1024-PosW-N64-Top32 AVID+CMA, 240 k bank (configs/main/avid-cma/kinetics/InstX-N1024-PosW-N64-Top32.yaml:47-62)
+    N4 = a.bank
+    sync()
+    t0 = time.perf_counter()
+    crit4 = AVID_CMA(num_data=N4, embedding_dim=128, num_negatives=a.negatives, num_negatives_within=64, momentum=0.5,
+                     xModalInstCoeff=1., wModalInstCoeff=0., xModalPosCoeff=0., wModalPosCoeff=1.,
+                     sampling_args={"type": "consensus", "pos_k": 32}, resample_freq=-1, device=local)
+    sync()
+    build_s, = _max_over_ranks([time.perf_counter() - t0], dev, world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    crit4.nce_average.find_correspondences()
+    e1.record()
+    sync()
+    mining_ms, = _max_over_ranks([e0.elapsed_time(e1)], dev, world)
+    rec = sub_record("config4", crit4, net, opt, resident, a, world, rank, dev, N4)
+    rec.update({"workload": "InstX-N1024-PosW-N64-Top32 AVID+CMA, 240k bank, CMA top-32 consensus positive expansion, mining sharded over the ranks",
+                "bank_rows": N4, "mining_ms": mining_ms, "mining_TFLOPs": 2 * 2.0 * N4 * N4 * 128 / (mining_ms * 1e-3) / 1e12,
+                "criterion_build_s": build_s})
+    out["config4"] = rec
+    del crit4
+    torch.cuda.empty_cache()
+    os.environ["AVID_SHARD_BANK"] = "0" if a.bank_mode == "replicated" else "1"
+    return out
+
+
 def run_ours(a):
     import torch.distributed as dist
     from avid_cma_b200 import models, ops, optim
@@ -168,6 +377,10 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    parity = None
+    if world > 1 and a.bank_mode != "replicated":
+        parity = parity_check(net, resident[0][0], resident[0][1], a, world, rank, local, dev)
 
     it = 0
     for _ in range(a.warmup):
@@ -230,6 +443,9 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    subs = None
+    if world > 1 and not a.no_subrecords and a.bank_mode != "replicated":
+        subs = sub_records(net, opt, resident, a, world, rank, local, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,6 +522,17 @@ def run_ours(a):
             "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches, "roofline": roofline, "last_loss": last_loss,
             "step_tflops": clips * STEP_GFLOP_PER_CLIP * 1e9 / (ms * 1e-3) / 1e12 / world}
+    if parity is not None:
+        line["parity_check"] = parity
+    if subs is not None:
+        line.update(subs)
+    if world == 1 and not a.no_gpu_baseline:
+        try:   # the reference's step through stock torch on this very GPU, measured in the same run (diagnostic)
+            line["gpu_library_baseline"] = torch_gpu_baseline(a, 5, 3, dev)
+            line["gpu_library_baseline"]["ours_over_fp32"] = line["value"] / line["gpu_library_baseline"]["fp32"]["clips_per_s"]
+            line["gpu_library_baseline"]["ours_over_tf32"] = line["value"] / line["gpu_library_baseline"]["tf32_on"]["clips_per_s"]
+        except Exception as e:   # noqa: BLE001 -- a diagnostic leg must not take the headline line down
+            line["gpu_library_baseline"] = {"error": repr(e)[:300]}
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_reference(a, 6, 1, a.cpu_sample_batch)
         line["cpu_baseline"] = cb
@@ -318,5 +545,7 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
