@@ -106,33 +106,28 @@ __device__ __forceinline__ void load_normalized(const float* emb, int b, int l8,
     for (int j = 0; j < 4; ++j) out[j] = make_float4(out[j].x * inv, out[j].y * inv, out[j].z * inv, out[j].w * inv);
 }
 
-// ---- bank rows reach the SM as bulk async copies (cp.async.bulk, 512 B per row) into a per-warp shared-memory ring ----
+// ---- bank rows reach the SM as asynchronous copies (cp.async, 16 B per lane = one 512-byte row per warp instruction) into a
+// per-warp shared-memory ring ----
 // The gather is a latency problem, not a bandwidth one (K = 1024: 131 k rows of 512 B per step, ~4 dependent DRAM round trips
 // per warp when the rows in flight are bounded by registers).  With the rows landing in shared memory the data in flight per SM
 // is the ring size (3 CTAs x 4 warps x 16 KB = 192 KB, far above the ~44 KB bandwidth-delay product per SM), independent of
 // registers and occupancy; the arithmetic then reads the rows with conflict-free 128-byte group loads.
+// Measured (round 2): per-row cp.async.bulk (TMA engine) copies instead are request-rate bound -- ~1 request per ~35 cycles and
+// SM, i.e. ~15 B/clk/SM for 512-byte rows: K = 1024 took 49 us against 39 us for the register version; LDGSTS moves 512 B per
+// warp instruction at the LSU rate.
 constexpr int kStageItems = 8;                                  // one pass of the quad loop: 2 quads x 4 groups
 constexpr int kRowBytes = kD * 4;                               // 512
 constexpr int kStageBytes = kStageItems * 2 * kRowBytes;        // [item][bank][128] floats = 8 KB
 constexpr int kRing = 2;                                        // stages in flight per warp
-constexpr int kGatherSmem = kGatherWarps * kRing * kStageBytes + kGatherWarps * kRing * 8;
+constexpr int kGatherSmem = kGatherWarps * kRing * kStageBytes;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_row(void* dst, const void* src, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
-                 "n"(kRowBytes), "r"(smem_addr(bar))
-                 : "memory");
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
-            : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct ItemDesc {          // what lane l knows about item l of a 32-item chunk
     int kind;              // -1 nothing to score here, 0 negative kk, 1 self, 2 positive-set entry kk
@@ -153,13 +148,6 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     const int64_t* negs = p.neg_idx ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg_idx) + in_off) + (size_t)bl * p.K : nullptr;
 
     float* ring = reinterpret_cast<float*>(nce_smem + (size_t)warp * kRing * kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(nce_smem + (size_t)kGatherWarps * kRing * kStageBytes) + warp * kRing;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kRing; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
 
     float4 e_ctx[2][4];
     load_normalized(emb0, bl, l8, e_ctx[0]);
@@ -186,7 +174,6 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     float loss_acc[2] = {0.f, 0.f};
     const int key_passes = (p.num_keys + 3) >> 2;
     const int u_sel = l8 >> 2;
-    const uint32_t row_bytes = (p.bank_used[0] ? kRowBytes : 0) + (p.bank_used[1] ? kRowBytes : 0);
 
     // lane l describes item c0 + l: kind, slot, bank row (Philox draw or the injected index)
     auto describe = [&](int c0) {
@@ -207,18 +194,21 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
         if (!(d.idx >= p.row_begin && d.idx < p.row_end)) d.kind = -1;      // rows another shard holds are scored there
         return d;
     };
-    // the 8 lanes describing stage `st` of a chunk start the copies of their rows into ring slot `slot`
+    // stage `st` of a chunk (items 8 st .. 8 st + 7): every lane copies its 16 bytes of each row the stage needs into ring slot
+    // `slot`; one commit group per stage and lane (an empty group completes at once)
     auto issue = [&](const ItemDesc& d, int st, int slot) {
-        const bool mine = (lane >> 3) == st && d.kind >= 0;
-        const uint32_t n = __popc(__ballot_sync(0xffffffffu, mine));
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bars[slot])), "r"(n * row_bytes) : "memory");
-        __syncwarp();
-        if (mine) {
-            const size_t off = (size_t)(d.idx - p.row_begin) * kD;
-            float* dst = ring + (size_t)slot * (kStageBytes / 4) + (lane & 7) * (2 * kD);
-            if (p.bank_used[0]) bulk_row(dst, p.bank[0] + off, &bars[slot]);
-            if (p.bank_used[1]) bulk_row(dst + kD, p.bank[1] + off, &bars[slot]);
+        float* dst = ring + (size_t)slot * (kStageBytes / 4) + lane * 4;
+#pragma unroll
+        for (int i = 0; i < kStageItems; ++i) {
+            const int64_t idx_i = __shfl_sync(0xffffffffu, d.idx, st * 8 + i);
+            const int kind_i = __shfl_sync(0xffffffffu, d.kind, st * 8 + i);
+            if (kind_i >= 0) {
+                const size_t off = (size_t)(idx_i - p.row_begin) * kD + lane * 4;
+                if (p.bank_used[0]) cp_async16(dst + i * (2 * kD), p.bank[0] + off);
+                if (p.bank_used[1]) cp_async16(dst + i * (2 * kD) + kD, p.bank[1] + off);
+            }
         }
+        cp_async_commit();
     };
 
     const int first = warp * 32;
@@ -236,7 +226,9 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
 #pragma unroll
         for (int st = 0; st < 4; ++st) {
             const int t = ci * 4 + st, slot = t % kRing;
-            bar_wait(&bars[slot], (uint32_t)((t / kRing) & 1));
+            // groups complete in order: all but the kRing - 1 youngest are done (the tail of the stream commits empty groups)
+            cp_async_wait<kRing - 1>();
+            __syncwarp();
             const float* stage = ring + (size_t)slot * (kStageBytes / 4);
             float4 rv[2][4], ra[2][4];
             int kind_u[2], kk_u[2];
@@ -267,6 +259,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
             __syncwarp();
             if (st + kRing < 4) issue(cur, st + kRing, slot);
             else if (has_next) issue(nxt, st + kRing - 4, slot);
+            else cp_async_commit();
             // d[u][bank][ctx] of this group's two rows, on all 8 lanes of the group
             float d[2][2][2];
 #pragma unroll

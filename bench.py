@@ -351,7 +351,10 @@ def run_ours(a):
     model = models.av_wrapper('R2Plus1D', {'depth': 18}, 'Conv2D', {'depth': 10}, proj_dim=[512, 512, 128]).to(dev).train()
     os.environ["AVID_SHARD_BANK"] = "0" if a.bank_mode == "replicated" else "1"
     crit = AVID(num_data=a.bank, embedding_dim=model.out_dim, num_negatives=a.negatives, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=local)
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    # broadcast_buffers=False: the per-forward broadcast of rank 0's 126 BatchNorm buffers only matters for what a checkpoint holds,
+    # and rank 0 writes the checkpoint either way (utils/main_utils.py CheckpointManager)
+    ddp = world > 1 and os.environ.get("AVID_BENCH_NO_DDP", "0") != "1"       # AVID_BENCH_NO_DDP=1: diagnostic only (no gradient sync)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True) if ddp else model
     opt = optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
 
     B = a.batch

@@ -91,8 +91,17 @@ def _worker(rank, world, port, backend, q):
         bank.find_correspondences()
         want = oc.cma_topk(full_v.double(), full_a.double(), POS_K, "consensus")
         got = bank.positive_set.cpu()
-        mism = float((got != want).any(1).float().mean())
-        q.put((rank, mism, len(walks), None))
+        # index outputs must be identical; a differing row is only admissible as a proven tie at the k-th boundary (fp32 kernels vs
+        # the fp64 oracle): every index of the symmetric difference has an exact similarity within 1e-6 of the boundary value
+        unproven = 0
+        for r in torch.nonzero((got != want).any(1)).flatten().tolist():
+            sim = torch.minimum(full_v.double() @ full_v[r].double(), full_a.double() @ full_a[r].double())
+            boundary = sim.sort().values[-(POS_K + 1)]
+            diff = set(got[r].tolist()) ^ set(want[r].tolist())
+            if cuda and all(0 <= j < N and abs(float(sim[j] - boundary)) < 1e-6 for j in diff):
+                continue
+            unproven += 1
+        q.put((rank, unproven, len(walks), None))
     except Exception:   # noqa: BLE001
         import traceback
         q.put((rank, None, None, traceback.format_exc()))
@@ -114,7 +123,7 @@ def _run(backend, expect_walks, world=2):
         p.join(timeout=60)
     for rank, mism, walks, err in results:
         assert err is None, f"rank {rank}:\n{err}"
-        assert mism < 0.01, (rank, mism)                         # fp32 / fp64 ties at the k-th boundary only
+        assert mism == 0, (rank, mism)                           # rows that differ from the oracle without being a proven tie
         if expect_walks is not None:
             assert walks == expect_walks, (rank, walks)          # BOTH ranks walked the shard stream twice (one rank had failures)
 
