@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--math", default=os.environ.get("AVID_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-experiment", action="store_true",
+                    help="diagnostic: also time K replays of ONE training step captured in a CUDA graph (negatives / Adam step count frozen: timing only)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch GPU leg (gpu_library_baseline) of the N=1 line")
     ap.add_argument("--no-subrecords", action="store_true", help="N > 1: skip the config-3 (2 M-row sharded bank) and config-4 (sharded CMA) sub-records")
     ap.add_argument("--sub-steps", type=int, default=8, help="timed steps of each N > 1 sub-record (after 3 warm-up steps)")
@@ -405,6 +407,31 @@ def run_ours(a):
     prof = ops.profile_end()
     clocks = sampler.summary()
 
+    graph_ms = None
+    if a.graph_experiment and world == 1:
+        sv, sa, sy = resident[0][0].clone(), resident[0][1].clone(), ys_dev[0].clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step(sv, sa, sy)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step(sv, sa, sy)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eg0.record()
+        for _ in range(a.steps):
+            g.replay()
+        eg1.record()
+        torch.cuda.synchronize()
+        graph_ms = eg0.elapsed_time(eg1) / a.steps
+        del g
+
     # ---- timed region 2: end to end, pinned host buffers -> H2D each step (side stream, one step ahead, like a prefetching
     #      loader with non_blocking copies: main-avid.py:161-163), loss.item() each step ----
     e2e_steps = 0 if a.skip_e2e else a.steps
@@ -525,6 +552,9 @@ def run_ours(a):
             "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches, "roofline": roofline, "last_loss": last_loss,
             "step_tflops": clips * STEP_GFLOP_PER_CLIP * 1e9 / (ms * 1e-3) / 1e12 / world}
+    if graph_ms is not None:
+        line["graph_experiment"] = {"ms_per_step": graph_ms, "clips_per_s": B / (graph_ms * 1e-3),
+                                    "note": "one captured step replayed (frozen negatives / Adam step count): launch-gap diagnostic, not a bench value"}
     if parity is not None:
         line["parity_check"] = parity
     if subs is not None:
