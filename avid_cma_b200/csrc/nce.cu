@@ -14,6 +14,7 @@
 // Kernel 2  nce_reduce_finalize_kernel  grid (B) x 256 threads: the same tail as a separate launch, for the sharded
 //           protocol (avid_nce_finalize runs after the all-reduce of the partials).
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace avid {
@@ -106,37 +107,14 @@ __device__ __forceinline__ void load_normalized(const float* emb, int b, int l8,
     for (int j = 0; j < 4; ++j) out[j] = make_float4(out[j].x * inv, out[j].y * inv, out[j].z * inv, out[j].w * inv);
 }
 
-// ---- bank rows reach the SM as asynchronous copies (cp.async, 16 B per lane = one 512-byte row per warp instruction) into a
-// per-warp shared-memory ring ----
-// The gather is a latency problem, not a bandwidth one (K = 1024: 131 k rows of 512 B per step, ~4 dependent DRAM round trips
-// per warp when the rows in flight are bounded by registers).  With the rows landing in shared memory the data in flight per SM
-// is the ring size (3 CTAs x 4 warps x 16 KB = 192 KB, far above the ~44 KB bandwidth-delay product per SM), independent of
-// registers and occupancy; the arithmetic then reads the rows with conflict-free 128-byte group loads.
-// Measured (round 2): per-row cp.async.bulk (TMA engine) copies instead are request-rate bound -- ~1 request per ~35 cycles and
-// SM, i.e. ~15 B/clk/SM for 512-byte rows: K = 1024 took 49 us against 39 us for the register version; LDGSTS moves 512 B per
-// warp instruction at the LSU rate.
-constexpr int kStageItems = 8;                                  // one pass of the quad loop: 2 quads x 4 groups
-constexpr int kRowBytes = kD * 4;                               // 512
-constexpr int kStageBytes = kStageItems * 2 * kRowBytes;        // [item][bank][128] floats = 8 KB
-constexpr int kRing = 2;                                        // stages in flight per warp
-constexpr int kGatherSmem = kGatherWarps * kRing * kStageBytes;
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct ItemDesc {          // what lane l knows about item l of a 32-item chunk
-    int kind;              // -1 nothing to score here, 0 negative kk, 1 self, 2 positive-set entry kk
-    int kk;
-    int64_t idx;
-};
+// a warp keeps 2 row quads (4 rows each) per bank in flight: 2 x 4 rows x 2 banks x 512 B = 8 KB.
+// Measured and dropped (round 2): landing the rows in a per-warp shared-memory ring instead of registers -- with per-row
+// cp.async.bulk copies (request-rate bound: ~35 cycles per 512-byte request and SM; K = 1024: 49 us vs 39 us) and with cp.async
+// 16 B per lane (58 us; K = 16384: 0.60 instead of 0.77 of the HBM peak): the extra shared-memory hop costs more than the deeper
+// queue gives, because the kernel is bound by its few dependent round trips, not by bytes in flight.
+constexpr int kGatherSmem = 0;
 
 __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {
-    extern __shared__ __align__(128) uint8_t nce_smem[];
     const int b = blockIdx.x, split = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, l8 = lane & 7;
@@ -146,8 +124,6 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     const float* emb0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[0]) + in_off);
     const float* emb1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[1]) + in_off);
     const int64_t* negs = p.neg_idx ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg_idx) + in_off) + (size_t)bl * p.K : nullptr;
-
-    float* ring = reinterpret_cast<float*>(nce_smem + (size_t)warp * kRing * kStageBytes);
 
     float4 e_ctx[2][4];
     load_normalized(emb0, bl, l8, e_ctx[0]);
@@ -175,91 +151,73 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     const int key_passes = (p.num_keys + 3) >> 2;
     const int u_sel = l8 >> 2;
 
-    // lane l describes item c0 + l: kind, slot, bank row (Philox draw or the injected index)
-    auto describe = [&](int c0) {
-        ItemDesc d{-1, 0, -1};
+    // lane l describes item c0 + l of a 32-item chunk (kind 0 = negative k, 1 = self, 2 = positive-set entry) and, as soon as the
+    // bank row is known, asks L2 for its 2 x 512 bytes: the register loads of the quad loop below then find the rows in L2 (one
+    // DRAM round trip per chunk instead of one per pass of the quad loop); the next chunk is described and prefetched before the
+    // current one is scored.
+    auto describe = [&](int c0, int& kind, int& kk, int64_t& idx) {
         const int item = c0 + lane;
+        kind = -1;  kk = 0;  idx = -1;
         if (item < n_items) {
             if (item < npos) {
-                d.kind = item == 0 ? 1 : 2;
-                d.kk = item - 1;
-                d.idx = item == 0 ? y : (int64_t)pos_row[item - 1];
+                kind = item == 0 ? 1 : 2;
+                kk = item - 1;
+                idx = item == 0 ? y : (int64_t)pos_row[item - 1];
             } else {
-                d.kind = 0;
-                d.kk = k_begin + (item - npos);
-                d.idx = negs ? negs[d.kk] : draw_negative(p.seed, p.offset, b, d.kk, p.K, p.N, y, pos_row, p.pos_k);
-                if (p.neg_idx_out) p.neg_idx_out[(size_t)b * p.K + d.kk] = d.idx;
+                kind = 0;
+                kk = k_begin + (item - npos);
+                idx = negs ? negs[kk] : draw_negative(p.seed, p.offset, b, kk, p.K, p.N, y, pos_row, p.pos_k);
+                if (p.neg_idx_out) p.neg_idx_out[(size_t)b * p.K + kk] = idx;
             }
         }
-        if (!(d.idx >= p.row_begin && d.idx < p.row_end)) d.kind = -1;      // rows another shard holds are scored there
-        return d;
-    };
-    // stage `st` of a chunk (items 8 st .. 8 st + 7): every lane copies its 16 bytes of each row the stage needs into ring slot
-    // `slot`; one commit group per stage and lane (an empty group completes at once)
-    auto issue = [&](const ItemDesc& d, int st, int slot) {
-        float* dst = ring + (size_t)slot * (kStageBytes / 4) + lane * 4;
+        if (!(idx >= p.row_begin && idx < p.row_end)) kind = -1;      // rows another shard holds are scored there
+        if (kind >= 0) {
+            const size_t off = (size_t)(idx - p.row_begin) * kD;
 #pragma unroll
-        for (int i = 0; i < kStageItems; ++i) {
-            const int64_t idx_i = __shfl_sync(0xffffffffu, d.idx, st * 8 + i);
-            const int kind_i = __shfl_sync(0xffffffffu, d.kind, st * 8 + i);
-            if (kind_i >= 0) {
-                const size_t off = (size_t)(idx_i - p.row_begin) * kD + lane * 4;
-                if (p.bank_used[0]) cp_async16(dst + i * (2 * kD), p.bank[0] + off);
-                if (p.bank_used[1]) cp_async16(dst + i * (2 * kD) + kD, p.bank[1] + off);
+            for (int q = 0; q < 4; ++q) {
+                if (p.bank_used[0]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bank[0] + off + 32 * q));
+                if (p.bank_used[1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bank[1] + off + 32 * q));
             }
         }
-        cp_async_commit();
     };
-
-    const int first = warp * 32;
-    const int n_chunks = first < n_items ? (n_items - first + kGatherWarps * 32 - 1) / (kGatherWarps * 32) : 0;
-    ItemDesc cur = describe(first), nxt = cur;
-    if (n_chunks > 0) {
-#pragma unroll
-        for (int s = 0; s < kRing; ++s) issue(cur, s, s);
-    }
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        const int c0 = first + ci * kGatherWarps * 32;
-        const bool has_next = ci + 1 < n_chunks;
-        if (has_next) nxt = describe(c0 + kGatherWarps * 32);
+    int kind_n, kk_n;
+    int64_t idx_n;
+    if (warp * 32 < n_items) describe(warp * 32, kind_n, kk_n, idx_n);
+    for (int c0 = warp * 32; c0 < n_items; c0 += kGatherWarps * 32) {
+        const int kind = kind_n, kk = kk_n;
+        const int64_t idx = idx_n;
+        if (c0 + kGatherWarps * 32 < n_items) describe(c0 + kGatherWarps * 32, kind_n, kk_n, idx_n);
         const int n_chunk = min(32, n_items - c0);
-#pragma unroll
-        for (int st = 0; st < 4; ++st) {
-            const int t = ci * 4 + st, slot = t % kRing;
-            // groups complete in order: all but the kRing - 1 youngest are done (the tail of the stream commits empty groups)
-            cp_async_wait<kRing - 1>();
-            __syncwarp();
-            const float* stage = ring + (size_t)slot * (kStageBytes / 4);
+
+        for (int j0 = 0; j0 < n_chunk; j0 += 8) {
             float4 rv[2][4], ra[2][4];
             int kind_u[2], kk_u[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int src = st * 8 + 4 * u + grp;          // the item this group scores in quad u
-                kind_u[u] = __shfl_sync(0xffffffffu, cur.kind, src);
-                kk_u[u] = __shfl_sync(0xffffffffu, cur.kk, src);
-                if (src >= n_chunk) kind_u[u] = -1;
+                const int src = (j0 + 4 * u + grp) & 31;          // the item this group scores in quad u
+                const int64_t idx_u = __shfl_sync(0xffffffffu, idx, src);
+                kind_u[u] = __shfl_sync(0xffffffffu, kind, src);
+                kk_u[u] = __shfl_sync(0xffffffffu, kk, src);
+                if (j0 + 4 * u + grp >= n_chunk) kind_u[u] = -1;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     rv[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     ra[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (kind_u[u] >= 0) {
-                    const float4* r = reinterpret_cast<const float4*>(stage + (4 * u + grp) * (2 * kD)) + l8;
+                    const size_t off = (size_t)(idx_u - p.row_begin) * kD;
                     if (p.bank_used[0]) {
+                        const float4* r = reinterpret_cast<const float4*>(p.bank[0] + off) + l8;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) rv[u][j] = r[8 * j];
+                        for (int j = 0; j < 4; ++j) rv[u][j] = ld_stream(r + 8 * j);
                     }
                     if (p.bank_used[1]) {
+                        const float4* r = reinterpret_cast<const float4*>(p.bank[1] + off) + l8;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ra[u][j] = r[kD / 4 + 8 * j];
+                        for (int j = 0; j < 4; ++j) ra[u][j] = ld_stream(r + 8 * j);
                     }
                 }
             }
-            // every lane has its rows in registers: the slot can take the stage kRing steps ahead
-            __syncwarp();
-            if (st + kRing < 4) issue(cur, st + kRing, slot);
-            else if (has_next) issue(nxt, st + kRing - 4, slot);
-            else cp_async_commit();
             // d[u][bank][ctx] of this group's two rows, on all 8 lanes of the group
             float d[2][2][2];
 #pragma unroll
@@ -286,8 +244,8 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
                         const float d1 = key.bank == 0 ? (key.ctx == 0 ? d[1][0][0] : d[1][0][1]) : (key.ctx == 0 ? d[1][1][0] : d[1][1][1]);
                         const float s = (u_sel ? d1 : d0) * p.inv_T;
                         if (p.scores) {
-                            const int slot_s = kind_m == 1 ? 0 : (kind_m == 2 ? 1 + kk_m : 1 + p.score_pos_k + kk_m);
-                            p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot_s] = s;
+                            const int slot = kind_m == 1 ? 0 : (kind_m == 2 ? 1 + kk_m : 1 + p.score_pos_k + kk_m);
+                            p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot] = s;
                         }
                         if (p.Z) {
                             // nce.py:42-57 with c = K_key * Z
@@ -310,12 +268,12 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
                 const int nk = min(4, p.num_keys - 4 * kp);
                 for (int q = 0; q < nk; ++q) {
                     const int bank = p.keys[q + 4 * kp].bank, ctx = p.keys[q + 4 * kp].ctx;      // uniform
-                    const float c0q = __shfl_sync(0xffffffffu, coef, (lane & 24) | q);
-                    const float c1q = __shfl_sync(0xffffffffu, coef, (lane & 24) | 4 | q);
+                    const float c0 = __shfl_sync(0xffffffffu, coef, (lane & 24) | q);
+                    const float c1 = __shfl_sync(0xffffffffu, coef, (lane & 24) | 4 | q);
                     if (bank == 0) {
-                        if (ctx == 0) { cf[0][0][0] += c0q; cf[1][0][0] += c1q; } else { cf[0][0][1] += c0q; cf[1][0][1] += c1q; }
+                        if (ctx == 0) { cf[0][0][0] += c0; cf[1][0][0] += c1; } else { cf[0][0][1] += c0; cf[1][0][1] += c1; }
                     } else {
-                        if (ctx == 0) { cf[0][1][0] += c0q; cf[1][1][0] += c1q; } else { cf[0][1][1] += c0q; cf[1][1][1] += c1q; }
+                        if (ctx == 0) { cf[0][1][0] += c0; cf[1][1][0] += c1; } else { cf[0][1][1] += c0; cf[1][1][1] += c1; }
                     }
                 }
             }
@@ -334,7 +292,6 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
                     }
                 }
         }
-        cur = nxt;
     }
     if (!p.Z) return;
 
@@ -570,6 +527,12 @@ __global__ void sample_negatives_kernel(const int64_t* y, int B, int K, int64_t 
 // Items per CTA (a multiple of 128 = 4 warps x 32-item chunks) chosen to minimise waves x (items + fixed per-CTA cost) with
 // 3 resident CTAs per SM, so the grid neither ends in a thin second wave nor starves the SMs.
 static void choose_split(int B, int K, int* splits, int* kc) {
+    static const int forced = [] { const char* e = getenv("AVID_NCE_KC"); return e ? atoi(e) : 0; }();     // tuning experiments only
+    if (forced > 0) {
+        *kc = forced;
+        *splits = (K + forced - 1) / forced;
+        return;
+    }
     const int slots = 3 * kNumSMs;
     long best_cost = -1;
     int best_c = 128;
