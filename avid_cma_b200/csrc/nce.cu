@@ -111,7 +111,8 @@ __device__ __forceinline__ void load_normalized(const float* emb, int b, int l8,
 // Measured and dropped (round 2): landing the rows in a per-warp shared-memory ring instead of registers -- with per-row
 // cp.async.bulk copies (request-rate bound: ~35 cycles per 512-byte request and SM; K = 1024: 49 us vs 39 us) and with cp.async
 // 16 B per lane (58 us; K = 16384: 0.60 instead of 0.77 of the HBM peak): the extra shared-memory hop costs more than the deeper
-// queue gives, because the kernel is bound by its few dependent round trips, not by bytes in flight.
+// queue gives, because the kernel is bound by its few dependent round trips, not by bytes in flight.  Also dropped: a per-lane
+// prefetch.global.L2 of the chunk's rows before scoring it (32 scattered lines per instruction: K = 1024 47 us, K = 16384 0.52).
 constexpr int kGatherSmem = 0;
 
 __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {
@@ -151,13 +152,11 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
     const int key_passes = (p.num_keys + 3) >> 2;
     const int u_sel = l8 >> 2;
 
-    // lane l describes item c0 + l of a 32-item chunk (kind 0 = negative k, 1 = self, 2 = positive-set entry) and, as soon as the
-    // bank row is known, asks L2 for its 2 x 512 bytes: the register loads of the quad loop below then find the rows in L2 (one
-    // DRAM round trip per chunk instead of one per pass of the quad loop); the next chunk is described and prefetched before the
-    // current one is scored.
-    auto describe = [&](int c0, int& kind, int& kk, int64_t& idx) {
+    for (int c0 = warp * 32; c0 < n_items; c0 += kGatherWarps * 32) {
+        // each lane describes one item of the chunk: kind 0 = negative k, 1 = self, 2 = positive-set entry
         const int item = c0 + lane;
-        kind = -1;  kk = 0;  idx = -1;
+        int kind = -1, kk = 0;
+        int64_t idx = -1;
         if (item < n_items) {
             if (item < npos) {
                 kind = item == 0 ? 1 : 2;
@@ -171,22 +170,6 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
             }
         }
         if (!(idx >= p.row_begin && idx < p.row_end)) kind = -1;      // rows another shard holds are scored there
-        if (kind >= 0) {
-            const size_t off = (size_t)(idx - p.row_begin) * kD;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (p.bank_used[0]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bank[0] + off + 32 * q));
-                if (p.bank_used[1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bank[1] + off + 32 * q));
-            }
-        }
-    };
-    int kind_n, kk_n;
-    int64_t idx_n;
-    if (warp * 32 < n_items) describe(warp * 32, kind_n, kk_n, idx_n);
-    for (int c0 = warp * 32; c0 < n_items; c0 += kGatherWarps * 32) {
-        const int kind = kind_n, kk = kk_n;
-        const int64_t idx = idx_n;
-        if (c0 + kGatherWarps * 32 < n_items) describe(c0 + kGatherWarps * 32, kind_n, kk_n, idx_n);
         const int n_chunk = min(32, n_items - c0);
 
         for (int j0 = 0; j0 < n_chunk; j0 += 8) {

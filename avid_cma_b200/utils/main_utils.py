@@ -80,6 +80,8 @@ def build_model(cfg, logger=None):
     assert cfg['arch'] in models.__dict__, 'Unknown model architecture'
     model = models.__dict__[cfg['arch']](**cfg['args'])
     if logger is not None:
+        from .. import __version__, _lib
+        logger.add_line("backend: avid_cma_b200 {} ({})".format(__version__, _lib.LIB_PATH))
         parts = model if isinstance(model, (list, tuple)) else [model]
         logger.add_line("=" * 30 + "   Model   " + "=" * 30)
         for m in parts:
