@@ -41,6 +41,13 @@ class BnBackwardFuse(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("z", "mean", "invstd", "gamma", "beta", "sums")]
 
 
+AVID_MAX_PEERS = 16
+
+
+class PeerPtrs(C.Structure):
+    _fields_ = [("ptr", c_void_p * AVID_MAX_PEERS)]
+
+
 class ConvShape(C.Structure):
     _fields_ = [(n, c_int32) for n in ("n", "ti", "hi", "wi", "ci", "to", "ho", "wo", "co", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw")]
 
@@ -105,6 +112,8 @@ _SIGNATURES = {
     "avid_filter_from_tapmajor_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "avid_adam_step_multi": (C.c_int, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _F, _P]),
     "avid_zero_bytes": (C.c_int, [_P, _Z, _P]),
+    "avid_adam_shard_step": (C.c_int, [_P, C.POINTER(PeerPtrs), _I, _P, _P, _L, _L, _L, _F, _F, _F, _F, _F, _F, _P]),
+    "avid_pull_shards": (C.c_int, [_P, C.POINTER(PeerPtrs), _I, _I, _L, _P]),
     "avid_add_inplace": (C.c_int, [_P, _P, _L, _P]),
     "avid_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _F, _P]),
 }

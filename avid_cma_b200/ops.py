@@ -874,6 +874,30 @@ def adam_step_multi_(params, grads, exp_avgs, exp_avg_sqs, step, lr, betas=(0.9,
                                           weight_decay, grad_scale, _stream()))
 
 
+def peer_ptrs(ptrs):
+    """avid_peer_ptrs_t from a list of raw device pointers (symmetric-memory handle.buffer_ptrs: rank r's buffer as mapped here)."""
+    if len(ptrs) > _lib.AVID_MAX_PEERS:
+        raise ValueError("at most %d peers" % _lib.AVID_MAX_PEERS)
+    s = _lib.PeerPtrs()
+    for i, p in enumerate(ptrs):
+        s.ptr[i] = int(p)
+    return s
+
+
+@_timed("adam")
+def adam_shard_step_(flat_param, peer_grads, world, exp_avg, exp_avg_sq, begin, count, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                     grad_scale=1.0):
+    """Fused reduce-scatter (P2P loads from every rank's flat gradients) + Adam on the shard [begin, begin + count) this rank owns."""
+    check(_lib.lib().avid_adam_shard_step(_p(flat_param), C.byref(peer_grads), world, _p(exp_avg), _p(exp_avg_sq), begin, count, step, lr,
+                                          betas[0], betas[1], eps, weight_decay, grad_scale, _stream()))
+
+
+@_timed("adam")
+def pull_shards_(flat_param, peer_params, world, rank, shard):
+    """All-gather of the updated parameter shards by P2P loads into the local flat parameter buffer."""
+    check(_lib.lib().avid_pull_shards(_p(flat_param), C.byref(peer_params), world, rank, shard, _stream()))
+
+
 def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
     check(_lib.lib().avid_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), step, lr, betas[0], betas[1], eps,
                                     weight_decay, grad_scale, _stream()))

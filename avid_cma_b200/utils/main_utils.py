@@ -105,6 +105,11 @@ def distribute_model_to_cuda(models, args, batch_size, num_workers, ngpus_per_no
 
     def place(m):
         if args.distributed:
+            if pinned and fused_grad_sync():
+                # AVID_GRAD_SYNC=fused: gradients stay local, build_optimizer returns the optimizer that exchanges them over NVLink
+                # peer memory inside its step (optim.ShardedAdam); the wrapper only provides `.module` and the `module.` key prefix
+                from ..optim import LocalGradients
+                return LocalGradients(m.cuda(args.gpu))
             ddp = torch.nn.parallel.DistributedDataParallel
             return ddp(m.cuda(args.gpu), device_ids=[args.gpu]) if pinned else ddp(m.cuda())
         if pinned:
@@ -117,6 +122,15 @@ def distribute_model_to_cuda(models, args, batch_size, num_workers, ngpus_per_no
     if args.distributed and pinned:
         batch_size, num_workers = int(batch_size / ngpus_per_node), int((num_workers + ngpus_per_node - 1) / ngpus_per_node)
     return placed, args, batch_size, num_workers
+
+
+def fused_grad_sync():
+    """AVID_GRAD_SYNC=fused (default: ddp, the reference's DistributedDataParallel + Adam): W > 1 ranks on one node exchange the
+    gradients inside the optimizer step over NVLink peer memory (optim.ShardedAdam)."""
+    if os.environ.get('AVID_GRAD_SYNC', 'ddp') != 'fused':
+        return False
+    from ..optim import ShardedAdam
+    return ShardedAdam.available()
 
 
 def build_dataloaders(cfg, num_workers, distributed, logger):
@@ -162,10 +176,10 @@ def build_optimizer(params, cfg, logger=None):
     if kind == 'sgd':
         optimizer = torch.optim.SGD(params, lr=lr['base_lr'], momentum=cfg['momentum'], weight_decay=cfg['weight_decay'], nesterov=cfg['nesterov'])
     elif kind == 'adam':
-        from ..optim import Adam as FusedAdam
+        from ..optim import Adam as FusedAdam, ShardedAdam
         on_gpu = bool(params) and all(p.is_cuda for p in params)
-        optimizer = (FusedAdam if on_gpu else torch.optim.Adam)(params, lr=lr['base_lr'], weight_decay=cfg['weight_decay'],
-                                                               betas=cfg.get('betas', [0.9, 0.999]))
+        cls = (ShardedAdam if fused_grad_sync() else FusedAdam) if on_gpu else torch.optim.Adam
+        optimizer = cls(params, lr=lr['base_lr'], weight_decay=cfg['weight_decay'], betas=cfg.get('betas', [0.9, 0.999]))
     else:
         raise ValueError('Unknown optimizer.')
     return optimizer, torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=lr['milestones'], gamma=lr['gamma'])
@@ -207,9 +221,11 @@ class CheckpointManager(object):
         return os.path.isfile(self.checkpoint_fn(last, best))
 
     def save(self, epoch, filename=None, eval_metric=0., **kwargs):
-        """kwargs: name -> module / optimizer.  A criterion with row-sharded banks makes this call COLLECTIVE (the banks are gathered
-        on every rank); otherwise ranks other than 0 return at once."""
-        gather = any(getattr(getattr(m, 'nce_average', None), 'sharded', False) for m in kwargs.values())
+        """kwargs: name -> module / optimizer.  A criterion with row-sharded banks or an optimizer with sharded moments
+        (optim.ShardedAdam) makes this call COLLECTIVE (the shards are gathered on every rank); otherwise ranks other than 0 return
+        at once."""
+        gather = any(getattr(getattr(m, 'nce_average', None), 'sharded', False) or getattr(m, 'collective_state_dict', False)
+                     for m in kwargs.values())
         if self.rank != 0 and not gather:
             return
         state = {name: (reference_state_dict(m) if hasattr(m, 'nce_average') else m.state_dict()) for name, m in kwargs.items()}

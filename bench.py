@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--sub-steps", type=int, default=8, help="timed steps of each N > 1 sub-record (after 3 warm-up steps)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the end-to-end timed region")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event table of the timed region (mean over steps, launch order) to this file")
+    ap.add_argument("--grad-sync", default="auto", choices=["auto", "fused", "ddp"],
+                    help="N > 1: fused = gradients exchanged inside the optimizer step over NVLink peer memory (optim.ShardedAdam, default when "
+                         "symmetric memory is available), ddp = the reference's DistributedDataParallel all-reduce + Adam")
     ap.add_argument("--bank-mode", default="auto", choices=["auto", "replicated", "sharded"],
                     help="memory-bank layout for N > 1: sharded = row-partitioned over the ranks (default), replicated = the reference's")
     return ap.parse_args()
@@ -62,7 +65,7 @@ def config_of(a, n_gpus):
     return {"workload": "Cross-N1024 AVID, 240k-entry memory bank (Kinetics-shape), batch=64/GPU 8x3x224x224 + 1x200x257",
             "global_batch": a.batch * n_gpus, "batch_per_gpu": a.batch, "clip": [3, a.frames, a.size, a.size], "spectrogram": [1] + list(a.spec),
             "bank_rows": a.bank, "num_negatives": a.negatives, "optimizer": "adam lr 2e-4 wd 1e-5",
-            "parallelism": f"dp{n_gpus}", "bank_layout": "single" if n_gpus == 1 else ("replicated" if a.bank_mode == "replicated" else "row-sharded"), "math": a.math, "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
+            "parallelism": f"dp{n_gpus}", "grad_sync": getattr(a, "grad_sync_used", "none"), "bank_layout": "single" if n_gpus == 1 else ("replicated" if a.bank_mode == "replicated" else "row-sharded"), "math": a.math, "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -356,8 +359,17 @@ def run_ours(a):
     # broadcast_buffers=False: the per-forward broadcast of rank 0's 126 BatchNorm buffers only matters for what a checkpoint holds,
     # and rank 0 writes the checkpoint either way (utils/main_utils.py CheckpointManager)
     ddp = world > 1 and os.environ.get("AVID_BENCH_NO_DDP", "0") != "1"       # AVID_BENCH_NO_DDP=1: diagnostic only (no gradient sync)
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True) if ddp else model
-    opt = optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
+    fused = ddp and a.grad_sync != "ddp" and optim.ShardedAdam.available()
+    if a.grad_sync == "fused" and world > 1 and not fused:
+        raise RuntimeError("--grad-sync fused needs torch symmetric memory (all ranks on one node, NCCL backend)")
+    a.grad_sync_used = "none" if world == 1 else ("fused reduce-scatter + Adam + all-gather over NVLink peer memory (ShardedAdam)" if fused else
+                                                  ("DistributedDataParallel all-reduce + Adam" if ddp else "off (diagnostic)"))
+    if fused:
+        net = optim.LocalGradients(model)
+        opt = optim.ShardedAdam(model.parameters(), lr=2e-4, weight_decay=1e-5)
+    else:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True) if ddp else model
+        opt = optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
 
     B = a.batch
     g = torch.Generator().manual_seed(1234 + rank)

@@ -392,6 +392,29 @@ int avid_log_spectrogram(const float* wave, int32_t batch, int32_t num_samples, 
                          float top_db, const float* mean, const float* stdv, float* out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- Sharded optimizer over NVLink peer memory -------------------------------------------------------------------------
+ * Replaces DistributedDataParallel's gradient all-reduce (utils/main_utils.py:105-117) followed by torch.optim.Adam.step on every
+ * rank (main_utils.py:250-256) for runs with W > 1 ranks on one node: rank r owns elements [r * S, (r + 1) * S) of the flat
+ * parameter vector.  The buffers are symmetric allocations (same layout on every rank, peer-mapped); ptr[r] is rank r's buffer as
+ * seen from this process.  The caller orders the ranks (gradients complete before avid_adam_shard_step, shards updated before
+ * avid_pull_shards) with a barrier each. */
+#define AVID_MAX_PEERS 16
+typedef struct avid_peer_ptrs {
+    const void* ptr[AVID_MAX_PEERS];
+} avid_peer_ptrs_t;
+
+/* Reduce-scatter + Adam in one pass over the shard [begin, begin + count) (both multiples of 4):
+ *   g = grad_scale * sum_{r < world} grads->ptr[r][begin + i]   (grad_scale = 1 / world is DDP's average; P2P loads, rank order)
+ *   torch.optim.Adam update (L2 weight decay, bias correction at `step`) of param_flat[begin + i], exp_avg[i], exp_avg_sq[i];
+ * exp_avg / exp_avg_sq hold `count` elements (only the owner keeps the moments of its shard). */
+int avid_adam_shard_step(float* param_flat, const avid_peer_ptrs_t* grads, int32_t world, float* exp_avg, float* exp_avg_sq, int64_t begin,
+                         int64_t count, int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                         void* stream);
+
+/* All-gather of the updated parameters by P2P loads: param_flat[r * shard, (r + 1) * shard) <- params->ptr[r][same range] for
+ * every r != rank (shard a multiple of 4; the flat buffers hold world * shard elements). */
+int avid_pull_shards(float* param_flat, const avid_peer_ptrs_t* params, int32_t world, int32_t rank, int64_t shard, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ def main():
     n = 22 * 1024 * 1024          # 88 MB of fp32: the size of the gradient set
     t = symm.empty(n, dtype=torch.float32, device=dev)
     hdl = symm.rendezvous(t, dist.group.WORLD)
-    print(rank, "rendezvous ok: world", hdl.world_size, "rank", hdl.rank, "ptrs", [hex(p) for p in hdl.buffer_ptrs], "multicast", hdl.has_multicast_support(dev.type, local) if hasattr(hdl, "has_multicast_support") else None, flush=True)
+    print(rank, "rendezvous ok: world", hdl.world_size, "rank", hdl.rank, "ptrs", [hex(p) for p in hdl.buffer_ptrs], flush=True)
     t.fill_(float(rank + 1))
     hdl.barrier(channel=0)
     peer = (rank + 1) % world

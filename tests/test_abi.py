@@ -46,6 +46,16 @@ def test_invalid_arguments_report_einval(lib):
     s = _lib.ConvShape(1, 1, 8, 8, 4, 1, 8, 8, 64, 1, 3, 3, 1, 1, 1, 0, 1, 1)
     rc = lib.avid_conv_forward(C.byref(s), C.c_void_p(16), C.c_void_p(16), None, C.c_void_p(16), 7, None)
     assert rc == 4   # unknown math mode -> AVID_EUNSUPPORTED, before any launch
+    # sharded optimizer: shard bounds must be float4-aligned, peers bounded, every peer buffer present (all checked before any launch)
+    peers = _lib.PeerPtrs()
+    peers.ptr[0] = 16
+    rc = lib.avid_adam_shard_step(C.c_void_p(16), C.byref(peers), 2, C.c_void_p(16), C.c_void_p(16), 0, 8, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.5, None)
+    assert rc == 1 and b"rank 1 is NULL" in lib.avid_last_error()
+    rc = lib.avid_adam_shard_step(C.c_void_p(16), C.byref(peers), 1, C.c_void_p(16), C.c_void_p(16), 2, 8, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None)
+    assert rc == 1 and b"aligned" in lib.avid_last_error()
+    rc = lib.avid_pull_shards(C.c_void_p(16), C.byref(peers), 40, 0, 8, None)
+    assert rc == 1 and b"world" in lib.avid_last_error()
+    assert C.sizeof(_lib.PeerPtrs) == 8 * _lib.AVID_MAX_PEERS
 
 
 def test_ops_refuse_cpu_tensors():
