@@ -52,7 +52,7 @@ class ConvShape(C.Structure):
     _fields_ = [(n, c_int32) for n in ("n", "ti", "hi", "wi", "ci", "to", "ho", "wo", "co", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw")]
 
 
-_P, _I, _L, _F, _Z, _U = c_void_p, c_int32, c_int64, c_float, c_size_t, c_uint64
+_P, _I, _L, _F, _Z, _U, _D = c_void_p, c_int32, c_int64, c_float, c_size_t, c_uint64, C.c_double
 _SIGNATURES = {
     "avid_version": (C.c_int, []),
     "avid_last_error": (C.c_char_p, []),
@@ -112,7 +112,7 @@ _SIGNATURES = {
     "avid_filter_from_tapmajor_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "avid_adam_step_multi": (C.c_int, [_P, _P, _P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _F, _P]),
     "avid_zero_bytes": (C.c_int, [_P, _Z, _P]),
-    "avid_adam_shard_step": (C.c_int, [_P, C.POINTER(PeerPtrs), _I, _P, _P, _L, _L, _L, _F, _F, _F, _F, _F, _F, _P]),
+    "avid_adam_shard_step": (C.c_int, [_P, C.POINTER(PeerPtrs), _I, _P, _P, _L, _L, _L, _D, _D, _D, _D, _D, _D, _P]),
     "avid_pull_shards": (C.c_int, [_P, C.POINTER(PeerPtrs), _I, _I, _L, _P]),
     "avid_add_inplace": (C.c_int, [_P, _P, _L, _P]),
     "avid_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _F, _P]),

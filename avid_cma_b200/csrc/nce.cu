@@ -112,7 +112,12 @@ __device__ __forceinline__ void load_normalized(const float* emb, int b, int l8,
 // cp.async.bulk copies (request-rate bound: ~35 cycles per 512-byte request and SM; K = 1024: 49 us vs 39 us) and with cp.async
 // 16 B per lane (58 us; K = 16384: 0.60 instead of 0.77 of the HBM peak): the extra shared-memory hop costs more than the deeper
 // queue gives, because the kernel is bound by its few dependent round trips, not by bytes in flight.  Also dropped: a per-lane
-// prefetch.global.L2 of the chunk's rows before scoring it (32 scattered lines per instruction: K = 1024 47 us, K = 16384 0.52).
+// prefetch.global.L2 of the chunk's rows before scoring it (32 scattered lines per instruction: K = 1024 47 us, K = 16384 0.52),
+// and TMA tile::gather4 requests (4 rows per request, scripts/probes/gather4_tma.cu: correct, but the TMA unit serves ~one 512-byte
+// row per ~60 cycles and SM: K = 1024 49 us, K = 16384 0.35 of the HBM peak with a 6-stage ring).  Same box, register path:
+// 37 us / 0.54 (K = 4096) / 0.77 (K = 16384).  Little's law on those numbers: ~96 KB in flight per SM at 5.0 TB/s is an
+// effective round trip of ~2.8 us for random 512-byte rows, so K = 1024 (8 dependent round trips per warp) cannot go below ~25 us
+// in this structure.
 constexpr int kGatherSmem = 0;
 
 __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {

@@ -24,7 +24,7 @@ struct PeerPtrs {
 
 __global__ void __launch_bounds__(256) adam_shard_kernel(float* __restrict__ param, const PeerPtrs grads, int world, float* __restrict__ m,
                                                          float* __restrict__ v, int64_t begin, int64_t count4, float lr_over_bc1, float beta1, float beta2,
-                                                         float eps, float weight_decay, float inv_bc2_sqrt, float grad_scale) {
+                                                         float omb1, float omb2, float eps, float weight_decay, float bc2_sqrt, float grad_scale) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < world; ++r) {       // fixed order: the sum does not depend on who computes it
@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(256) adam_shard_kernel(float* __restrict__ par
 #pragma unroll
         for (int j = 0; j < 4; ++j) {           // torch.optim.Adam with L2 weight decay, the arithmetic of adam_multi_kernel (misc.cu)
             const float gi = fmaf(weight_decay, pp[j], gg[j] * grad_scale);
-            mm[j] = beta1 * mm[j] + (1.f - beta1) * gi;
-            vv[j] = beta2 * vv[j] + (1.f - beta2) * gi * gi;
-            const float denom = sqrtf(vv[j]) * inv_bc2_sqrt + eps;
+            mm[j] = beta1 * mm[j] + omb1 * gi;
+            vv[j] = beta2 * vv[j] + omb2 * gi * gi;
+            const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
             pp[j] = pp[j] - lr_over_bc1 * (mm[j] / denom);
         }
         reinterpret_cast<float4*>(param + begin)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
@@ -64,7 +64,7 @@ using namespace avid;
 extern "C" {
 
 int avid_adam_shard_step(float* param_flat, const avid_peer_ptrs_t* grads, int32_t world, float* exp_avg, float* exp_avg_sq, int64_t begin,
-                         int64_t count, int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                         int64_t count, int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                          void* stream) {
     AVID_REQUIRE(param_flat && grads && exp_avg && exp_avg_sq, "adam_shard_step: NULL pointer");
     AVID_REQUIRE(world >= 1 && world <= AVID_MAX_PEERS, "adam_shard_step: world %d not in [1, %d]", world, AVID_MAX_PEERS);
@@ -73,13 +73,16 @@ int avid_adam_shard_step(float* param_flat, const avid_peer_ptrs_t* grads, int32
     PeerPtrs g;
     for (int r = 0; r < AVID_MAX_PEERS; ++r) g.p[r] = r < world ? static_cast<const float*>(grads->ptr[r]) : nullptr;
     for (int r = 0; r < world; ++r) AVID_REQUIRE(g.p[r], "adam_shard_step: gradient buffer of rank %d is NULL", r);
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    // hyper-parameters arrive as doubles (python floats) and are rounded to fp32 the way torch.optim.Adam's kernels see them:
+    // beta and (1 - beta) are rounded separately -- fl(1 - fl(0.999)) differs from fl(1 - 0.999) by 4.7e-5 relative
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     const int64_t count4 = count / 4;
     int64_t blocks = (count4 + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     adam_shard_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param_flat, g, world, exp_avg, exp_avg_sq, begin, count4,
-                                                                                      (float)(lr / bc1), beta1, beta2, eps, weight_decay,
-                                                                                      (float)(1.0 / sqrt(bc2)), grad_scale);
+                                                                                      (float)(lr / bc1), (float)beta1, (float)beta2, (float)(1.0 - beta1),
+                                                                                      (float)(1.0 - beta2), (float)eps, (float)weight_decay,
+                                                                                      (float)sqrt(bc2), (float)grad_scale);
     return check_launch("adam_shard_kernel");
 }
 

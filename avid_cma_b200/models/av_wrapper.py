@@ -82,7 +82,7 @@ class AV_Wrapper(nn.Module):
         return getattr(self, head_name)(emb) if self.use_linear_proj else emb
 
     def forward(self, video, audio):
-        if os.environ.get('AVID_TOWER_STREAMS', '0') == '1' and video.is_cuda:
+        if os.environ.get('AVID_TOWER_STREAMS', '1') == '1' and video.is_cuda:
             # the two towers are independent until the criterion: the audio tower (11 % of the FLOPs) runs on a side stream, so
             # its bandwidth-bound passes overlap the video tower's tensor-bound ones; autograd replays each tower's backward on
             # the stream of its forward

@@ -65,7 +65,7 @@ def config_of(a, n_gpus):
     return {"workload": "Cross-N1024 AVID, 240k-entry memory bank (Kinetics-shape), batch=64/GPU 8x3x224x224 + 1x200x257",
             "global_batch": a.batch * n_gpus, "batch_per_gpu": a.batch, "clip": [3, a.frames, a.size, a.size], "spectrogram": [1] + list(a.spec),
             "bank_rows": a.bank, "num_negatives": a.negatives, "optimizer": "adam lr 2e-4 wd 1e-5",
-            "parallelism": f"dp{n_gpus}", "grad_sync": getattr(a, "grad_sync_used", "none"), "bank_layout": "single" if n_gpus == 1 else ("replicated" if a.bank_mode == "replicated" else "row-sharded"), "math": a.math, "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
+            "parallelism": f"dp{n_gpus}", "grad_sync": getattr(a, "grad_sync_used", "none"), "bank_layout": "single" if n_gpus == 1 else ("replicated" if a.bank_mode == "replicated" else "row-sharded"), "math": a.math, "tower_streams": 2 if os.environ.get("AVID_TOWER_STREAMS", "1") == "1" else 1, "l2": "inputs larger than L2 (one batch of clips = %.0f MB)" % (a.batch * 3 * a.frames * a.size * a.size * 4 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -378,7 +378,7 @@ def run_ours(a):
             for _ in range(nbuf)]
     resident = [(v.to(dev), s.to(dev)) for v, s in host]
     perm = torch.randperm(a.bank, generator=torch.Generator().manual_seed(7))
-    total_steps = 2 * (a.warmup + a.steps) + 4
+    total_steps = 3 * (a.warmup + a.steps) + 16
     ys_host = [perm[(i * world + rank) * B % (a.bank - B):][:B].contiguous().pin_memory() for i in range(total_steps)]
     ys_dev = [y.to(dev) for y in ys_host]
 
@@ -402,12 +402,11 @@ def run_ours(a):
     it = 0
     for _ in range(a.warmup):
         step(*resident[it % nbuf], ys_dev[it]); it += 1
-    # ---- timed region 1: inputs resident in HBM ----
+    # ---- timed region 1: inputs resident in HBM (the headline `value`) ----
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ops.reset_launch_count()
-    ops.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -416,8 +415,29 @@ def run_ours(a):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count()
-    prof = ops.profile_end()
     clocks = sampler.summary()
+
+    # ---- timed region 1b: the same steps with a CUDA-event pair around every tensor-core / criterion launch (roofline).  The two
+    #      towers normally run on two streams (models/av_wrapper.py); per-launch durations are only meaningful when the launches do
+    #      not overlap, so this region runs them on one stream -- which is also why it is not the region `value` comes from.
+    prof_steps = min(a.steps, 10)
+    streams_env = os.environ.get("AVID_TOWER_STREAMS")
+    os.environ["AVID_TOWER_STREAMS"] = "0"
+    step(*resident[it % nbuf], ys_dev[it]); it += 1
+    barrier()
+    ops.profile_begin()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(prof_steps):
+        step(*resident[it % nbuf], ys_dev[it]); it += 1
+    p1.record()
+    barrier()
+    ms_prof = p0.elapsed_time(p1)
+    prof = ops.profile_end()
+    if streams_env is None:
+        os.environ.pop("AVID_TOWER_STREAMS", None)
+    else:
+        os.environ["AVID_TOWER_STREAMS"] = streams_env
 
     graph_ms = None
     if a.graph_experiment and world == 1:
@@ -494,11 +514,11 @@ def run_ours(a):
         return
 
     clips = B * world * a.steps
-    if a.dump_launches and len(prof) % a.steps == 0:
-        per = len(prof) // a.steps
+    if a.dump_launches and len(prof) % prof_steps == 0:
+        per = len(prof) // prof_steps
         with open(a.dump_launches, "w") as f:
             for i in range(per):
-                durs = [prof[s_ * per + i][2] for s_ in range(a.steps)]
+                durs = [prof[s_ * per + i][2] for s_ in range(prof_steps)]
                 name, work = prof[i][0], prof[i][1]
                 mean = sum(durs) / len(durs)
                 f.write("%3d %-18s %9.1f us  work %10.3e  rate %8.1f (TFLOP/s or GB/s)\n" % (i, name, mean * 1e3, work, work / (mean * 1e-3) / (1e9 if name.startswith("nce") else 1e12)))
@@ -517,7 +537,7 @@ def run_ours(a):
     roofline, families = None, {}
     for name, (work, dur, cnt) in fam.items():
         rate = work / (dur * 1e-3) if dur > 0 else 0.0
-        families[name] = {"launches": cnt, "ms_per_step": dur / a.steps, "share_of_step": dur / ms}
+        families[name] = {"launches": cnt, "ms_per_step": dur / prof_steps, "share_of_step": dur / ms_prof}
         families[name]["GB/s" if name.startswith("nce") else "TFLOP/s"] = rate / (1e9 if name.startswith("nce") else 1e12)
     kernels = {}
     for name, (work, dur, cnt) in fam.items():
@@ -544,7 +564,9 @@ def run_ours(a):
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
                     "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured" if peaks else "fallback",
-                    "launches_timed": cnt, "avg_launch_ms": dur / cnt, "share_of_step": dur / ms,
+                    "launches_timed": cnt, "avg_launch_ms": dur / cnt, "share_of_step": dur / ms_prof,
+                    "measured_in": "%d single-stream steps with a CUDA-event pair around each launch (%.2f ms per step); `value` comes from the "
+                                   "region before it (towers on two streams, no per-launch events)" % (prof_steps, ms_prof / prof_steps),
                     "algorithmic_flops_per_launch": work / cnt,
                     "executed_mma_factor": mma_factor, "executed_frac": ach * mma_factor / tensor_peak,
                     "note": "achieved counts each product once (2*MAC of the convolution); bf16x3 issues 3 bf16 MMAs per product, so the "

@@ -406,9 +406,10 @@ typedef struct avid_peer_ptrs {
 /* Reduce-scatter + Adam in one pass over the shard [begin, begin + count) (both multiples of 4):
  *   g = grad_scale * sum_{r < world} grads->ptr[r][begin + i]   (grad_scale = 1 / world is DDP's average; P2P loads, rank order)
  *   torch.optim.Adam update (L2 weight decay, bias correction at `step`) of param_flat[begin + i], exp_avg[i], exp_avg_sq[i];
- * exp_avg / exp_avg_sq hold `count` elements (only the owner keeps the moments of its shard). */
+ * exp_avg / exp_avg_sq hold `count` elements (only the owner keeps the moments of its shard).  The hyper-parameters are doubles and
+ * are rounded to fp32 the way torch.optim.Adam's kernels see them (beta and 1 - beta separately). */
 int avid_adam_shard_step(float* param_flat, const avid_peer_ptrs_t* grads, int32_t world, float* exp_avg, float* exp_avg_sq, int64_t begin,
-                         int64_t count, int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                         int64_t count, int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                          void* stream);
 
 /* All-gather of the updated parameters by P2P loads: param_flat[r * shard, (r + 1) * shard) <- params->ptr[r][same range] for
