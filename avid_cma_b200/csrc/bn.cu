@@ -9,6 +9,8 @@
 
 namespace avid {
 
+constexpr int kEwUnroll = 4;      // independent 16-byte loads per thread and stream in the elementwise BatchNorm passes
+
 // The video stem is conv -> BN -> ReLU -> MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (models/video.py:20-23).  In the fused path the
 // ReLU output is never written: the forward pools relu(bn(z)) on the fly and records the winning window position; the
 // backward kernels obtain "dy" (the gradient at the ReLU output) by gathering the pooled gradient through that argmax.
@@ -166,20 +168,24 @@ __global__ void __launch_bounds__(256) bn_relu_forward_kernel(const float* __res
     const int cc = (int)(i0 % c4);
     const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cc);
     const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cc);
-    for (int64_t i = i0; i < n4; i += 2 * stride) {
-        const bool two = i + stride < n4;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + i);
-        const float4 v1 = two ? __ldg(reinterpret_cast<const float4*>(x) + i + stride) : v0;
+    // kEwUnroll independent 16-byte loads per thread and input stream before the first use: ~100 KB in flight per SM (the
+    // bandwidth-delay product of HBM3e is ~44 KB per SM; with 2 loads these passes ran at 4.6-5.1 TB/s of the 6.5 TB/s copy peak)
+    for (int64_t i = i0; i < n4; i += kEwUnroll * stride) {
+        float4 v[kEwUnroll];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
-            const float4 v = u ? v1 : v0;
+        for (int u = 0; u < kEwUnroll; ++u) {
             const int64_t k = i + u * stride;
+            v[u] = k < n4 ? __ldg(reinterpret_cast<const float4*>(x) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t k = i + u * stride;
+            if (k >= n4) break;
             float4 o;
-            o.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
-            o.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-            o.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
-            o.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+            o.x = fmaxf(fmaf(v[u].x, sc.x, sh.x), 0.f);
+            o.y = fmaxf(fmaf(v[u].y, sc.y, sh.y), 0.f);
+            o.z = fmaxf(fmaf(v[u].z, sc.z, sh.z), 0.f);
+            o.w = fmaxf(fmaf(v[u].w, sc.w, sh.w), 0.f);
             if (y) reinterpret_cast<float4*>(y)[k] = o;
             if (y_hi) {
                 const float f[4] = {o.x, o.y, o.z, o.w};
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_forward_kernel(const floa
     }
 }
 
-__global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) bn_relu_backward_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      const double* __restrict__ sums, int64_t rows, int c,
@@ -259,24 +265,21 @@ __global__ void __launch_bounds__(256) bn_relu_backward_apply_kernel(const float
         sg[j] = (float)sums[ch] * inv_n;
         sgx[j] = (float)sums[c + ch] * inv_n;
     }
-    for (int64_t i = i0; i < n4; i += 2 * stride) {
-        const bool two = i + stride < n4;
-        const float4 va = __ldg(reinterpret_cast<const float4*>(x) + i);
-        const float4 vb = two ? __ldg(reinterpret_cast<const float4*>(x) + i + stride) : va;
-        float4 da, db;
-        if (pool.argmax) {
-            da = pool_gather(pool, (uint32_t)i / (uint32_t)c4, cc, c4);
-            db = two ? pool_gather(pool, (uint32_t)(i + stride) / (uint32_t)c4, cc, c4) : da;
-        } else {
-            da = __ldg(reinterpret_cast<const float4*>(dy) + i);
-            db = two ? __ldg(reinterpret_cast<const float4*>(dy) + i + stride) : da;
+    for (int64_t i = i0; i < n4; i += kEwUnroll * stride) {
+        float4 xv4[kEwUnroll], dv4[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t k = i + u * stride;
+            const bool in = k < n4;
+            xv4[u] = in ? __ldg(reinterpret_cast<const float4*>(x) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pool.argmax) dv4[u] = in ? pool_gather(pool, (uint32_t)k / (uint32_t)c4, cc, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else dv4[u] = in ? __ldg(reinterpret_cast<const float4*>(dy) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
-            const float4 v = u ? vb : va, d = u ? db : da;
+        for (int u = 0; u < kEwUnroll; ++u) {
             const int64_t k = i + u * stride;
-            const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
+            if (k >= n4) break;
+            const float xv[4] = {xv4[u].x, xv4[u].y, xv4[u].z, xv4[u].w}, dv[4] = {dv4[u].x, dv4[u].y, dv4[u].z, dv4[u].w};
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

@@ -22,35 +22,131 @@ def prepare_tower_filters(tower):
     ops.prepare_filter_planes(ws, need_lo=tower.math == ops.MATH_BF16X3)
 
 
+def _run_forward(tower, x):
+    arena = tower.__dict__.setdefault('_fwd_arena', ops.ZeroArena())
+    arena.begin(x.device)
+    ops.set_arena(arena)
+    try:
+        prepare_tower_filters(tower)
+        return tower._fwd(x, tower.training, tower.math)
+    finally:
+        ops.set_arena(None)
+        ops.clear_filter_planes()
+
+
+def _run_backward(tower, dpooled, saved):
+    grads = {}
+    arena = tower.__dict__.setdefault('_bwd_arena', ops.ZeroArena())
+    arena.begin(dpooled.device)
+    ops.set_arena(arena)
+    ops.defer_filter_gradients(True)          # every filter gradient is brought to the PyTorch layout by ONE launch at the end
+    try:
+        tower._bwd(dpooled, saved, grads, tower.math)
+        ops.flush_filter_gradients()
+    finally:
+        ops.defer_filter_gradients(False)
+        ops.set_arena(None)
+    return grads
+
+
+class GraphedTower:
+    """CUDA graphs of one tower's training forward and backward for one input shape.
+
+    A tower step is ~150 (forward) + ~170 (backward) dependent kernel launches of 5 us .. 2 ms: replaying them from two captured
+    graphs removes the launch gaps and the host work per launch (ctypes call, tensor-map encoding, allocator).  Everything a
+    launch reads or writes has a fixed address: the input is copied into a static buffer, activations / saved tensors / gradients
+    live in the graph's private memory pool, parameters and BatchNorm buffers are updated in place by the optimizer.  The first
+    calls run eagerly (they also size the zero arenas); the capture happens on call number `kWarmup + 1`."""
+    kWarmup = 2
+
+    def __init__(self, tower, x):
+        self.tower = tower
+        self.x = torch.empty_like(x)
+        self.fwd = self.bwd = None
+        self.pooled = self.saved = self.dpooled = self.grads = None
+        self.launches_fwd = self.launches_bwd = 0
+        self.pending = False        # a forward whose backward has not run yet owns the static buffers
+
+    def forward(self, x):
+        self.x.copy_(x)
+        self.pending = True
+        if self.fwd is None:
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.pooled, self.saved = _run_forward(self.tower, self.x)
+            self.launches_fwd = ops.launch_count() - n0
+            self.fwd = g
+        self.fwd.replay()
+        ops.add_launches(self.launches_fwd)
+        return self.pooled
+
+    def backward(self, dpooled):
+        if self.bwd is None:
+            self.dpooled = torch.empty_like(dpooled)
+            self.dpooled.copy_(dpooled)
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.fwd.pool()):
+                self.grads = _run_backward(self.tower, self.dpooled, self.saved)
+            self.launches_bwd = ops.launch_count() - n0
+            self.bwd = g
+        else:
+            self.dpooled.copy_(dpooled)
+        self.bwd.replay()
+        ops.add_launches(self.launches_bwd)
+        self.pending = False
+        return self.grads
+
+
+def _graphs_enabled():
+    return os.environ.get('AVID_CUDA_GRAPH', '1') == '1' and not ops.profiling()
+
+
 class TowerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tower, x, *params):
-        arena = tower.__dict__.setdefault('_fwd_arena', ops.ZeroArena())
-        arena.begin(x.device)
-        ops.set_arena(arena)
-        try:
-            prepare_tower_filters(tower)
-            pooled, saved = tower._fwd(x.detach().contiguous().float(), tower.training, tower.math)
-        finally:
-            ops.set_arena(None)
-            ops.clear_filter_planes()
-        ctx.tower, ctx.saved, ctx.params = tower, saved, params
+        x = x.detach().contiguous().float()
+        graphed = None
+        if tower.training and _graphs_enabled():
+            # one graph pair per (input shape, arithmetic, parameter storage): anything else falls back to eager launches
+            key = (tuple(x.shape), tower.math, x.device.index, params[0].data_ptr(), params[-1].data_ptr())
+            cache = tower.__dict__.setdefault('_graphs', {})
+            entry = cache.get(key)
+            if entry is None:
+                entry = cache[key] = [0, None]
+            entry[0] += 1
+            if entry[0] > GraphedTower.kWarmup and entry[1] is not False and not (entry[1] is not None and entry[1].pending):
+                if entry[1] is None:
+                    entry[1] = GraphedTower(tower, x)
+                graphed = entry[1]
+                try:
+                    pooled = graphed.forward(x)
+                except Exception as e:        # noqa: BLE001 -- capture is an optimisation: fall back to eager launches, loudly
+                    import warnings
+                    warnings.warn('avid_cma_b200: CUDA-graph capture of %s failed (%r); running eager' % (type(tower).__name__, e))
+                    entry[1] = False
+                    graphed = None
+        if graphed is None:
+            pooled, saved = _run_forward(tower, x)
+            ctx.saved = saved
+        ctx.tower, ctx.graphed, ctx.params = tower, graphed, params
         return pooled
 
     @staticmethod
     def backward(ctx, dpooled):
-        grads = {}
-        arena = ctx.tower.__dict__.setdefault('_bwd_arena', ops.ZeroArena())
-        arena.begin(dpooled.device)
-        ops.set_arena(arena)
-        ops.defer_filter_gradients(True)          # every filter gradient is brought to the PyTorch layout by ONE launch at the end
-        try:
-            ctx.tower._bwd(dpooled.contiguous(), ctx.saved, grads, ctx.tower.math)
-            ops.flush_filter_gradients()
-        finally:
-            ops.defer_filter_gradients(False)
-            ops.set_arena(None)
-        ctx.saved = None
+        dpooled = dpooled.contiguous()
+        if ctx.graphed is not None:
+            grads = ctx.graphed.backward(dpooled)
+            # the gradient tensors are the graph's static buffers: hand out copies if a parameter still holds last step's gradient
+            # (autograd would add the buffer to itself), otherwise autograd just takes the reference
+            if any(p.grad is not None for p in ctx.params):
+                grads = {k: v.clone() for k, v in grads.items()}
+        else:
+            grads = _run_backward(ctx.tower, dpooled, ctx.saved)
+            ctx.saved = None
         return (None, None) + tuple(grads.get(p) for p in ctx.params)
 
 

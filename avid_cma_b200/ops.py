@@ -137,12 +137,29 @@ def _conv_flops(s, ci_real=None):
     return 2.0 * s.n * s.to * s.ho * s.wo * s.kt * s.kh * s.kw * (ci_real or s.ci) * s.co
 
 
+_replayed_launches = 0
+
+
 def launch_count():
-    return int(_lib.lib().avid_launch_count())
+    """Kernels of libavid_b200.so launched so far: direct launches (counted by the library) + launches replayed from CUDA graphs."""
+    return int(_lib.lib().avid_launch_count()) + _replayed_launches
+
+
+def add_launches(n):
+    """A CUDA-graph replay executes `n` captured launches the library's own counter does not see."""
+    global _replayed_launches
+    _replayed_launches += int(n)
 
 
 def reset_launch_count():
+    global _replayed_launches
+    _replayed_launches = 0
     _lib.lib().avid_reset_launch_count()
+
+
+def profiling():
+    """True while bench.py records CUDA-event pairs around the launches (event timing cannot be captured into a graph)."""
+    return _prof is not None
 
 
 # ------------------------------------------------------------------ criterion
@@ -156,7 +173,8 @@ def _group_layout(name, t, elem_bytes, rows_per_group):
     """(pointer to record 0, bytes between records) of a packed per-rank tensor (W, rows_per_group, ...) whose records are dense."""
     if t.shape[1] != rows_per_group or not t[0].is_contiguous():
         raise ValueError(f"{name}: every rank record must be a dense block of {rows_per_group} rows")
-    return t[0], t.stride(0) * elem_bytes
+    # a single record has no stride to speak of (PyTorch reports an arbitrary one for a size-1 dimension)
+    return t[0], (t.stride(0) * elem_bytes if t.shape[0] > 1 else None)
 
 
 def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows=None, row_begin=0, row_end=None,
@@ -179,9 +197,10 @@ def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows
         for name, t, eb in ins:
             views[name], st = _group_layout(name, t, eb, B)
             strides.add(st)
-        if len(strides) != 1:
+        strides.discard(None)
+        if len(strides) > 1:
             raise ValueError("packed inputs must share one record stride")
-        a.group_batch, a.in_group_stride = B, strides.pop()
+        a.group_batch, a.in_group_stride = B, (strides.pop() if strides else 0)
         outs = [(n_, t) for n_, t in (("grad_hat_v", grad_hat_v), ("grad_hat_a", grad_hat_a)) if t is not None]
         strides = set()
         for name, t in outs:
@@ -191,7 +210,8 @@ def make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, num_neg, Z, *, num_rows
             if tuple(loss_part.shape) != (W, len(keys), B) or not loss_part[0].is_contiguous():
                 raise ValueError("packed loss_part must be (W, num_keys, B) with dense records")
             views["loss_part"] = loss_part[0]
-            strides.add(loss_part.stride(0) * 4)
+            strides.add(loss_part.stride(0) * 4 if W > 1 else None)
+        strides.discard(None)
         if len(strides) > 1:
             raise ValueError("packed outputs must share one record stride")
         a.out_group_stride = strides.pop() if strides else 0
@@ -260,9 +280,9 @@ def bank_update(bank_v, bank_a, emb_v, emb_a, y, mom_v, mom_a, row_begin=0, row_
         n, gb = emb_v.shape[0] * emb_v.shape[1], emb_v.shape[1]
         (emb_v, s0), (emb_a, s1), (y, s2) = (_group_layout("emb_v", emb_v, 4, gb), _group_layout("emb_a", emb_a, 4, gb),
                                              _group_layout("y", y, 8, gb))
-        if not s0 == s1 == s2:
+        if len({s0, s1, s2} - {None}) > 1:
             raise ValueError("packed inputs must share one record stride")
-        stride = s0
+        stride = s0 or 0
     check(_lib.lib().avid_bank_update(_p(bank_v), _p(bank_a), row_begin, row_end, _p(emb_v), _p(emb_a), _p(y, torch.int64),
                                       n, gb, stride, float(mom_v), float(mom_a), _stream()))
 
