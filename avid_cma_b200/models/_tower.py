@@ -76,8 +76,10 @@ class GraphedTower:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.pooled, self.saved = _run_forward(self.tower, self.x)
-            self.launches_fwd = ops.launch_count() - n0
+            self.launches_fwd = ops.launch_count() - n0     # counted by the library while being captured: the first replay runs them
             self.fwd = g
+            self.fwd.replay()
+            return self.pooled
         self.fwd.replay()
         ops.add_launches(self.launches_fwd)
         return self.pooled
@@ -95,8 +97,8 @@ class GraphedTower:
             self.bwd = g
         else:
             self.dpooled.copy_(dpooled)
+            ops.add_launches(self.launches_bwd)
         self.bwd.replay()
-        ops.add_launches(self.launches_bwd)
         self.pending = False
         return self.grads
 
