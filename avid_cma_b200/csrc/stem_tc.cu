@@ -31,7 +31,9 @@ constexpr int kSlotRows = 11;                // rows per (kt, parity, plane) uni
 constexpr int kSlotBytes = kSlotRows * kRowBytes;
 constexpr int kChunkBBytes = kStemCo * 64;   // [64 co][32 k] bf16
 constexpr int kDzBytes = 128 * 128;          // [128 pixels][64 co] bf16
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 14;
+constexpr int kStgLd = 20;                   // row pitch (floats) of the 32 x 16 epilogue staging tiles: 16-byte aligned, conflict-free float4 rows
+constexpr int kStemStgBytes = 4 * 32 * kStgLd * 4;
 constexpr int kSmemLimit = 232448 - 1024;    // 227 KB minus alignment slack
 
 struct StemParams {
@@ -66,7 +68,8 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     const int chunks = p.kt * p.kh, planes = p.x3 ? 2 : 1;
     uint8_t* w_smem = smem;                                          // [chunk][plane][64 co][32 k]: hi | lo of a chunk = one 128-row operand
     uint8_t* ring = smem + planes * chunks * kChunkBBytes;           // [stage][11 rows][16 wo][32 k]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.stages * kSlotBytes);
+    float* s_stage = reinterpret_cast<float*>(ring + p.stages * kSlotBytes);       // [4 epilogue warps][32 rows][kStgLd] transpose staging
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.stages * kSlotBytes + kStemStgBytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* w_bar = empty_bar + kMaxStages;
     uint64_t* tmem_full = w_bar + 1;      // [2]
@@ -167,79 +170,100 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
             umma_commit(&tmem_full[buf]);
         }
     } else if (warp >= 2) {
-        // ===== epilogue: TMEM -> registers -> global, one output pixel (64 channels) per thread =====
+        // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> coalesced global rows + BatchNorm statistics =====
+        // tcgen05.ld hands every thread one output pixel (row of 64 channels).  Round 1 stored those rows straight from that layout:
+        // every STG.128 of a warp touched 32 different 256-byte rows with 16 bytes each (512 partial-sector writes per warp and
+        // tile), and ncu showed the epilogue warps stalled on the store queue for 40 % of all samples with the tensor pipe 46 %
+        // active -- the stores, not the MMAs, paced the kernel.  Now each warp transposes 32 x 16 half-chunks through a padded
+        // staging tile and writes 64-byte segments (4 lanes per row, 8 rows per instruction: full sectors, 4x fewer requests), like
+        // conv_tc_kernel; the per-channel sums stay in registers across the CTA's tiles and leave once, as fp64 atomics.
         const int q = warp & 3;
+        float* const stg = s_stage + (warp - 2) * (32 * kStgLd);
+        const int r8 = lane >> 2, c4 = (lane & 3) * 4;
         const int r = q * 32 + lane;
+        float run1[4][4], run2[4][4];      // running column sums: [16-column chunk][4 columns of this lane]
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) run1[a][t] = run2[a][t] = 0.f;
         int it = 0;
-        double run_s[2] = {0.0, 0.0}, run_q[2] = {0.0, 0.0};     // BatchNorm statistics of channels lane and 32 + lane over this warp's rows
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             int n_i, t_o, h0, w0;
             tile_coords(p, tile, n_i, t_o, h0, w0);
+            const int ho = h0 + r / kTileW, wo = w0 + r % kTileW;
+            const unsigned long long my_row = (ho < p.ho && wo < p.wo)
+                                                  ? (unsigned long long)((((size_t)n_i * p.to + t_o) * p.ho + ho) * p.wo + wo) * kStemCo : ~0ull;
+            unsigned long long rows4[4];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rows4[i] = __shfl_sync(0xffffffffu, my_row, i * 8 + r8);
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            uint32_t v0[32], v1[32];
             const uint32_t taddr = tmem_base + buf * ((X3 ? 2 : 1) * kStemCo) + ((uint32_t)(q * 32) << 16);
-            if (X3) {
-                uint32_t t0[32];
-                tmem_ld_32x32b_x32(taddr, v0);
-                tmem_ld_32x32b_x32(taddr + kStemCo, t0);
+#pragma unroll
+            for (int hc = 0; hc < 4; ++hc) {
+                uint32_t v[16], v2[16];
+                tmem_ld_32x32b_x16(taddr + hc * 16, v);
+                if (X3) tmem_ld_32x32b_x16(taddr + kStemCo + hc * 16, v2);       // the hi*lo half of the bf16x3 accumulator
                 tmem_ld_wait();
-#pragma unroll
-                for (int v = 0; v < 32; ++v) v0[v] = __float_as_uint(__uint_as_float(v0[v]) + __uint_as_float(t0[v]));
-                tmem_ld_32x32b_x32(taddr + 32, v1);
-                tmem_ld_32x32b_x32(taddr + kStemCo + 32, t0);
-                tmem_ld_wait();
-#pragma unroll
-                for (int v = 0; v < 32; ++v) v1[v] = __float_as_uint(__uint_as_float(v1[v]) + __uint_as_float(t0[v]));
-            } else {
-                tmem_ld_32x32b_x32(taddr, v0);
-                tmem_ld_32x32b_x32(taddr + 32, v1);
-                tmem_ld_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);     // the accumulator is in registers: the next tile may start
-            const int ho = h0 + r / kTileW, wo = w0 + r % kTileW;
-            const bool valid = ho < p.ho && wo < p.wo;
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(out + ((((size_t)n_i * p.to + t_o) * p.ho + ho) * p.wo + wo) * kStemCo);
-#pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    dst[v] = make_float4(__uint_as_float(v0[4 * v]), __uint_as_float(v0[4 * v + 1]), __uint_as_float(v0[4 * v + 2]),
-                                         __uint_as_float(v0[4 * v + 3]));
-#pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    dst[8 + v] = make_float4(__uint_as_float(v1[4 * v]), __uint_as_float(v1[4 * v + 1]), __uint_as_float(v1[4 * v + 2]),
-                                             __uint_as_float(v1[4 * v + 3]));
-            }
-            if (stats) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float o[32], sq[32];
-#pragma unroll
-                    for (int v = 0; v < 32; ++v) {
-                        o[v] = valid ? __uint_as_float(j ? v1[v] : v0[v]) : 0.f;
-                        sq[v] = o[v] * o[v];
-                    }
-                    run_s[j] += (double)warp_column_sums(o, lane);
-                    run_q[j] += (double)warp_column_sums(sq, lane);
+                if (hc == 3) {          // the accumulator is in registers: the next tile may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
+                float4* const srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float4 o = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+                    if (X3) {
+                        o.x += __uint_as_float(v2[4 * u]);  o.y += __uint_as_float(v2[4 * u + 1]);
+                        o.z += __uint_as_float(v2[4 * u + 2]);  o.w += __uint_as_float(v2[4 * u + 3]);
+                    }
+                    srow[u] = o;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 o = *reinterpret_cast<const float4*>(stg + (i * 8 + r8) * kStgLd + c4);
+                    if (rows4[i] == ~0ull) continue;
+                    *reinterpret_cast<float4*>(out + rows4[i] + hc * 16 + c4) = o;
+                    if (stats) {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            run1[hc][t] += ov[t];
+                            run2[hc][t] = fmaf(ov[t], ov[t], run2[hc][t]);
+                        }
+                    }
+                }
+                __syncwarp();                       // the staging tile is rewritten by the next half-chunk
             }
         }
         if (stats) {
-            // all tiles are done (every MMA has completed), so the row-slot ring is free: [4 warps][2][64] doubles
-            double* s_stat = reinterpret_cast<double*>(ring);
+            // lanes with equal (lane & 3) hold partial sums of the same 4 columns: reduce over the 8 row groups of the warp, over the
+            // 4 lane quarters through shared memory (the staging tiles are free now), then ONE fp64 atomic per column and CTA
+            float* const s_red = s_stage;           // [4 quarters][2 sums][64]
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                s_stat[(q * 2 + 0) * kStemCo + j * 32 + lane] = run_s[j];
-                s_stat[(q * 2 + 1) * kStemCo + j * 32 + lane] = run_q[j];
-            }
+            for (int hc = 0; hc < 4; ++hc)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float a = run1[hc][t], b = run2[hc][t];
+#pragma unroll
+                    for (int o = 4; o <= 16; o <<= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        b += __shfl_xor_sync(0xffffffffu, b, o);
+                    }
+                    if (lane < 4) {
+                        s_red[(q * 2 + 0) * kStemCo + hc * 16 + c4 + t] = a;
+                        s_red[(q * 2 + 1) * kStemCo + hc * 16 + c4 + t] = b;
+                    }
+                }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int t = threadIdx.x - 64;      // 0..127 = (which, channel)
             const int which = t >> 6, ch = t & 63;
-            atomicAdd(stats + which * kStemCo + ch, s_stat[(0 * 2 + which) * kStemCo + ch] + s_stat[(1 * 2 + which) * kStemCo + ch] +
-                                                        s_stat[(2 * 2 + which) * kStemCo + ch] + s_stat[(3 * 2 + which) * kStemCo + ch]);
+            atomicAdd(stats + which * kStemCo + ch, (double)s_red[(0 * 2 + which) * kStemCo + ch] + (double)s_red[(1 * 2 + which) * kStemCo + ch] +
+                                                        (double)s_red[(2 * 2 + which) * kStemCo + ch] + (double)s_red[(3 * 2 + which) * kStemCo + ch]);
         }
     }
     tc_fence_before();
@@ -480,10 +504,10 @@ int stem_forward_run(const avid_conv_shape_t* s, const void* x_hi, const void* x
     p.x3 = x_lo != nullptr;
     const int planes = p.x3 ? 2 : 1, chunks = p.kt * p.kh;
     const int w_bytes = planes * chunks * kChunkBBytes;
-    p.stages = (kSmemLimit - 256 - w_bytes) / kSlotBytes;
+    p.stages = (kSmemLimit - 512 - kStemStgBytes - w_bytes) / kSlotBytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     AVID_REQUIRE(p.stages >= 2, "stem_forward_tc: filter does not fit in shared memory");
-    const int smem = 1024 + w_bytes + p.stages * kSlotBytes + 256;
+    const int smem = 1024 + w_bytes + p.stages * kSlotBytes + kStemStgBytes + 512;
     CUtensorMap mx[2], mw[2];
     if ((rc = encode_stem_x(&mx[0], x_hi, s, wp))) return rc;
     mx[1] = mx[0];
@@ -519,9 +543,9 @@ int stem_wgrad_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_l
     AVID_REQUIRE(x_hi && d_hi && dfilt && (x_lo == nullptr) == (d_lo == nullptr), "stem_wgrad_tc: NULL pointer / mismatched lo planes");
     p.x3 = x_lo != nullptr;
     const int planes = p.x3 ? 2 : 1;
-    p.stages = (kSmemLimit - 256 - 2 * planes * kDzBytes) / kSlotBytes;
+    p.stages = (kSmemLimit - 512 - 2 * planes * kDzBytes) / kSlotBytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
-    const int smem = 1024 + 2 * planes * kDzBytes + p.stages * kSlotBytes + 256;
+    const int smem = 1024 + 2 * planes * kDzBytes + p.stages * kSlotBytes + 512;
     uint32_t cols = 32;
     while ((int)cols < 2 * (p.x3 ? 2 : 1) * kStemCo) cols <<= 1;       // two row-parity accumulators per CTA (the kt taps are split over CTAs)
     CUtensorMap mx[2], md[2];
