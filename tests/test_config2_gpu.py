@@ -1,0 +1,90 @@
+"""Whole-step parity at BASELINE config-2 SHAPES (8x3x224x224 clips, 1x200x257 spectrograms, 240 k-row bank, K = 1024, injected
+negatives): the CUDA path (bf16x3 tcgen05 towers, fused criterion) against the oracle towers + criterion run on the same GPU in
+fp32 with TF32 off -- which is how the reference itself computes on a GPU -- and against an fp64 run of the oracle (ground truth).
+North-star tolerance: 1e-3 relative on embeddings, loss and the updated bank rows.  Batch 8 instead of 64 keeps the oracle's
+autograd graph small; every layer runs at its full config-2 spatial extent."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import criterion as oc
+from oracle import synth, towers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+B, N, K = 8, 240000, 1024
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _oracle(video, audio, y, idx, sd, bank_v, bank_a, dtype):
+    """towers -> criterion -> backward -> bank update with stock torch ops on the GPU in `dtype` (TF32 off)."""
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = {k: (v.to(DEV, dtype) if v.is_floating_point() else v.to(DEV)) for k, v in sd.items()}
+        keys = towers.param_keys(sd)
+        for k in keys:
+            sd[k].requires_grad_(True)
+        ve, ae = towers.av_forward(video.to(DEV, dtype), audio.to(DEV, dtype), sd, training=True)
+        bv, ba = bank_v.to(DEV, dtype), bank_a.to(DEV, dtype)
+        total, losses, Z = oc.criterion_forward(ve, ae, y.to(DEV), bv, ba, idx.to(DEV), oc.avid_keys(K), -1.0)
+        total.backward()
+        with torch.no_grad():
+            oc.bank_update(bv, ba, ve, ae, y.to(DEV), 0.5)
+        grads = {k: sd[k].grad.detach().cpu() for k in ("video_model.conv5x.1.tmp_conv2.weight", "audio_model.block4.conv2.weight",
+                                                        "video_proj.projection.4.weight", "video_model.conv2x.0.spt_conv1.weight")}
+        return dict(ve=ve.detach().cpu(), ae=ae.detach().cpu(), loss=float(total), Z=Z, rows_v=bv[y.to(DEV)].cpu(), rows_a=ba[y.to(DEV)].cpu(),
+                    grads=grads, v2a=float(losses["v2a"]))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+
+
+def test_training_step_at_config2_shapes_matches_fp32_and_fp64_oracles():
+    from avid_cma_b200 import models
+    from avid_cma_b200.criterions import AVID
+    from avid_cma_b200.models._tower import _MATH
+    seed = 22
+    video, audio = synth.clips(B, 8, 224, seed), synth.spectrograms(B, 200, 257, seed)
+    y = synth.instance_ids(B, N, seed)
+    idx = synth.negatives(y, K, N, seed)
+    bank_v, bank_a = synth.bank(N, seed=seed, tag="bank_v"), synth.bank(N, seed=seed, tag="bank_a")
+    sd0 = synth.fill_state_dict(towers.state_dict_template(), seed=seed)
+
+    ref32 = _oracle(video, audio, y, idx, sd0, bank_v, bank_a, torch.float32)
+    ref64 = _oracle(video, audio, y, idx, sd0, bank_v, bank_a, torch.float64)
+    torch.cuda.empty_cache()
+
+    model = models.av_wrapper('R2Plus1D', {'depth': 18}, 'Conv2D', {'depth': 10}, proj_dim=[512, 512, 128])
+    model.load_state_dict(sd0)
+    model.video_model.math = model.audio_model.math = _MATH["bf16x3"]
+    model = model.to(DEV).train()
+    crit = AVID(num_data=N, embedding_dim=128, num_negatives=K, momentum=0.5, xModal_coeff=1., wModal_coeff=0., device=0)
+    crit.nce_average.view1_mem.copy_(bank_v)
+    crit.nce_average.view2_mem.copy_(bank_a)
+    crit.nce_average.sample_negatives = lambda y_, K_: idx.to(DEV)
+    ve, ae = model(video.to(DEV), audio.to(DEV))
+    loss, log = crit(ve, ae, y.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+
+    tol = 1e-3       # north-star tolerance
+    for name, ref in (("fp32 oracle on the GPU (TF32 off)", ref32), ("fp64 oracle", ref64)):
+        assert _rel(ve, ref["ve"]) < tol and _rel(ae, ref["ae"]) < tol, (name, _rel(ve, ref["ve"]), _rel(ae, ref["ae"]))
+        np.testing.assert_allclose(float(loss), ref["loss"], rtol=tol, err_msg=name)
+        np.testing.assert_allclose(float(log["Loss/v2a"]), ref["v2a"], rtol=tol, err_msg=name)
+        np.testing.assert_allclose(float(crit.criterion.avg_exp_score), ref["Z"], rtol=tol, err_msg=name)
+        assert _rel(crit.nce_average.view1_mem[y.to(DEV)], ref["rows_v"]) < tol, name
+        assert _rel(crit.nce_average.view2_mem[y.to(DEV)], ref["rows_a"]) < tol, name
+    # the arithmetic is reference-grade: no further from the fp64 truth than a few times the fp32 reference's own rounding
+    assert _rel(ve, ref64["ve"]) < max(1e-4, 8 * _rel(ref32["ve"], ref64["ve"]))
+    assert _rel(ae, ref64["ae"]) < max(1e-4, 8 * _rel(ref32["ae"], ref64["ae"]))
+    # gradients (against fp64): head / late layers tightly, the first 64-channel layer within the ReLU-gate-flip budget of
+    # tests/test_towers_gpu.py (the fp32 oracle's own distance from fp64 is the yardstick)
+    params = dict(model.named_parameters())
+    for k, want in ref64["grads"].items():
+        own = _rel(ref32["grads"][k], want)
+        assert _rel(params[k].grad, want) < max(2e-3 if "conv2x" not in k else 2e-2, 8 * own), (k, _rel(params[k].grad, want), own)
