@@ -245,3 +245,71 @@ def test_sharded_bank_nccl_world2():
         _run("nccl")
     finally:
         os.environ.pop("AVID_SHARD_BANK", None)
+
+
+# ---------------------------------------------------------------------------------------------- in-kernel sampler across ranks
+def _philox_worker(rank, world, port, q):
+    """No injected negatives: both layouts draw inside the kernel from the Philox stream whose seed rank 0 broadcasts.  Each rank
+    deliberately has a DIFFERENT default-generator seed (what mp.spawn workers get when only the parent was seeded)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from oracle import synth
+        from avid_cma_b200.criterions import AVID
+        torch.manual_seed(1000 + 17 * rank)
+        n_rows, k_neg, b = 5000, 256, 8
+        crits = {}
+        for mode in ("sharded", "replicated"):
+            os.environ["AVID_SHARD_BANK"] = "1" if mode == "sharded" else "0"
+            crits[mode] = AVID(num_data=n_rows, embedding_dim=128, num_negatives=k_neg, momentum=0.5, xModal_coeff=1., wModal_coeff=1., device=rank)
+        bs, br = crits["sharded"].nce_average, crits["replicated"].nce_average
+        assert bs.sharded and not br.sharded and bs._seed == br._seed
+        seeds = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(seeds, torch.tensor([bs._seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev))
+        assert len({int(s) for s in seeds}) == 1, "ranks disagree on the Philox seed"
+        assert torch.equal(bs.view1_mem, br.view1_mem[bs.row_begin:bs.row_end])       # per-row seeded init: same rows, no broadcast
+        worst = 0.0
+        for step in range(3):
+            ev, ea = synth.embeddings(b, seed=10 * step + rank)
+            y = synth.instance_ids(world * b, n_rows, seed=step)[rank * b:(rank + 1) * b].to(dev)
+            res = {}
+            for mode, crit in crits.items():
+                v, a = ev.to(dev).requires_grad_(True), ea.to(dev).requires_grad_(True)
+                loss, _ = crit(v, a, y)
+                loss.backward()
+                res[mode] = (loss.detach().double(), v.grad.double(), a.grad.double())
+            worst = max(worst, float((res["sharded"][0] - res["replicated"][0]).abs() / res["replicated"][0].abs()))
+            for i in (1, 2):
+                worst = max(worst, float((res["sharded"][i] - res["replicated"][i]).norm() / res["replicated"][i].norm()))
+            worst = max(worst, float((bs.view1_mem.double() - br.view1_mem[bs.row_begin:bs.row_end].double()).norm() / br.view1_mem.double().norm()))
+            worst = max(worst, abs(float(crits["sharded"].criterion.avg_exp_score) - float(crits["replicated"].criterion.avg_exp_score)))
+        q.put((rank, worst, None))
+    except Exception:   # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    finally:
+        os.environ.pop("AVID_SHARD_BANK", None)
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_equals_replicated_with_in_kernel_sampler_nccl_world2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_philox_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, worst, err in results:
+        assert err is None, f"rank {rank}:\n{err}"
+        assert worst < 1e-5, (rank, worst)
