@@ -261,7 +261,9 @@ def nce_forward_backward(args, workspace):
     e0 = _t0()
     nb = len({args.keys[i].bank for i in range(args.num_keys)})
     check(_lib.lib().avid_nce_forward_backward(C.byref(args), _p(workspace, torch.uint8), workspace.numel(), _stream()))
-    _t1(e0, "nce_fused", float(nb * args.batch * (args.num_neg + 1 + args.pos_k) * 512))   # bytes: SURVEY.md §8d
+    # bytes: every scored row is read once; a shard holds (row_end - row_begin) / num_rows of the rows of every query
+    held = (args.row_end - args.row_begin) / float(args.num_rows)
+    _t1(e0, "nce_fused", float(nb * args.batch * (args.num_neg + 1 + args.pos_k) * 512) * held)
 
 
 def nce_finalize(args, workspace):

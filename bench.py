@@ -245,15 +245,26 @@ def sub_record(name, crit, net, opt, resident, a, world, rank, dev, rows):
     from avid_cma_b200 import ops
     B = a.batch
     perm = torch.randperm(rows, generator=torch.Generator().manual_seed(11))
-    n_total = 3 + a.sub_steps
-    ys = [perm[(i * world + rank) * B % (rows - B):][:B].contiguous().to(dev) for i in range(n_total)]
+    ys = [perm[(i * world + rank) * B % (rows - B):][:B].contiguous().to(dev) for i in range(3 + a.sub_steps + 3)]
 
-    def step(i):
+    marks = []          # (forward+criterion start, criterion start, criterion end, step end) CUDA events of the timed steps
+
+    def step(i, timed=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        if timed:
+            ev[0].record()
         ve, ae = net(*resident[i % len(resident)])
+        if timed:
+            ev[1].record()
         loss, _ = crit(ve, ae, ys[i])
+        if timed:
+            ev[2].record()
         opt.zero_grad()
         loss.backward()
         opt.step()
+        if timed:
+            ev[3].record()
+            marks.append(ev)
         return loss
 
     for i in range(3):
@@ -261,24 +272,31 @@ def sub_record(name, crit, net, opt, resident, a, world, rank, dev, rows):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ops.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(3, n_total):
-        loss = step(i)
+    for i in range(3, 3 + a.sub_steps):
+        loss = step(i, timed=True)
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    prof = ops.profile_end()
     ms, = _max_over_ranks([e0.elapsed_time(e1)], dev, world)
+    crit_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks)
+    fwd_ms = sum(m[0].elapsed_time(m[1]) for m in marks) / len(marks)
+    bwd_ms = sum(m[2].elapsed_time(m[3]) for m in marks) / len(marks)
+    # three more steps with a CUDA-event pair around the fused criterion launch (not part of the timed region: per-launch events
+    # switch the towers' CUDA graphs off)
+    ops.profile_begin()
+    for i in range(3 + a.sub_steps, 3 + a.sub_steps + 3):
+        step(i)
+    prof = ops.profile_end()
     nce = [(w, d) for n_, w, d in prof if n_ == "nce_fused"]
     rec = {"clips_per_s": B * world * a.sub_steps / (ms * 1e-3), "ms_per_step": ms / a.sub_steps, "steps": a.sub_steps, "warmup": 3,
-           "last_loss": float(loss)}
+           "last_loss": float(loss.detach()), "ms_towers_forward": fwd_ms, "ms_criterion": crit_ms, "ms_backward_optimizer": bwd_ms}
     if nce:
         rec["nce_GBps_per_gpu"] = sum(w for w, _ in nce) / (sum(d for _, d in nce) * 1e-3) / 1e9
         rec["nce_us_per_launch"] = 1e3 * sum(d for _, d in nce) / len(nce)
-        rec["nce_algorithmic_bytes_per_launch"] = nce[0][0]
+        rec["nce_algorithmic_bytes_per_launch_per_gpu"] = nce[0][0]
     return rec
 
 
