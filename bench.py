@@ -426,13 +426,14 @@ def run_ours(a):
     sampler.start()
     ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.nvtx.range_push("avid_timed")           # ncu --nvtx --nvtx-include "avid_timed/": the launch list of steady-state steps
+    nvtx_id = torch.cuda.nvtx.range_start("avid_timed")   # ncu --nvtx --nvtx-include "avid_timed": steady-state steps (a start/end range
+    #                                                       spans threads: the backward kernels are launched by autograd's worker thread)
     e0.record()
     for _ in range(a.steps):
         step(*resident[it % nbuf], ys_dev[it]); it += 1
     e1.record()
     barrier()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_end(nvtx_id)
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count()
     clocks = sampler.summary()
@@ -574,11 +575,11 @@ def run_ours(a):
         mma_factor = 3 if a.math == "bf16x3" and top != "conv_igemm_kernel" else 1
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of this kernel from the committed ncu pass of the same command (profiles/)
-            prof_k = json.load(open(os.path.join(ROOT, "profiles", "r1_%s_kernels.json" % a.math)))["kernels"]
+            prof_k = json.load(open(os.path.join(ROOT, "profiles", "r2_%s_kernels.json" % a.math)))["kernels"]
             rows = [r for r in prof_k if top in r["kernel"]]
             n_l = sum(r["launches_per_step"] for r in rows)
             traffic = sum((r["dram_read_MB_per_launch"] + r["dram_write_MB_per_launch"]) * 1e6 * r["launches_per_step"] for r in rows) / n_l
-            traffic_src = "profiles/r1_%s_kernels.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)" % a.math
+            traffic_src = "profiles/r2_%s_kernels.json (steady-state ncu launch list of this command: dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)" % a.math
         except Exception:
             pass
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
@@ -597,7 +598,7 @@ def run_ours(a):
             hbm = peaks.get("hbm_gbs", 6650.0)
             roofline["nce"] = {"kernel": "nce_gather_kernel (one launch: gather + score + NCE + gradient + reduce)", "bound": "hbm", "achieved": w_ / (d_ * 1e-3) / 1e9,
                                "peak": hbm, "unit": "GB/s", "frac": w_ / (d_ * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_launch": w_ / c_,
-                               "sweep": "profiles/r1_nce_sweep_2M_fused.json (K = 256..16384: 0.09 .. 0.77 of measured HBM)"}
+                               "sweep": "profiles/r2_nce_sweep.json (2 M-row banks, K = 256 / 1024 / 4096 / 16384: 0.10 / 0.28 / 0.54 / 0.76 of measured HBM)"}
 
     line = {"metric": METRIC, "value": clips / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
