@@ -1,0 +1,381 @@
+// 64 -> 64 channel 1x3x3 stride-1 convolutions (forward and input gradient) on CTA PAIRS: tcgen05.mma.cta_group::2, halo tile,
+// shared-memory-resident filter.  These are the layers of the 64-channel stage (video conv2x: 8 x 56 x 56 pixels per clip, audio
+// block1): 41 % of the video FLOPs at the smallest N the tensor core sees.
+//
+// Why (round-2 measurements, scripts/probes/umma_fetch.cu + ncu): an SS-mode MMA reads its operands from shared memory at 128 B/clk,
+// whatever the swizzle mode; M128 x N64 x K16 reads 6 KB for 32 cycles of math, so the 64-channel kernels are SHARED-MEMORY-bandwidth
+// bound, and the TMA writes of their operands share that bandwidth.  conv_tc_kernel<64> writes 48 KB per 64-channel k-block (each
+// activation tile once PER TAP through im2col TMA, the filter tile once per pixel tile) and reads 56 KB: 104 KB per 384 cycles of
+// math = the measured 47-51 % tensor-pipe activity.  Here
+//   * the activation tile is written ONCE per plane: a strip of R rows x (W + 2) pixels x 64 channels (zero padding by TMA) whose
+//     128 MMA rows are 128 CONSECUTIVE strip pixels; tap (dh, dw) is the same strip shifted by dh * (W + 2) + dw pixels, i.e. an
+//     operand descriptor that starts dh * (W + 2) + dw rows of 128 bytes later -- inside a 1024-byte swizzle atom (verified:
+//     scripts/probes/halo_desc.cu, the swizzle is a function of the absolute shared-memory address);
+//   * the filter stays resident: a CTA pair splits the N = 64 filter rows, 32 rows x 9 taps x 2 planes = 72 KB per CTA, loaded once
+//     per launch (scripts/probes/pair_mma.cu shows the cta_group::2 protocol);
+//   * bf16x3 as THREE M256 x N64 MMAs per k-step (A_hi B_hi, A_hi B_lo, A_lo B_hi) into one accumulator, ordered in two phases
+//     per tile (all taps of the hi plane, then all taps of the lo plane) so that three plane slots pipeline the loads.
+// Per k-step and SM: 15 KB read + ~2.5 KB written for 96 cycles of math.  The two CTAs of a pair work on the same strip position
+// of two consecutive frames, so one A descriptor serves both.  Columns 0 and W + 1 of the strip are padding: their MMA rows are
+// computed and dropped (W / (W + 2) efficiency), as are the rows past the end of a frame.
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace avid {
+using namespace tc;
+
+constexpr int kPairThreads = 320;     // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer (leader CTA), warps 2-9: epilogue
+constexpr int kPairSlots = 3;         // activation plane slots
+constexpr int kPairBN = 64;
+constexpr int kPairBBytes = 9 * 2 * 32 * 128;          // [tap][plane][32 filter rows][64 k] bf16: 72 KB per CTA
+constexpr int kPairStgLd = 20;
+constexpr int kPairStgBytes = 8 * 32 * kPairStgLd * 4;
+constexpr int kPairMaxSlot = 45056;
+
+struct PairParams {
+    int frames, T, H, W, Wp;          // N * T frames of H x W pixels; strip pitch Wp = W + 2
+    int tiles_per_frame, num_pairs;   // 128-pixel strip tiles per frame; (frame pairs) x (tiles per frame)
+    int slot_bytes;                   // pitch of the plane slots: R rows x Wp pixels x 128 B rounded up to 1 KB
+    int slot_bytes_tx;                // bytes one strip load delivers (R * Wp * 128)
+    uint32_t taps[9];                 // (dw + 1) | (dh + 1) << 8 | filter tap << 24
+    int x3;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of a CTA pair: executed by both CTAs, the transaction bytes update the barrier of CTA 0 (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db),
+                 "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at this offset in CTA 0 of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const PairParams p,
+                 const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats, const BnBwdFuse fuse) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_smem = smem;                                        // resident filter half: [tap][plane][32 rows][64 k]
+    uint8_t* ring = smem + kPairBBytes;                            // [3 slots] activation plane strips
+    float4* s_par = reinterpret_cast<float4*>(ring + kPairSlots * p.slot_bytes);
+    float* s_stage = reinterpret_cast<float*>(ring + kPairSlots * p.slot_bytes + kPairBN * 16);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + kPairSlots * p.slot_bytes + kPairBN * 16 + kPairStgBytes);
+    uint64_t* a_empty = a_full + kPairSlots;
+    uint64_t* w_full = a_empty + kPairSlots;
+    uint64_t* tmem_full = w_full + 1;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int planes = p.x3 ? 2 : 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a_hi);
+        prefetch_tensormap(&map_b_hi);
+        for (int s = 0; s < kPairSlots; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        mbar_init(w_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 16);     // one arrive per epilogue warp of BOTH CTAs (on the leader's barrier)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * kPairBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                     // both CTAs' barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs): this CTA's half of the filter once, then its plane strips =====
+        if (rank == 0) mbar_expect_tx(w_full, 2u * (uint32_t)(9 * planes * 4096));
+        for (int t = 0; t < 9; ++t) {
+            const int ftap = p.taps[t] >> 24;
+            for (int pl = 0; pl < planes; ++pl)
+                tma_load_2d_pair(b_smem + (t * 2 + pl) * 4096, pl ? &map_b_lo : &map_b_hi, w_full, 0, ftap * kPairBN + (int)rank * 32);
+        }
+        int n_load = 0;      // plane loads issued so far: load j goes to slot j % 3
+        for (int pr = cluster_id; pr < p.num_pairs; pr += num_clusters) {
+            const int g = pr / p.tiles_per_frame, i = pr - g * p.tiles_per_frame;
+            int f = 2 * g + (int)rank;
+            if (f >= p.frames) f = p.frames - 1;             // odd frame count: the last pair's second CTA recomputes a tile and stores nothing
+            const int r0 = (128 * i) / p.Wp;
+            for (int pl = 0; pl < planes; ++pl, ++n_load) {
+                const int slot = n_load % kPairSlots;
+                mbar_wait(&a_empty[slot], ((n_load / kPairSlots) & 1) ^ 1);
+                if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * (uint32_t)p.slot_bytes_tx);
+                tma_load_5d_pair(ring + slot * p.slot_bytes, pl ? &map_a_lo : &map_a_hi, &a_full[slot], 0, -1, r0 - 1, f % p.T, f / p.T);
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===== MMA issuer (leader CTA) =====
+        constexpr uint32_t idesc = make_idesc_bf16(256, kPairBN, 0, 0);
+        const uint64_t ring_desc = make_smem_desc_sw128(smem_u32(ring), 16, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        int n_use = 0, it = 0;
+        for (int pr = cluster_id; pr < p.num_pairs; pr += num_clusters, ++it) {
+            const int i = pr % p.tiles_per_frame;
+            const int s0 = 128 * i;
+            const int l0 = s0 - (s0 / p.Wp - 1) * p.Wp;           // strip pixel of MMA row 0 inside the slot (tap (0, 0))
+            const int buf = it & 1;
+            mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * kPairBN;
+            for (int pl = 0; pl < planes; ++pl, ++n_use) {
+                const int slot = n_use % kPairSlots;
+                mbar_wait(&a_full[slot], (n_use / kPairSlots) & 1);
+                tc_fence_after();
+                const uint64_t a_slot = ring_desc + (uint32_t)((slot * p.slot_bytes) >> 4);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t tp = p.taps[t];
+                    const int shift = l0 + ((int)((tp >> 8) & 0xFF) - 1) * p.Wp + ((int)(tp & 0xFF) - 1);      // >= -1
+                    const uint64_t da = a_slot + (uint64_t)(int64_t)(shift * 8);                                // 128 bytes per strip pixel = 8 encoded units
+                    const uint64_t db = b_desc + (uint32_t)((t * 2 * 4096) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (pl == 0) {
+                            umma_bf16_pair(acc, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);                   // hi * hi
+                            if (p.x3) umma_bf16_pair(acc, da + 2 * k, db + 256 + 2 * k, idesc, 1);              // hi * lo
+                        } else {
+                            umma_bf16_pair(acc, da + 2 * k, db + 2 * k, idesc, 1);                              // lo * hi
+                        }
+                    }
+                }
+                umma_commit_pair(&a_empty[slot]);       // both producers may refill the slot once these MMAs have read it
+            }
+            umma_commit_pair(&tmem_full[buf]);          // accumulator complete: both CTAs' epilogues
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue (both CTAs): the same transposing epilogue as conv_tc_kernel -- TMEM -> registers -> per-warp staging -> coalesced
+        //       64-byte segments, optional addend, BatchNorm statistics / fused BatchNorm-backward sums kept in registers =====
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int hsel = (warp - 2) >> 2;           // which 32 columns of the 64
+        float* const stg = s_stage + (warp - 2) * (32 * kPairStgLd);
+        const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+        double* const acc_out = stats ? stats : fuse.sums;
+        if (fuse.z) {
+            const int t = threadIdx.x - 64;
+            if (t < kPairBN) s_par[t] = make_float4(__ldg(fuse.mean + t), __ldg(fuse.invstd + t), __ldg(fuse.gamma + t), __ldg(fuse.beta + t));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        float run1[2][4], run2[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) run1[b][t] = run2[b][t] = 0.f;
+        int it = 0;
+        for (int pr = cluster_id; pr < p.num_pairs; pr += num_clusters, ++it) {
+            const int buf = it & 1;
+            const int g = pr / p.tiles_per_frame, i = pr - g * p.tiles_per_frame;
+            const int f = 2 * g + (int)rank;
+            const int s = 128 * i + q * 32 + lane;          // strip pixel of this thread's accumulator row
+            const int h = s / p.Wp, c = s - h * p.Wp;
+            const bool valid = f < p.frames && h < p.H && c >= 1 && c <= p.W;
+            const unsigned long long my_row = valid ? (unsigned long long)(((size_t)f * p.H + h) * p.W + (c - 1)) * kPairBN : ~0ull;
+            unsigned long long rows4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rows4[j] = __shfl_sync(0xffffffffu, my_row, j * 8 + r8);
+            mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
+            tc_fence_after();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {            // 16-column half-chunks of this warp's 32 columns
+                const int col = hsel * 32 + hh * 16;
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tmem_base + buf * kPairBN + ((uint32_t)(q * 32) << 16) + col, r);
+                float4 ad[4], zz[4];
+                if (addend) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        ad[j] = rows4[j] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4[j] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (fuse.z) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        zz[j] = rows4[j] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[j] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                tmem_ld_wait();
+                if (hh == 1) {          // this warp's part of the accumulator is in registers: hand the TMEM buffer back to the leader
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+                }
+                float4* const srow = reinterpret_cast<float4*>(stg + lane * kPairStgLd);
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    srow[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                __syncwarp();
+                float4 par[4];
+                if (fuse.z) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) par[t] = s_par[col + c4 + t];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + r8) * kPairStgLd + c4);
+                    if (rows4[j] == ~0ull) continue;
+                    if (addend) { o.x += ad[j].x; o.y += ad[j].y; o.z += ad[j].z; o.w += ad[j].w; }
+                    *reinterpret_cast<float4*>(out + rows4[j] + col + c4) = o;
+                    if (acc_out) {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+                        if (fuse.z) {
+                            const float zv[4] = {zz[j].x, zz[j].y, zz[j].z, zz[j].w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float xh = (zv[t] - par[t].x) * par[t].y;
+                                const float gg = fmaf(xh, par[t].z, par[t].w) > 0.f ? ov[t] : 0.f;
+                                run1[hh][t] += gg;
+                                run2[hh][t] = fmaf(gg, xh, run2[hh][t]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                run1[hh][t] += ov[t];
+                                run2[hh][t] = fmaf(ov[t], ov[t], run2[hh][t]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (acc_out) {
+            float* const s_red = s_stage;           // [4 quarters][2 sums][64]
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float a = run1[hh][t], b = run2[hh][t];
+#pragma unroll
+                    for (int o = 4; o <= 16; o <<= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        b += __shfl_xor_sync(0xffffffffu, b, o);
+                    }
+                    if (lane < 4) {
+                        const int col = hsel * 32 + hh * 16 + c4 + t;
+                        s_red[(q * 2 + 0) * kPairBN + col] = a;
+                        s_red[(q * 2 + 1) * kPairBN + col] = b;
+                    }
+                }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int t = threadIdx.x - 64;         // 0..255: (which sum, column) for t < 128
+            if (t < 2 * kPairBN) {
+                const int which = t / kPairBN, col = t - which * kPairBN;
+                const float tot = s_red[(0 * 2 + which) * kPairBN + col] + s_red[(1 * 2 + which) * kPairBN + col] + s_red[(2 * 2 + which) * kPairBN + col] +
+                                  s_red[(3 * 2 + which) * kPairBN + col];
+                atomicAdd(acc_out + (size_t)which * kPairBN + col, (double)tot);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                     // no CTA frees its half of the pair's TMEM while the other may still use it
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kPairBN) : "memory");
+}
+
+// the layers this kernel takes: 1 x 3 x 3, stride 1, padding (0, 1, 1), 64 -> 64 channels, both bf16 planes or hi only
+int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* addend,
+                  float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
+    static const bool enabled = [] { const char* e = getenv("AVID_CONV_PAIR"); return !(e && atoi(e) == 0); }();
+    if (!enabled) return AVID_EUNSUPPORTED;
+    if (!(s->kt == 1 && s->kh == 3 && s->kw == 3 && s->st == 1 && s->sh == 1 && s->sw == 1 && s->pt == 0 && s->ph == 1 && s->pw == 1 && s->ci == 64 &&
+          s->co == 64))
+        return AVID_EUNSUPPORTED;
+    PairParams p;
+    p.frames = s->n * s->ti;  p.T = s->ti;  p.H = s->hi;  p.W = s->wi;  p.Wp = s->wi + 2;
+    if (p.Wp > 256 || p.frames < 2) return AVID_EUNSUPPORTED;
+    const int rows = (p.Wp + 126) / p.Wp + 3;              // input rows a 128-pixel strip tile can touch
+    const int slot_tx = rows * p.Wp * 128;
+    p.slot_bytes = (slot_tx + 1023) & ~1023;
+    if (p.slot_bytes > kPairMaxSlot || rows > 256) return AVID_EUNSUPPORTED;
+    p.slot_bytes_tx = slot_tx;
+    p.tiles_per_frame = (p.H * p.Wp + 127) / 128;
+    p.num_pairs = ((p.frames + 1) / 2) * p.tiles_per_frame;
+    p.x3 = a_lo != nullptr;
+    for (int dh = 0; dh < 3; ++dh)
+        for (int dw = 0; dw < 3; ++dw) {
+            // forward: output (h, w) reads input (h + dh - 1, w + dw - 1) with filter tap (dh, dw); input gradient: din(h, w) reads
+            // dout(h + dh - 1, w + dw - 1) with the mirrored tap (2 - dh, 2 - dw)
+            const int ftap = dgrad ? (2 - dh) * 3 + (2 - dw) : dh * 3 + dw;
+            p.taps[dh * 3 + dw] = (uint32_t)dw | ((uint32_t)dh << 8) | ((uint32_t)ftap << 24);
+        }
+    const TensorMapApi& api = tensor_map_api();
+    if (!api.ok) { set_error("conv_pair: cuTensorMapEncode* driver entry points unavailable"); return AVID_ECUDA; }
+    CUtensorMap maps[4];
+    const void* planes_a[2] = {a_hi, a_lo ? a_lo : a_hi};
+    const void* planes_b[2] = {b_hi, b_lo ? b_lo : b_hi};
+    for (int pl = 0; pl < 2; ++pl) {
+        // activations [N][T][H][W][64] bf16: one box = the whole strip of a tile [rows][Wp][64 channels], zero-filled outside the frame
+        cuuint64_t dims[5] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.T, (cuuint64_t)s->n};
+        cuuint64_t strides[4] = {128, (cuuint64_t)p.W * 128, (cuuint64_t)p.H * p.W * 128, (cuuint64_t)p.T * p.H * p.W * 128};
+        cuuint32_t box[5] = {64, (cuuint32_t)p.Wp, (cuuint32_t)rows, 1, 1};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = api.tiled(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(planes_a[pl]), dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_pair: cuTensorMapEncodeTiled (activations) failed (%d)", (int)r); return AVID_ECUDA; }
+        // filter planes [9 taps * 64 rows][64 k]: boxes of 32 rows (this CTA's half of N)
+        cuuint64_t bdims[2] = {64, 9 * 64};
+        cuuint64_t bstr[1] = {128};
+        cuuint32_t bbox[2] = {64, 32}, bes[2] = {1, 1};
+        r = api.tiled(&maps[2 + pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(planes_b[pl]), bdims, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_pair: cuTensorMapEncodeTiled (filter) failed (%d)", (int)r); return AVID_ECUDA; }
+    }
+    const int smem = 1024 + kPairBBytes + kPairSlots * p.slot_bytes + kPairBN * 16 + kPairStgBytes + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) { set_error("conv_pair: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
+        configured = true;
+    }
+    if (smem > 232448) return AVID_EUNSUPPORTED;
+    int clusters = kNumSMs / 2;
+    if (clusters > p.num_pairs) clusters = p.num_pairs;
+    conv_pair_kernel<<<2 * clusters, kPairThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
+    return check_launch("conv_pair_kernel");
+}
+
+}  // namespace avid

@@ -43,6 +43,11 @@ const TensorMapApi& tensor_map_api() {
 
 using namespace tc;
 
+// conv_pair.cu: 64 -> 64 channel 1x3x3 stride-1 layers on CTA pairs (halo tile + resident filter); returns AVID_EUNSUPPORTED when the
+// geometry is not its case
+int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* addend,
+                  float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st);
+
 constexpr int kBM = 128;        // output pixels per CTA (UMMA M)
 constexpr int kBK = 64;         // channels per k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int kTcThreads = 192; // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
@@ -66,18 +71,6 @@ struct TcConvParams {
     int Td, Hd, Wd, ot, oh, ow, rt, rh, rw;
     int debug;                      // AVID_TC_DEBUG probe bits (scripts/probe_conv.py; 0 in production): 1 no global stores, 2 no
                                     // statistics, 4 epilogue only hands the accumulator back, 8 no MMAs, 64 no per-tile atomics
-};
-
-// Optional fusion of the NEXT BatchNorm backward's reduction into an input-gradient launch: the tensor this launch writes is
-// the gradient dy at the ReLU output of the previous layer, whose BatchNorm backward needs sum(g) and sum(g * xhat) per
-// channel with g = dy * relu'(bn(z)), xhat = (z - mean) * invstd (z = that layer's conv output, same shape as dy).
-struct BnBwdFuse {
-    const float* z = nullptr;
-    const float* mean = nullptr;
-    const float* invstd = nullptr;
-    const float* gamma = nullptr;
-    const float* beta = nullptr;
-    double* sums = nullptr;          // (2, channels) doubles, zeroed by the caller
 };
 
 template <int BN>
@@ -717,6 +710,9 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     const int taps_total = s->kt * s->kh * s->kw;
     const bool x3 = a_lo != nullptr;
     int rc;
+    // the 64 -> 64 channel 1x3x3 stride-1 layers (forward and input gradient) run on CTA pairs with a halo tile and a resident filter
+    rc = conv_pair_run(s, dgrad, a_hi, a_lo, b_hi, b_lo, addend, out, stats, fuse, st);
+    if (rc != AVID_EUNSUPPORTED) return rc;
     CUtensorMap map_b[2];
     if ((rc = encode_tiled_2d(&map_b[0], b_hi, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
     map_b[1] = map_b[0];

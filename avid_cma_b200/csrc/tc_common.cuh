@@ -180,6 +180,18 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
 
 }  // namespace tc
 
+// Optional fusion of the NEXT BatchNorm backward's reduction into an input-gradient launch: the tensor this launch writes is
+// the gradient dy at the ReLU output of the previous layer, whose BatchNorm backward needs sum(g) and sum(g * xhat) per
+// channel with g = dy * relu'(bn(z)), xhat = (z - mean) * invstd (z = that layer's conv output, same shape as dy).
+struct BnBwdFuse {
+    const float* z = nullptr;
+    const float* mean = nullptr;
+    const float* invstd = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    double* sums = nullptr;          // (2, channels) doubles, zeroed by the caller
+};
+
 // ---- host: tensor-map encoding through the driver entry points (no link-time libcuda dependency) ----
 struct TensorMapApi {
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
