@@ -18,6 +18,7 @@
 // Per k-step and SM: 15 KB read + ~2.5 KB written for 96 cycles of math.  The two CTAs of a pair work on the same strip position
 // of two consecutive frames, so one A descriptor serves both.  Columns 0 and W + 1 of the strip are padding: their MMA rows are
 // computed and dropped (W / (W + 2) efficiency), as are the rows past the end of a frame.
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -39,7 +40,10 @@ struct PairParams {
     int slot_bytes;                   // pitch of the plane slots: R rows x Wp pixels x 128 B rounded up to 1 KB
     int slot_bytes_tx;                // bytes one strip load delivers (R * Wp * 128)
     uint32_t taps[9];                 // (dw + 1) | (dh + 1) << 8 | filter tap << 24
+    int tap_shift8[9];                // ((dh - 1) * Wp + (dw - 1)) * 8: descriptor units (16 B) from the tile's first strip pixel to tap t's
     int x3;
+    int debug;                        // AVID_PAIR_DEBUG probe bits (scripts/probe_pair.py; 0 in production): 1 no epilogue stores, 8 no activation
+                                      // loads, 256 report the launch geometry
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -97,7 +101,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int planes = p.x3 ? 2 : 1;
@@ -124,7 +128,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __syncthreads();
     cluster_sync_all();                     // both CTAs' barriers exist before anything signals them
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): this CTA's half of the filter once, then its plane strips =====
@@ -135,7 +139,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 tma_load_2d_pair(b_smem + (t * 2 + pl) * 4096, pl ? &map_b_lo : &map_b_hi, w_full, 0, ftap * kPairBN + (int)rank * 32);
         }
         int n_load = 0;      // plane loads issued so far: load j goes to slot j % 3
-        for (int pr = cluster_id; pr < p.num_pairs; pr += num_clusters) {
+        for (int pr = cluster_id; pr < p.num_pairs && !(p.debug & 8); pr += num_clusters) {
             const int g = pr / p.tiles_per_frame, i = pr - g * p.tiles_per_frame;
             int f = 2 * g + (int)rank;
             if (f >= p.frames) f = p.frames - 1;             // odd frame count: the last pair's second CTA recomputes a tile and stores nothing
@@ -147,11 +151,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 tma_load_5d_pair(ring + slot * p.slot_bytes, pl ? &map_a_lo : &map_a_hi, &a_full[slot], 0, -1, r0 - 1, f % p.T, f / p.T);
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
-        // ===== MMA issuer (leader CTA) =====
+    } else if (warp == 1 && rank == 0) {
+        // ===== MMA issuer (leader CTA).  The WHOLE warp walks the loop (waits included) and one elected lane issues: every operand of
+        //       the MMAs is then provably warp-uniform and lives in uniform registers -- issued from `if (lane == 0)` each UTCHMMA sat in
+        //       an ELECT / R2UR.BROADCAST waterfall over spilled 64-bit descriptors (119 cycles per MMA measured for 32 of math) =====
         constexpr uint32_t idesc = make_idesc_bf16(256, kPairBN, 0, 0);
-        const uint64_t ring_desc = make_smem_desc_sw128(smem_u32(ring), 16, 1024);
-        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);
+        constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
+        const uint32_t ring_lo = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);            // start address, LBO 16 B
+        const uint32_t b_lo = ((smem_u32(b_smem) >> 4) & 0x3FFF) | (1u << 16);
         mbar_wait(w_full, 0);
         tc_fence_after();
         int n_use = 0, it = 0;
@@ -165,28 +172,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const uint32_t acc = tmem_base + buf * kPairBN;
             for (int pl = 0; pl < planes; ++pl, ++n_use) {
                 const int slot = n_use % kPairSlots;
-                mbar_wait(&a_full[slot], (n_use / kPairSlots) & 1);
+                if (!(p.debug & 8)) mbar_wait(&a_full[slot], (n_use / kPairSlots) & 1);
                 tc_fence_after();
-                const uint64_t a_slot = ring_desc + (uint32_t)((slot * p.slot_bytes) >> 4);
+                const uint32_t a_lo32 = ring_lo + (uint32_t)((slot * p.slot_bytes) >> 4) + (uint32_t)(l0 * 8);      // 128 bytes per strip pixel = 8 units
+                if (elect_one()) {
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const uint32_t tp = p.taps[t];
-                    const int shift = l0 + ((int)((tp >> 8) & 0xFF) - 1) * p.Wp + ((int)(tp & 0xFF) - 1);      // >= -1
-                    const uint64_t da = a_slot + (uint64_t)(int64_t)(shift * 8);                                // 128 bytes per strip pixel = 8 encoded units
-                    const uint64_t db = b_desc + (uint32_t)((t * 2 * 4096) >> 4);
+                    for (int t = 0; t < 9; ++t) {
+                        const uint32_t at = a_lo32 + (uint32_t)p.tap_shift8[t];
+                        const uint32_t bt = b_lo + (uint32_t)(t * ((2 * 4096) >> 4));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (pl == 0) {
-                            umma_bf16_pair(acc, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);                   // hi * hi
-                            if (p.x3) umma_bf16_pair(acc, da + 2 * k, db + 256 + 2 * k, idesc, 1);              // hi * lo
-                        } else {
-                            umma_bf16_pair(acc, da + 2 * k, db + 2 * k, idesc, 1);                              // lo * hi
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (at + 2 * k);
+                            if (pl == 0) {
+                                umma_bf16_pair(acc, da, ((uint64_t)desc_hi << 32) | (bt + 2 * k), idesc, (t | k) != 0);                  // hi * hi
+                                if (p.x3) umma_bf16_pair(acc, da, ((uint64_t)desc_hi << 32) | (bt + 256 + 2 * k), idesc, 1);             // hi * lo
+                            } else {
+                                umma_bf16_pair(acc, da, ((uint64_t)desc_hi << 32) | (bt + 2 * k), idesc, 1);                             // lo * hi
+                            }
                         }
                     }
+                    umma_commit_pair(&a_empty[slot]);                              // both producers may refill the slot once these MMAs have read it
+                    if (pl == planes - 1) umma_commit_pair(&tmem_full[buf]);       // accumulator complete: both CTAs' epilogues
                 }
-                umma_commit_pair(&a_empty[slot]);       // both producers may refill the slot once these MMAs have read it
+                __syncwarp();
             }
-            umma_commit_pair(&tmem_full[buf]);          // accumulator complete: both CTAs' epilogues
         }
     } else if (warp >= 2) {
         // ===== epilogue (both CTAs): the same transposing epilogue as conv_tc_kernel -- TMEM -> registers -> per-warp staging -> coalesced
@@ -255,7 +264,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + r8) * kPairStgLd + c4);
-                    if (rows4[j] == ~0ull) continue;
+                    if (rows4[j] == ~0ull || (p.debug & 1)) continue;
                     if (addend) { o.x += ad[j].x; o.y += ad[j].y; o.z += ad[j].z; o.w += ad[j].w; }
                     *reinterpret_cast<float4*>(out + rows4[j] + col + c4) = o;
                     if (acc_out) {
@@ -335,12 +344,14 @@ int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const
     p.tiles_per_frame = (p.H * p.Wp + 127) / 128;
     p.num_pairs = ((p.frames + 1) / 2) * p.tiles_per_frame;
     p.x3 = a_lo != nullptr;
+    { const char* dbg = getenv("AVID_PAIR_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     for (int dh = 0; dh < 3; ++dh)
         for (int dw = 0; dw < 3; ++dw) {
             // forward: output (h, w) reads input (h + dh - 1, w + dw - 1) with filter tap (dh, dw); input gradient: din(h, w) reads
             // dout(h + dh - 1, w + dw - 1) with the mirrored tap (2 - dh, 2 - dw)
             const int ftap = dgrad ? (2 - dh) * 3 + (2 - dw) : dh * 3 + dw;
             p.taps[dh * 3 + dw] = (uint32_t)dw | ((uint32_t)dh << 8) | ((uint32_t)ftap << 24);
+            p.tap_shift8[dh * 3 + dw] = ((dh - 1) * p.Wp + (dw - 1)) * 8;
         }
     const TensorMapApi& api = tensor_map_api();
     if (!api.ok) { set_error("conv_pair: cuTensorMapEncode* driver entry points unavailable"); return AVID_ECUDA; }
@@ -374,6 +385,15 @@ int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const
     if (smem > 232448) return AVID_EUNSUPPORTED;
     int clusters = kNumSMs / 2;
     if (clusters > p.num_pairs) clusters = p.num_pairs;
+    if (p.debug & 256) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);  cfg.blockDim = dim3(kPairThreads);  cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at;  at.id = cudaLaunchAttributeClusterDimension;  at.val.clusterDim.x = 2;  at.val.clusterDim.y = 1;  at.val.clusterDim.z = 1;
+        cfg.attrs = &at;  cfg.numAttrs = 1;
+        int nc = -1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, conv_pair_kernel, &cfg);
+        printf("conv_pair: %d clusters launched, max active clusters %d (%s), smem %d, slot %d\n", clusters, nc, cudaGetErrorString(e), smem, p.slot_bytes);
+    }
     conv_pair_kernel<<<2 * clusters, kPairThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
     return check_launch("conv_pair_kernel");
 }

@@ -57,6 +57,14 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     }
 }
 
+// one lane of a fully active warp (elect.sync): ptxas then knows the guarded region runs on a single thread, so warp-uniform operands of
+// UTCHMMA / UTMALDG go through uniform registers instead of a per-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
