@@ -63,7 +63,7 @@ cma_scan_tc_kernel(const __grid_constant__ CUtensorMap map_qv, const __grid_cons
     uint64_t* tmem_empty = tmem_full + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     const bool use_v = p.mode != 3, use_a = p.mode != 2;
     const int nmod = (use_v ? 1 : 0) + (use_a ? 1 : 0);
     const int num_qtiles = (int)((p.num_queries + 127) / 128);
@@ -90,30 +90,38 @@ cma_scan_tc_kernel(const __grid_constant__ CUtensorMap map_qv, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
+    // producer and MMA issuer: whole warps walk the loops, one elected lane issues (uniform-register operands, no per-instruction
+    // ELECT / R2UR waterfall -- see conv_tc_kernel)
+    if (warp == 0) {
         // ===== TMA producer =====
         int stage = 0, phase = 0, it = 0;
         for (int qt = blockIdx.x; qt < num_qtiles; qt += gridDim.x, ++it) {
             if (it > 0) mbar_wait(q_free, (it - 1) & 1);            // the MMAs of the previous query tile have read it
-            mbar_expect_tx(q_full, (uint32_t)(nmod * 2 * kCmaBlk));
-            for (int m = 0; m < 2; ++m) {
-                if (!(m ? use_a : use_v)) continue;
-                for (int kb = 0; kb < 2; ++kb) tma_load_2d(q_smem + (m * 2 + kb) * kCmaBlk, m ? &map_qa : &map_qv, q_full, kb * 64, qt * 128);
+            if (elect_one()) {
+                mbar_expect_tx(q_full, (uint32_t)(nmod * 2 * kCmaBlk));
+                for (int m = 0; m < 2; ++m) {
+                    if (!(m ? use_a : use_v)) continue;
+                    for (int kb = 0; kb < 2; ++kb) tma_load_2d(q_smem + (m * 2 + kb) * kCmaBlk, m ? &map_qa : &map_qv, q_full, kb * 64, qt * 128);
+                }
             }
+            __syncwarp();
             for (int ct = 0; ct < num_ctiles; ++ct)
                 for (int m = 0; m < 2; ++m) {
                     if (!(m ? use_a : use_v)) continue;
                     for (int kb = 0; kb < 2; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)kCmaBlk);
-                        tma_load_2d(ring + stage * kCmaBlk, m ? &map_ca : &map_cv, &full_bar[stage], kb * 64, ct * 128);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)kCmaBlk);
+                            tma_load_2d(ring + stage * kCmaBlk, m ? &map_ca : &map_cv, &full_bar[stage], kb * 64, ct * 128);
+                        }
+                        __syncwarp();
                         if (++stage == kCmaStages) { stage = 0; phase ^= 1; }
                     }
                 }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer: D[query][candidate] += Q[query][k] * C[candidate][k]^T, M = N = 128, K = 16 per instruction =====
         constexpr uint32_t idesc = make_idesc_f16(128, 128);
         const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
@@ -139,15 +147,21 @@ cma_scan_tc_kernel(const __grid_constant__ CUtensorMap map_qv, const __grid_cons
                         tc_fence_after();
                         const uint64_t a = q_desc + (uint32_t)(((m * 2 + kb) * kCmaBlk) >> 4);
                         const uint64_t b = r_desc + (uint32_t)((stage * kCmaBlk) >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(acc, a + 2 * k, b + 2 * k, idesc, (kb | k) != 0);
-                        umma_commit(&empty_bar[stage]);
+                            for (int k = 0; k < 4; ++k) umma_bf16(acc, a + 2 * k, b + 2 * k, idesc, (kb | k) != 0);
+                            umma_commit(&empty_bar[stage]);
+                        }
+                        __syncwarp();
                         if (++stage == kCmaStages) { stage = 0; phase ^= 1; }
                     }
                 }
-                umma_commit(&tmem_full[buf]);
+                if (elect_one()) {
+                    umma_commit(&tmem_full[buf]);
+                    if (ct == num_ctiles - 1) umma_commit(q_free);
+                }
+                __syncwarp();
             }
-            umma_commit(q_free);
         }
     } else if (warp >= 2) {
         // ===== epilogue: one thread per query row keeps that query's running top-64 =====

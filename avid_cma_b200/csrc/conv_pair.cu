@@ -13,9 +13,12 @@
 //     scripts/probes/halo_desc.cu, the swizzle is a function of the absolute shared-memory address);
 //   * the filter stays resident: a CTA pair splits the N = 64 filter rows, 32 rows x 9 taps x 2 planes = 72 KB per CTA, loaded once
 //     per launch (scripts/probes/pair_mma.cu shows the cta_group::2 protocol);
-//   * bf16x3 as THREE M256 x N64 MMAs per k-step (A_hi B_hi, A_hi B_lo, A_lo B_hi) into one accumulator, ordered in two phases
-//     per tile (all taps of the hi plane, then all taps of the lo plane) so that three plane slots pipeline the loads.
-// Per k-step and SM: 15 KB read + ~2.5 KB written for 96 cycles of math.  The two CTAs of a pair work on the same strip position
+//   * bf16x3 as TWO MMAs per k-step: A_hi x [B_hi ; B_lo] is ONE M256 x N128 MMA (the hi and lo planes of a tap are adjacent in each
+//     CTA's filter half, so the pair's N = 128 columns come out as [hi*hi | hi*lo] of channels 0..31 from CTA 0 and of channels
+//     32..63 from CTA 1), A_lo x B_hi an M256 x N64 MMA into a third 64-column accumulator; the epilogue adds the three pieces.
+//     Ordered in two phases per tile (all taps of the hi plane, then all taps of the lo plane) so that three plane slots pipeline
+//     the loads.  An SM's shared memory serves A (4 KB), its own half of B and the half the peer reads, at 128 B/clk: 8 KB = 64
+//     cycles for the wide MMA (64 of math), 6 KB = 48 for the narrow one (32 of math); three N = 64 MMAs took 3 x 48.  The two CTAs of a pair work on the same strip position
 // of two consecutive frames, so one A descriptor serves both.  Columns 0 and W + 1 of the strip are padding: their MMA rows are
 // computed and dropped (W / (W + 2) efficiency), as are the rows past the end of a frame.
 #include <stdio.h>
@@ -29,6 +32,7 @@ using namespace tc;
 constexpr int kPairThreads = 320;     // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer (leader CTA), warps 2-9: epilogue
 constexpr int kPairSlots = 3;         // activation plane slots
 constexpr int kPairBN = 64;
+constexpr int kPairAcc = 192;          // TMEM columns of one accumulator buffer: [hi*hi | hi*lo] x 2 channel halves, then lo*hi
 constexpr int kPairBBytes = 9 * 2 * 32 * 128;          // [tap][plane][32 filter rows][64 k] bf16: 72 KB per CTA
 constexpr int kPairStgLd = 20;
 constexpr int kPairStgBytes = 8 * 32 * kPairStgLd * 4;
@@ -77,13 +81,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                  : "memory");
 }
-// arrive on the barrier at this offset in CTA 0 of the pair
+// arrive on the barrier at this offset in CTA 0 of the pair.  Default (.release.cta) semantics: the TMEM reads it publishes are ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync; `.release.cluster` compiled to MEMBAR.ALL.GPU and made every tile's hand-back
+// wait for the previous tile's global stores (ncu: 2.1 membar stalls per issued instruction, +100 us per launch)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
-        : "memory");
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+                 : "memory");
 }
 
+template <bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const PairParams p,
@@ -104,7 +110,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int planes = p.x3 ? 2 : 1;
+    constexpr int planes = X3 ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a_hi);
@@ -121,7 +127,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * kPairBN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -130,14 +136,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer (both CTAs): this CTA's half of the filter once, then its plane strips =====
-        if (rank == 0) mbar_expect_tx(w_full, 2u * (uint32_t)(9 * planes * 4096));
-        for (int t = 0; t < 9; ++t) {
-            const int ftap = p.taps[t] >> 24;
-            for (int pl = 0; pl < planes; ++pl)
-                tma_load_2d_pair(b_smem + (t * 2 + pl) * 4096, pl ? &map_b_lo : &map_b_hi, w_full, 0, ftap * kPairBN + (int)rank * 32);
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; whole warp, one elected lane issues): this CTA's half of the filter once, then its plane strips =====
+        if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(w_full, 2u * (uint32_t)(9 * planes * 4096));
+            for (int t = 0; t < 9; ++t) {
+                const int ftap = p.taps[t] >> 24;
+                for (int pl = 0; pl < planes; ++pl)
+                    tma_load_2d_pair(b_smem + (t * 2 + pl) * 4096, pl ? &map_b_lo : &map_b_hi, w_full, 0, ftap * kPairBN + (int)rank * 32);
+            }
         }
+        __syncwarp();
         int n_load = 0;      // plane loads issued so far: load j goes to slot j % 3
         for (int pr = cluster_id; pr < p.num_pairs && !(p.debug & 8); pr += num_clusters) {
             const int g = pr / p.tiles_per_frame, i = pr - g * p.tiles_per_frame;
@@ -147,15 +156,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int pl = 0; pl < planes; ++pl, ++n_load) {
                 const int slot = n_load % kPairSlots;
                 mbar_wait(&a_empty[slot], ((n_load / kPairSlots) & 1) ^ 1);
-                if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * (uint32_t)p.slot_bytes_tx);
-                tma_load_5d_pair(ring + slot * p.slot_bytes, pl ? &map_a_lo : &map_a_hi, &a_full[slot], 0, -1, r0 - 1, f % p.T, f / p.T);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * (uint32_t)p.slot_bytes_tx);
+                    tma_load_5d_pair(ring + slot * p.slot_bytes, pl ? &map_a_lo : &map_a_hi, &a_full[slot], 0, -1, r0 - 1, f % p.T, f / p.T);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1 && rank == 0) {
         // ===== MMA issuer (leader CTA).  The WHOLE warp walks the loop (waits included) and one elected lane issues: every operand of
         //       the MMAs is then provably warp-uniform and lives in uniform registers -- issued from `if (lane == 0)` each UTCHMMA sat in
         //       an ELECT / R2UR.BROADCAST waterfall over spilled 64-bit descriptors (119 cycles per MMA measured for 32 of math) =====
-        constexpr uint32_t idesc = make_idesc_bf16(256, kPairBN, 0, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(256, kPairBN, 0, 0), idesc2 = make_idesc_bf16(256, 2 * kPairBN, 0, 0);
         constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
         const uint32_t ring_lo = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);            // start address, LBO 16 B
         const uint32_t b_lo = ((smem_u32(b_smem) >> 4) & 0x3FFF) | (1u << 16);
@@ -169,7 +181,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const int buf = it & 1;
             mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t acc = tmem_base + buf * kPairBN;
+            const uint32_t acc = tmem_base + buf * kPairAcc;
+#pragma unroll
             for (int pl = 0; pl < planes; ++pl, ++n_use) {
                 const int slot = n_use % kPairSlots;
                 if (!(p.debug & 8)) mbar_wait(&a_full[slot], (n_use / kPairSlots) & 1);
@@ -182,13 +195,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                         const uint32_t bt = b_lo + (uint32_t)(t * ((2 * 4096) >> 4));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t da = ((uint64_t)desc_hi << 32) | (at + 2 * k);
-                            if (pl == 0) {
-                                umma_bf16_pair(acc, da, ((uint64_t)desc_hi << 32) | (bt + 2 * k), idesc, (t | k) != 0);                  // hi * hi
-                                if (p.x3) umma_bf16_pair(acc, da, ((uint64_t)desc_hi << 32) | (bt + 256 + 2 * k), idesc, 1);             // hi * lo
-                            } else {
-                                umma_bf16_pair(acc, da, ((uint64_t)desc_hi << 32) | (bt + 2 * k), idesc, 1);                             // lo * hi
-                            }
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (at + 2 * k), db = ((uint64_t)desc_hi << 32) | (bt + 2 * k);
+                            if (X3 && pl == 0) umma_bf16_pair(acc, da, db, idesc2, (t | k) != 0);           // hi * [hi ; lo] -> columns 0..127
+                            else umma_bf16_pair(acc + 128, da, db, idesc, (t | k) != 0);                    // lo * hi (or the single plane) -> 128..191
                         }
                     }
                     umma_commit_pair(&a_empty[slot]);                              // both producers may refill the slot once these MMAs have read it
@@ -229,11 +238,33 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int j = 0; j < 4; ++j) rows4[j] = __shfl_sync(0xffffffffu, my_row, j * 8 + r8);
             mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
+            // this warp's 32 columns of all accumulator pieces go to registers first and the TMEM buffer is handed back at once: the
+            // MMAs of the tile after next wait for this arrive, and the chain commit -> ld -> arrive -> MMA was what paced the kernel
+            uint32_t ra[32];
+            {
+                const uint32_t tacc = tmem_base + buf * kPairAcc + ((uint32_t)(q * 32) << 16);
+                tmem_ld_32x32b_x32(tacc + 128 + hsel * 32, ra);                       // lo * hi (or the single plane)
+                if (X3) {
+                    uint32_t r1[32];                                                  // two rounds of 64 registers instead of one of 96 (no spills)
+                    tmem_ld_32x32b_x32(tacc + hsel * 64 + 32, r1);                    // hi * lo
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) ra[v] = __float_as_uint(__uint_as_float(r1[v]) + __uint_as_float(ra[v]));
+                    tmem_ld_32x32b_x32(tacc + hsel * 64, r1);                         // hi * hi of this channel half
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) ra[v] = __float_as_uint(__uint_as_float(r1[v]) + __uint_as_float(ra[v]));
+                } else {
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+            }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {            // 16-column half-chunks of this warp's 32 columns
                 const int col = hsel * 32 + hh * 16;
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(tmem_base + buf * kPairBN + ((uint32_t)(q * 32) << 16) + col, r);
+                const uint32_t* const r = ra + hh * 16;
                 float4 ad[4], zz[4];
                 if (addend) {
 #pragma unroll
@@ -244,12 +275,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         zz[j] = rows4[j] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[j] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                tmem_ld_wait();
-                if (hh == 1) {          // this warp's part of the accumulator is in registers: hand the TMEM buffer back to the leader
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
                 }
                 float4* const srow = reinterpret_cast<float4*>(stg + lane * kPairStgLd);
 #pragma unroll
@@ -322,7 +347,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                     // no CTA frees its half of the pair's TMEM while the other may still use it
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kPairBN) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 // the layers this kernel takes: 1 x 3 x 3, stride 1, padding (0, 1, 1), 64 -> 64 channels, both bf16 planes or hi only
@@ -376,25 +401,18 @@ int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const
         if (r != CUDA_SUCCESS) { set_error("conv_pair: cuTensorMapEncodeTiled (filter) failed (%d)", (int)r); return AVID_ECUDA; }
     }
     const int smem = 1024 + kPairBBytes + kPairSlots * p.slot_bytes + kPairBN * 16 + kPairStgBytes + 256;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    auto kern = p.x3 ? conv_pair_kernel<true> : conv_pair_kernel<false>;
+    static bool configured[2] = {false, false};
+    if (!configured[p.x3]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) { set_error("conv_pair: smem attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
-        configured = true;
+        configured[p.x3] = true;
     }
     if (smem > 232448) return AVID_EUNSUPPORTED;
     int clusters = kNumSMs / 2;
     if (clusters > p.num_pairs) clusters = p.num_pairs;
-    if (p.debug & 256) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters);  cfg.blockDim = dim3(kPairThreads);  cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute at;  at.id = cudaLaunchAttributeClusterDimension;  at.val.clusterDim.x = 2;  at.val.clusterDim.y = 1;  at.val.clusterDim.z = 1;
-        cfg.attrs = &at;  cfg.numAttrs = 1;
-        int nc = -1;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, conv_pair_kernel, &cfg);
-        printf("conv_pair: %d clusters launched, max active clusters %d (%s), smem %d, slot %d\n", clusters, nc, cudaGetErrorString(e), smem, p.slot_bytes);
-    }
-    conv_pair_kernel<<<2 * clusters, kPairThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
+    if (p.debug & 256) printf("conv_pair: %d clusters, smem %d, slot %d, %d tiles per frame\n", clusters, smem, p.slot_bytes, p.tiles_per_frame);
+    kern<<<2 * clusters, kPairThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
     return check_launch("conv_pair_kernel");
 }
 

@@ -106,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint64_t* tmem_empty = tmem_full + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     const int cblocks = p.cs / kBK;
     const int nkb = p.ntaps * cblocks;
     const int nblocks = p.cd / BN;
@@ -133,9 +133,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
+    // The producer and the MMA issuer are WHOLE warps walking their loops (waits included) with one elected lane issuing: the operands
+    // of UTMALDG / UTCHMMA are then provably warp-uniform and live in uniform registers.  Issued from `if (lane == 0)` ptxas wraps
+    // every such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (it cannot prove a single active thread), which made
+    // the issuing thread -- not the tensor pipe -- the pace of the short-K layers (scripts/probes/issue_rate.cu, probe_pair.py).
+    if (warp == 0) {
         // ===== TMA producer =====
         const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
         int stage = 0, phase = 0;
@@ -154,17 +158,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int ftap = tp >> 24;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + stage * S::kStageBytes;
-                mbar_expect_tx(&full_bar[stage], tx);
-                tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
-                tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
-                if (p.x3) {
-                    tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
-                    tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
+                if (elect_one()) {
+                    mbar_expect_tx(&full_bar[stage], tx);
+                    tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
+                    tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
+                    if (p.x3) {
+                        tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
+                        tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
+                    }
                 }
+                __syncwarp();
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
         // bf16x3 as TWO MMAs per k-step instead of three: the hi and lo filter planes are adjacent K-major tiles, i.e. ONE
@@ -188,21 +195,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 tc_fence_after();
                 const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
                 const uint64_t b_hi = a_hi + (uint32_t)((2 * S::kABytes) >> 4);
-                if (p.debug & 8) {
-                } else if (x3) {
+                if (elect_one()) {
+                    if (p.debug & 8) {
+                    } else if (x3) {
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kb | k) != 0);                               // hi*hi | hi*lo
-                        umma_bf16(acc, a_hi + (uint32_t)(S::kABytes >> 4) + 2 * k, b_hi + 2 * k, idesc, 1);              // + lo*hi
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc2, (kb | k) != 0);                               // hi*hi | hi*lo
+                            umma_bf16(acc, a_hi + (uint32_t)(S::kABytes >> 4) + 2 * k, b_hi + 2 * k, idesc, 1);              // + lo*hi
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k) umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
                     }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) umma_bf16(acc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs have read it
+                    if (kb == nkb - 1) umma_commit(&tmem_full[buf]);           // accumulator complete
                 }
-                umma_commit(&empty_bar[stage]);     // frees the smem stage once these MMAs have read it
+                __syncwarp();
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tmem_full[buf]);           // accumulator complete
         }
     } else if (warp >= 2) {
         // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> coalesced global rows, optional BatchNorm statistics =====
@@ -427,7 +437,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     uint64_t* accum_bar = empty_bar + S::kStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int g0 = blockIdx.x * G;                       // first (tap, channel-block) group of this CTA
     const int n0 = blockIdx.y * BN;
     const int cblocks = p.cs / 64;
@@ -449,10 +459,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+    if (warp == 0) {
+        // ===== TMA producer (whole warp, one elected lane issues: see conv_tc_kernel) =====
         int gtap[G], gc0[G], ga[G], gb[G], gc[G];
 #pragma unroll
         for (int i = 0; i < G; ++i) {
@@ -489,23 +499,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             const int bw = w_o * p.sw - p.pw, bh = h_o * p.sh - p.ph, bt = t_o * p.st - p.pt;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * S::kStageBytes;
-            mbar_expect_tx(&full_bar[stage], tx);
-            const int planes = p.x3 ? 2 : 1;
-            for (int pl = 0; pl < planes; ++pl) {
-                const CUtensorMap* mx = pl ? &map_x_lo : &map_x_hi;
-                const CUtensorMap* md = pl ? &map_d_lo : &map_d_hi;
-                uint8_t* a = st + pl * S::kABytes;
-                uint8_t* b = st + 2 * S::kABytes + pl * S::kBBytes;
+            if (elect_one()) {
+                mbar_expect_tx(&full_bar[stage], tx);
+                const int planes = p.x3 ? 2 : 1;
+                for (int pl = 0; pl < planes; ++pl) {
+                    const CUtensorMap* mx = pl ? &map_x_lo : &map_x_hi;
+                    const CUtensorMap* md = pl ? &map_d_lo : &map_d_hi;
+                    uint8_t* a = st + pl * S::kABytes;
+                    uint8_t* b = st + 2 * S::kABytes + pl * S::kBBytes;
 #pragma unroll
-                for (int i = 0; i < G; ++i)
-                    tma_load_im2col_5d(a + i * kSubTile, mx, &full_bar[stage], gc0[i], bw, bh, bt, n_i, (uint16_t)gc[i], (uint16_t)gb[i], (uint16_t)ga[i]);
+                    for (int i = 0; i < G; ++i)
+                        tma_load_im2col_5d(a + i * kSubTile, mx, &full_bar[stage], gc0[i], bw, bh, bt, n_i, (uint16_t)gc[i], (uint16_t)gb[i], (uint16_t)ga[i]);
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                    tma_load_2d(b + j * kSubTile, md, &full_bar[stage], n0 + j * 64, blk_row);
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_2d(b + j * kSubTile, md, &full_bar[stage], n0 + j * 64, blk_row);
+                }
             }
+            __syncwarp();
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         constexpr uint32_t idesc2 = make_idesc_bf16(128, S::kWide ? 2 * BN : BN, 1, 1);
@@ -518,6 +531,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             const uint64_t a_hi = desc0 + (uint32_t)((stage * S::kStageBytes) >> 4);
             const uint64_t b_hi = a_hi + (uint32_t)((2 * S::kABytes) >> 4);
             constexpr uint32_t kLoA = (uint32_t)(S::kABytes >> 4), kLoB = (uint32_t)(S::kBBytes >> 4);      // hi -> lo plane of an operand
+            if (elect_one()) {
 #pragma unroll
             for (int acc_i = 0; acc_i < kAcc; ++acc_i) {
                 const uint32_t acc = tmem_base + acc_i * S::kAccCols;
@@ -540,9 +554,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 }
             }
             umma_commit(&empty_bar[stage]);
+            if (kb == nkb - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
             if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(accum_bar);
     } else if (warp >= 2 && nkb > 0) {
         // ===== epilogue: accumulator row = (group, channel) -> fp32 atomics into dW[tap][ci][co] =====
         mbar_wait(accum_bar, 0);

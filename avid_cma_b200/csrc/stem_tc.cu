@@ -76,7 +76,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     uint64_t* tmem_empty = tmem_full + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_x_hi);
         prefetch_tensormap(&map_w_hi);
@@ -95,14 +95,19 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
+    // producer and MMA issuer: whole warps walk the loops, one elected lane issues (uniform-register operands, no per-instruction
+    // ELECT / R2UR waterfall -- see conv_tc_kernel)
+    if (warp == 0) {
         // ===== TMA producer: the filter once, then (kt, parity, plane) row slots of every tile =====
-        mbar_expect_tx(w_bar, (uint32_t)(planes * chunks * kChunkBBytes));
-        for (int pl = 0; pl < planes; ++pl)
-            for (int c = 0; c < chunks; ++c)
-                tma_load_2d(w_smem + (c * planes + pl) * kChunkBBytes, pl ? &map_w_lo : &map_w_hi, w_bar, c * 32, 0);
+        if (elect_one()) {
+            mbar_expect_tx(w_bar, (uint32_t)(planes * chunks * kChunkBBytes));
+            for (int pl = 0; pl < planes; ++pl)
+                for (int c = 0; c < chunks; ++c)
+                    tma_load_2d(w_smem + (c * planes + pl) * kChunkBBytes, pl ? &map_w_lo : &map_w_hi, w_bar, c * 32, 0);
+        }
+        __syncwarp();
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             int n_i, t_o, h0, w0;
@@ -111,13 +116,16 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
                 for (int par = 0; par < 2 && par < p.kh; ++par)
                     for (int pl = 0; pl < planes; ++pl) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], kSlotRows * kRowBytes);
-                        tma_load_5d(ring + stage * kSlotBytes, pl ? &map_x_lo : &map_x_hi, &full_bar[stage], 0, w0, 2 * h0 - p.ph + par,
-                                    t_o * p.st - p.pt + a, n_i);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], kSlotRows * kRowBytes);
+                            tma_load_5d(ring + stage * kSlotBytes, pl ? &map_x_lo : &map_x_hi, &full_bar[stage], 0, w0, 2 * h0 - p.ph + par,
+                                        t_o * p.st - p.pt + a, n_i);
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 0, 0);
         // bf16x3: x_hi x [w_hi ; w_lo] is ONE MMA of N = 128 (the planes of a chunk are adjacent in shared memory), its column
@@ -147,27 +155,28 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint64_t slot = ring_desc + (uint32_t)((stage * kSlotBytes) >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kh = par; kh < (KH > 0 ? KH : 8); kh += 2) {
-                            if (KH == 0 && kh >= kh_n) break;
+                            for (int kh = par; kh < (KH > 0 ? KH : 8); kh += 2) {
+                                if (KH == 0 && kh >= kh_n) break;
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t da = slot + (uint32_t)(((kh >> 1) * kRowBytes + ks * 32) >> 4);
-                                const uint64_t db_hi = w_a + (uint32_t)((kh * kPl * kChunkBBytes + ks * 32) >> 4);
-                                if (pl == 0) {
-                                    umma_bf16(acc, da, db_hi, X3 ? idesc2 : idesc, accumulate);
-                                    accumulate = 1;
-                                } else {
-                                    umma_bf16(acc, da, db_hi, idesc, 1);
+                                for (int ks = 0; ks < 2; ++ks) {
+                                    const uint64_t da = slot + (uint32_t)(((kh >> 1) * kRowBytes + ks * 32) >> 4);
+                                    const uint64_t db_hi = w_a + (uint32_t)((kh * kPl * kChunkBBytes + ks * 32) >> 4);
+                                    if (pl == 0) umma_bf16(acc, da, db_hi, X3 ? idesc2 : idesc, accumulate | (uint32_t)(kh != par || ks != 0));
+                                    else umma_bf16(acc, da, db_hi, idesc, 1);
                                 }
                             }
+                            umma_commit(&empty_bar[stage]);
                         }
-                        umma_commit(&empty_bar[stage]);
+                        __syncwarp();
+                        if (pl == 0) accumulate = 1;
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            umma_commit(&tmem_full[buf]);
+            if (elect_one()) umma_commit(&tmem_full[buf]);
+            __syncwarp();
         }
     } else if (warp >= 2) {
         // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> coalesced global rows + BatchNorm statistics =====
@@ -295,7 +304,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     uint64_t* accum_bar = dz_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_x_hi);
         prefetch_tensormap(&map_d_hi);
@@ -314,7 +323,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     // The temporal taps are split over the CTAs (CTA i works on tap i % kt of the tiles i / kt, i / kt + gridDim.x / kt, ...): a CTA
     // then needs only two accumulators (row parities), which leaves TMEM room for the wide bf16x3 form x_hi x [dZ_hi | dZ_lo]
     // (N = 128, the dZ planes are 16 KB apart = the descriptor's leading-dimension offset) + x_lo x dZ_hi: 14 KB instead of
@@ -324,28 +333,34 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     constexpr int kAccW = X3 ? 2 * kStemCo : kStemCo;      // accumulator columns per (tap, parity)
     const bool has_work = cta < p.num_tiles;
 
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+    if (warp == 0) {
+        // ===== TMA producer (whole warp, one elected lane issues: see conv_tc_kernel) =====
         int stage = 0, phase = 0, it = 0;
         for (int tile = cta; tile < p.num_tiles; tile += ctas, ++it) {
             int n_i, t_o, h0, w0;
             tile_coords(p, tile, n_i, t_o, h0, w0);
             const int buf = it & 1;
             mbar_wait(&dz_empty[buf], ((it >> 1) & 1) ^ 1);
-            mbar_expect_tx(&dz_full[buf], (uint32_t)(planes * kDzBytes));
-            for (int pl = 0; pl < planes; ++pl)
-                tma_load_5d(dz_smem + (buf * planes + pl) * kDzBytes, pl ? &map_d_lo : &map_d_hi, &dz_full[buf], 0, w0, h0, t_o, n_i);
+            if (elect_one()) {
+                mbar_expect_tx(&dz_full[buf], (uint32_t)(planes * kDzBytes));
+                for (int pl = 0; pl < planes; ++pl)
+                    tma_load_5d(dz_smem + (buf * planes + pl) * kDzBytes, pl ? &map_d_lo : &map_d_hi, &dz_full[buf], 0, w0, h0, t_o, n_i);
+            }
+            __syncwarp();
             for (int a = a_only; a <= a_only; ++a)
                 for (int par = 0; par < 2 && par < p.kh; ++par)
                     for (int pl = 0; pl < planes; ++pl) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], kSlotRows * kRowBytes);
-                        tma_load_5d(ring + stage * kSlotBytes, pl ? &map_x_lo : &map_x_hi, &full_bar[stage], 0, w0, 2 * h0 - p.ph + par,
-                                    t_o * p.st - p.pt + a, n_i);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], kSlotRows * kRowBytes);
+                            tma_load_5d(ring + stage * kSlotBytes, pl ? &map_x_lo : &map_x_hi, &full_bar[stage], 0, w0, 2 * h0 - p.ph + par,
+                                        t_o * p.st - p.pt + a, n_i);
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer: A = x slot (MN-major, 64-byte swizzle, 4 tap atoms one row apart), B = dZ (MN-major, 128-byte swizzle) =====
         constexpr uint32_t idesc = make_idesc_bf16(128, kStemCo, 1, 1);
         constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * kStemCo, 1, 1);
@@ -365,23 +380,29 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint64_t slot = ring_desc + (uint32_t)((stage * kSlotBytes) >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {          // 16 pixels (one patch row) per MMA
-                            const uint64_t da = slot + (uint32_t)((ks * kRowBytes) >> 4);
-                            const uint64_t db_hi = dz_hi + (uint32_t)((ks * 2048) >> 4);
-                            if (pl == 0) {
-                                umma_bf16(acc, da, db_hi, X3 ? idesc2 : idesc, (it | ks) != 0);      // x_hi x [dZ_hi | dZ_lo]
-                            } else {
-                                umma_bf16(acc, da, db_hi, idesc, 1);
+                            for (int ks = 0; ks < 8; ++ks) {          // 16 pixels (one patch row) per MMA
+                                const uint64_t da = slot + (uint32_t)((ks * kRowBytes) >> 4);
+                                const uint64_t db_hi = dz_hi + (uint32_t)((ks * 2048) >> 4);
+                                if (pl == 0) {
+                                    umma_bf16(acc, da, db_hi, X3 ? idesc2 : idesc, (it | ks) != 0);      // x_hi x [dZ_hi | dZ_lo]
+                                } else {
+                                    umma_bf16(acc, da, db_hi, idesc, 1);
+                                }
                             }
+                            umma_commit(&empty_bar[stage]);
                         }
-                        umma_commit(&empty_bar[stage]);
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
-            umma_commit(&dz_empty[buf]);
+            if (elect_one()) {
+                umma_commit(&dz_empty[buf]);
+                if (tile + ctas >= p.num_tiles) umma_commit(accum_bar);
+            }
+            __syncwarp();
         }
-        umma_commit(accum_bar);
     } else if (warp >= 2 && has_work) {
         // ===== epilogue: accumulator row = (tap kh = parity + 2*(row/32), kw = (row%32)/4, c = row%4) -> atomics into dW[tap][c][co] =====
         mbar_wait(accum_bar, 0);

@@ -36,7 +36,7 @@ def main():
     flops = 2.0 * n * t * h * w * ci * co * 9
     for label, dbg in [("full", 0), ("no stores", 1), ("no A loads", 8), ("no A loads, no stores", 9), ("full + report", 256)]:
         os.environ["AVID_PAIR_DEBUG"] = str(dbg)
-        us = time_it(lambda: ops.conv_forward_tc(shape, x_hi, x_lo, w_hi, w_lo, out=out, bn_stats=stats), iters=1 if dbg & 256 else 10)
+        us = time_it(lambda: ops.conv_forward_tc(shape, x_hi, x_lo, w_hi, w_lo, out=out, bn_stats=stats), iters=1 if dbg & (256 | 512) else 10)
         print("   %-36s %8.1f us  %7.1f TFLOP/s" % (label, us, flops / us / 1e6), flush=True)
     os.environ["AVID_PAIR_DEBUG"] = "0"
     us = time_it(lambda: ops.conv_forward_tc(shape, x_hi, None, w_hi, None, out=out, bn_stats=stats))
