@@ -34,8 +34,7 @@ constexpr int kPairSlots = 3;         // activation plane slots
 constexpr int kPairBN = 64;
 constexpr int kPairAcc = 192;          // TMEM columns of one accumulator buffer: [hi*hi | hi*lo] x 2 channel halves, then lo*hi
 constexpr int kPairBBytes = 9 * 2 * 32 * 128;          // [tap][plane][32 filter rows][64 k] bf16: 72 KB per CTA
-constexpr int kPairStgLd = 20;
-constexpr int kPairStgBytes = 8 * 32 * kPairStgLd * 4;
+constexpr int kPairStgBytes = 4 * 2 * kPairBN * 4;     // per-CTA reduction of the BatchNorm sums: [4 lane quarters][2 sums][64 columns]
 constexpr int kPairMaxSlot = 45056;
 
 struct PairParams {
@@ -209,51 +208,58 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     } else if (warp >= 2) {
         // ===== epilogue (both CTAs): the same transposing epilogue as conv_tc_kernel -- TMEM -> registers -> per-warp staging -> coalesced
         //       64-byte segments, optional addend, BatchNorm statistics / fused BatchNorm-backward sums kept in registers =====
+        // No shared-memory transpose: tcgen05.ld.16x256b hands lane l the column pairs 8 j + 2 (l % 4) + {0, 1} of rows l / 4 and l / 4 + 8, so the four
+        // lanes of a row cover 32 contiguous bytes (one full sector) per column group and a warp store touches 8 rows -- like the
+        // staged float4 stores did -- while the staging tile's 64 KB per tile of shared-memory traffic (the kernel is bound by the
+        // 128 B/clk the MMAs read operands at) and its two warp syncs per half-chunk are gone.
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int hsel = (warp - 2) >> 2;           // which 32 columns of the 64
-        float* const stg = s_stage + (warp - 2) * (32 * kPairStgLd);
-        const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+        const int r8 = lane >> 2, c2 = (lane & 3) * 2;
         double* const acc_out = stats ? stats : fuse.sums;
         if (fuse.z) {
             const int t = threadIdx.x - 64;
             if (t < kPairBN) s_par[t] = make_float4(__ldg(fuse.mean + t), __ldg(fuse.invstd + t), __ldg(fuse.gamma + t), __ldg(fuse.beta + t));
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        float run1[2][4], run2[2][4];
+        float run1[8], run2[8];                     // running sums of this lane's 8 columns: [column group j][pair element]
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) run1[b][t] = run2[b][t] = 0.f;
+        for (int t = 0; t < 8; ++t) run1[t] = run2[t] = 0.f;
         int it = 0;
         for (int pr = cluster_id; pr < p.num_pairs; pr += num_clusters, ++it) {
             const int buf = it & 1;
             const int g = pr / p.tiles_per_frame, i = pr - g * p.tiles_per_frame;
             const int f = 2 * g + (int)rank;
-            const int s = 128 * i + q * 32 + lane;          // strip pixel of this thread's accumulator row
+            const int s = 128 * i + q * 32 + lane;          // strip pixel of accumulator row q * 32 + lane
             const int h = s / p.Wp, c = s - h * p.Wp;
             const bool valid = f < p.frames && h < p.H && c >= 1 && c <= p.W;
             const unsigned long long my_row = valid ? (unsigned long long)(((size_t)f * p.H + h) * p.W + (c - 1)) * kPairBN : ~0ull;
-            unsigned long long rows4[4];
+            unsigned long long rows4[4];                    // this lane's rows: r8, r8 + 8, r8 + 16, r8 + 24 of the quarter
 #pragma unroll
             for (int j = 0; j < 4; ++j) rows4[j] = __shfl_sync(0xffffffffu, my_row, j * 8 + r8);
             mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
-            // this warp's 32 columns of all accumulator pieces go to registers first and the TMEM buffer is handed back at once: the
-            // MMAs of the tile after next wait for this arrive, and the chain commit -> ld -> arrive -> MMA was what paced the kernel
-            uint32_t ra[32];
+            // all accumulator pieces of this warp's 32 rows x 32 columns go to registers first and the TMEM buffer is handed back at once
+            uint32_t ra[2][16];                             // [16-row half][4 j + 2 (row + 8) + pair element]
             {
                 const uint32_t tacc = tmem_base + buf * kPairAcc + ((uint32_t)(q * 32) << 16);
-                tmem_ld_32x32b_x32(tacc + 128 + hsel * 32, ra);                       // lo * hi (or the single plane)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(tacc + ((uint32_t)(hf * 16) << 16) + 128 + hsel * 32, ra[hf]);     // lo * hi (or the single plane)
                 if (X3) {
-                    uint32_t r1[32];                                                  // two rounds of 64 registers instead of one of 96 (no spills)
-                    tmem_ld_32x32b_x32(tacc + hsel * 64 + 32, r1);                    // hi * lo
+                    uint32_t r1[2][16];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(tacc + ((uint32_t)(hf * 16) << 16) + hsel * 64 + 32, r1[hf]);  // hi * lo
                     tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < 32; ++v) ra[v] = __float_as_uint(__uint_as_float(r1[v]) + __uint_as_float(ra[v]));
-                    tmem_ld_32x32b_x32(tacc + hsel * 64, r1);                         // hi * hi of this channel half
+                    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                        for (int v = 0; v < 16; ++v) ra[hf][v] = __float_as_uint(__uint_as_float(r1[hf][v]) + __uint_as_float(ra[hf][v]));
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(tacc + ((uint32_t)(hf * 16) << 16) + hsel * 64, r1[hf]);       // hi * hi
                     tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < 32; ++v) ra[v] = __float_as_uint(__uint_as_float(r1[v]) + __uint_as_float(ra[v]));
+                    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                        for (int v = 0; v < 16; ++v) ra[hf][v] = __float_as_uint(__uint_as_float(r1[hf][v]) + __uint_as_float(ra[hf][v]));
                 } else {
                     tmem_ld_wait();
                 }
@@ -261,79 +267,74 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
             }
+            const int col0 = hsel * 32 + c2;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {            // 16-column half-chunks of this warp's 32 columns
-                const int col = hsel * 32 + hh * 16;
-                const uint32_t* const r = ra + hh * 16;
-                float4 ad[4], zz[4];
+            for (int hf = 0; hf < 2; ++hf) {
+                float2 ad[8], zz[8];                        // [column group j][row r8 + 16 hf, + 8]
                 if (addend) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        ad[j] = rows4[j] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4[j] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int v = 0; v < 8; ++v) {
+                        const unsigned long long row = rows4[hf * 2 + (v & 1)];
+                        ad[v] = row != ~0ull ? __ldg(reinterpret_cast<const float2*>(addend + row + col0 + 8 * (v >> 1))) : make_float2(0.f, 0.f);
+                    }
                 }
                 if (fuse.z) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        zz[j] = rows4[j] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[j] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float4* const srow = reinterpret_cast<float4*>(stg + lane * kPairStgLd);
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    srow[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-                __syncwarp();
-                float4 par[4];
-                if (fuse.z) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) par[t] = s_par[col + c4 + t];
+                    for (int v = 0; v < 8; ++v) {
+                        const unsigned long long row = rows4[hf * 2 + (v & 1)];
+                        zz[v] = row != ~0ull ? __ldg(reinterpret_cast<const float2*>(fuse.z + row + col0 + 8 * (v >> 1))) : make_float2(0.f, 0.f);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float4 o = *reinterpret_cast<const float4*>(stg + (j * 8 + r8) * kPairStgLd + c4);
-                    if (rows4[j] == ~0ull || (p.debug & 1)) continue;
-                    if (addend) { o.x += ad[j].x; o.y += ad[j].y; o.z += ad[j].z; o.w += ad[j].w; }
-                    *reinterpret_cast<float4*>(out + rows4[j] + col + c4) = o;
-                    if (acc_out) {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
-                        if (fuse.z) {
-                            const float zv[4] = {zz[j].x, zz[j].y, zz[j].z, zz[j].w};
+                    float4 par[2];
+                    if (fuse.z) { par[0] = s_par[col0 + 8 * j];  par[1] = s_par[col0 + 8 * j + 1]; }
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float xh = (zv[t] - par[t].x) * par[t].y;
-                                const float gg = fmaf(xh, par[t].z, par[t].w) > 0.f ? ov[t] : 0.f;
-                                run1[hh][t] += gg;
-                                run2[hh][t] = fmaf(gg, xh, run2[hh][t]);
-                            }
-                        } else {
+                    for (int rs = 0; rs < 2; ++rs) {
+                        const unsigned long long row = rows4[hf * 2 + rs];
+                        if (row == ~0ull || (p.debug & 1)) continue;
+                        float o[2] = {__uint_as_float(ra[hf][4 * j + 2 * rs]), __uint_as_float(ra[hf][4 * j + 2 * rs + 1])};
+                        if (addend) { o[0] += ad[2 * j + rs].x;  o[1] += ad[2 * j + rs].y; }
+                        *reinterpret_cast<float2*>(out + row + col0 + 8 * j) = make_float2(o[0], o[1]);
+                        if (acc_out) {
+                            if (fuse.z) {
+                                const float zv[2] = {zz[2 * j + rs].x, zz[2 * j + rs].y};
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                run1[hh][t] += ov[t];
-                                run2[hh][t] = fmaf(ov[t], ov[t], run2[hh][t]);
+                                for (int e = 0; e < 2; ++e) {
+                                    const float xh = (zv[e] - par[e].x) * par[e].y;
+                                    const float gg = fmaf(xh, par[e].z, par[e].w) > 0.f ? o[e] : 0.f;
+                                    run1[2 * j + e] += gg;
+                                    run2[2 * j + e] = fmaf(gg, xh, run2[2 * j + e]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    run1[2 * j + e] += o[e];
+                                    run2[2 * j + e] = fmaf(o[e], o[e], run2[2 * j + e]);
+                                }
                             }
                         }
                     }
                 }
-                __syncwarp();
             }
         }
         if (acc_out) {
             float* const s_red = s_stage;           // [4 quarters][2 sums][64]
             asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
+            for (int t = 0; t < 8; ++t) {
+                float a = run1[t], b = run2[t];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    float a = run1[hh][t], b = run2[hh][t];
-#pragma unroll
-                    for (int o = 4; o <= 16; o <<= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        b += __shfl_xor_sync(0xffffffffu, b, o);
-                    }
-                    if (lane < 4) {
-                        const int col = hsel * 32 + hh * 16 + c4 + t;
-                        s_red[(q * 2 + 0) * kPairBN + col] = a;
-                        s_red[(q * 2 + 1) * kPairBN + col] = b;
-                    }
+                for (int o = 4; o <= 16; o <<= 1) {         // over the 8 lanes (rows) that own the same columns
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
                 }
+                if (lane < 4) {
+                    const int col = hsel * 32 + 8 * (t >> 1) + c2 + (t & 1);
+                    s_red[(q * 2 + 0) * kPairBN + col] = a;
+                    s_red[(q * 2 + 1) * kPairBN + col] = b;
+                }
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int t = threadIdx.x - 64;         // 0..255: (which sum, column) for t < 128
             if (t < 2 * kPairBN) {
@@ -351,23 +352,34 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 }
 
 // the layers this kernel takes: 1 x 3 x 3, stride 1, padding (0, 1, 1), 64 -> 64 channels, both bf16 planes or hi only
-int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* addend,
-                  float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
+static bool conv_pair_plan(const avid_conv_shape_t* s, PairParams& p) {
     static const bool enabled = [] { const char* e = getenv("AVID_CONV_PAIR"); return !(e && atoi(e) == 0); }();
-    if (!enabled) return AVID_EUNSUPPORTED;
+    if (!enabled) return false;
     if (!(s->kt == 1 && s->kh == 3 && s->kw == 3 && s->st == 1 && s->sh == 1 && s->sw == 1 && s->pt == 0 && s->ph == 1 && s->pw == 1 && s->ci == 64 &&
           s->co == 64))
-        return AVID_EUNSUPPORTED;
-    PairParams p;
+        return false;
     p.frames = s->n * s->ti;  p.T = s->ti;  p.H = s->hi;  p.W = s->wi;  p.Wp = s->wi + 2;
-    if (p.Wp > 256 || p.frames < 2) return AVID_EUNSUPPORTED;
+    if (p.Wp > 256 || p.frames < 2) return false;
     const int rows = (p.Wp + 126) / p.Wp + 3;              // input rows a 128-pixel strip tile can touch
     const int slot_tx = rows * p.Wp * 128;
     p.slot_bytes = (slot_tx + 1023) & ~1023;
-    if (p.slot_bytes > kPairMaxSlot || rows > 256) return AVID_EUNSUPPORTED;
+    if (p.slot_bytes > kPairMaxSlot || rows > 256) return false;
     p.slot_bytes_tx = slot_tx;
     p.tiles_per_frame = (p.H * p.Wp + 127) / 128;
     p.num_pairs = ((p.frames + 1) / 2) * p.tiles_per_frame;
+    return true;
+}
+
+bool conv_pair_supported(const avid_conv_shape_t* s) {
+    PairParams p;
+    return conv_pair_plan(s, p);
+}
+
+int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* addend,
+                  float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
+    PairParams p;
+    if (!conv_pair_plan(s, p)) return AVID_EUNSUPPORTED;
+    const int rows = p.slot_bytes_tx / (p.Wp * 128);
     p.x3 = a_lo != nullptr;
     { const char* dbg = getenv("AVID_PAIR_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     for (int dh = 0; dh < 3; ++dh)

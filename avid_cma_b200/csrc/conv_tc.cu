@@ -45,6 +45,7 @@ using namespace tc;
 
 // conv_pair.cu: 64 -> 64 channel 1x3x3 stride-1 layers on CTA pairs (halo tile + resident filter); returns AVID_EUNSUPPORTED when the
 // geometry is not its case
+bool conv_pair_supported(const avid_conv_shape_t* s);
 int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* addend,
                   float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st);
 
@@ -881,6 +882,11 @@ int avid_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream)
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
     split_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n / 4);
     return check_launch("split_bf16_kernel");
+}
+
+int avid_conv_tc_uses_cta_pairs(const avid_conv_shape_t* s, int32_t dgrad) {
+    (void)dgrad;      // the pair kernel takes both directions of the layers it takes
+    return s && s->ci % 64 == 0 && s->co % 64 == 0 && conv_pair_supported(s) ? 1 : 0;
 }
 
 int avid_conv_forward_tc(const avid_conv_shape_t* s, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,

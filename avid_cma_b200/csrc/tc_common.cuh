@@ -168,6 +168,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x 256 bits, 4 column groups (32 columns): lane l gets, for group j, r[4 j + {0, 1}] = (row l / 4, columns 8 j + 2 (l % 4) + {0, 1}) and
+// r[4 j + {2, 3}] = (row l / 4 + 8, same columns) -- the accumulator-fragment layout of mma.m16n8: the 4 lanes of a row hold 32 contiguous bytes
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Column sums of a 32 x 32 block held one row per lane (v[c] = element (lane, c)): butterfly transpose-reduce, 31 shuffles.

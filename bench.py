@@ -562,7 +562,8 @@ def run_ours(a):
         families[name]["GB/s" if name.startswith("nce") else "TFLOP/s"] = rate / (1e9 if name.startswith("nce") else 1e12)
     kernels = {}
     for name, (work, dur, cnt) in fam.items():
-        kname = {"conv_forward_tc": "conv_tc_kernel", "conv_dgrad_tc": "conv_tc_kernel", "conv_wgrad_tc": "wgrad_tc_kernel",
+        kname = {"conv_forward_tc": "conv_tc_kernel", "conv_dgrad_tc": "conv_tc_kernel", "conv_pair_forward": "conv_pair_kernel",
+                 "conv_pair_dgrad": "conv_pair_kernel", "conv_wgrad_tc": "wgrad_tc_kernel",
                  "stem_forward_tc": "stem_forward_kernel", "stem_wgrad_tc": "stem_wgrad_kernel", "conv_forward": "conv_igemm_kernel",
                  "conv_dgrad": "conv_igemm_kernel", "conv_wgrad": "conv_wgrad_kernel"}.get(name)
         if kname:

@@ -258,6 +258,11 @@ typedef struct avid_bn_backward_fuse {
 } avid_bn_backward_fuse_t;
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
                        const float* addend, float* din, const avid_bn_backward_fuse_t* fuse_host /* may be NULL */, void* stream);
+/* Host-only query: which kernel avid_conv_forward_tc (dgrad == 0) / avid_conv_dgrad_tc (dgrad != 0) launches for this geometry:
+ * 1 = conv_pair_kernel (64 -> 64 channel 1x3x3 stride-1 layers: CTA pairs, tcgen05 cta_group::2, halo strip, resident filter;
+ * network_blocks.py:35-37 / :14-16 at 64 channels), 0 = conv_tc_kernel (im2col TMA, every other layer).  bench.py labels its
+ * per-launch roofline records with it. */
+int avid_conv_tc_uses_cta_pairs(const avid_conv_shape_t* s_host, int32_t dgrad);
 /*   wgrad  : in planes [n,ti,hi,wi,ci], dout planes [n,to,ho,wo,co] -> dfilt fp32 tap-major [taps][ci][co], zeroed by the
  *            caller (split over pixels, accumulated with fp32 vector atomics); any stride                               */
 int avid_conv_wgrad_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* dout_hi, const void* dout_lo,
