@@ -232,10 +232,31 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const int s = 128 * i + q * 32 + lane;          // strip pixel of accumulator row q * 32 + lane
             const int h = s / p.Wp, c = s - h * p.Wp;
             const bool valid = f < p.frames && h < p.H && c >= 1 && c <= p.W;
-            const unsigned long long my_row = valid ? (unsigned long long)(((size_t)f * p.H + h) * p.W + (c - 1)) * kPairBN : ~0ull;
-            unsigned long long rows4[4];                    // this lane's rows: r8, r8 + 8, r8 + 16, r8 + 24 of the quarter
+            const uint32_t my_row = valid ? (uint32_t)((f * p.H + h) * p.W + (c - 1)) : ~0u;       // output pixel (the host checks frames * H * W < 2^31)
+            uint32_t rows4[4];                              // this lane's rows: r8, r8 + 8, r8 + 16, r8 + 24 of the quarter
 #pragma unroll
             for (int j = 0; j < 4; ++j) rows4[j] = __shfl_sync(0xffffffffu, my_row, j * 8 + r8);
+            // residual addend / z of the fused BatchNorm backward: this lane's 8 column pairs of the first 16-row half are requested before
+            // the wait for the accumulator, those of the second half before the first half is processed (HBM latency off the per-tile chain)
+            const int col0 = hsel * 32 + c2;
+            float2 ad[2][8], zz[2][8];                      // [half][2 j + row select]
+            auto request = [&](int hf) {
+                if (addend) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const uint32_t row = rows4[hf * 2 + (v & 1)];
+                        ad[hf][v] = row != ~0u ? __ldg(reinterpret_cast<const float2*>(addend + (size_t)row * kPairBN + col0 + 8 * (v >> 1))) : make_float2(0.f, 0.f);
+                    }
+                }
+                if (fuse.z) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const uint32_t row = rows4[hf * 2 + (v & 1)];
+                        zz[hf][v] = row != ~0u ? __ldg(reinterpret_cast<const float2*>(fuse.z + (size_t)row * kPairBN + col0 + 8 * (v >> 1))) : make_float2(0.f, 0.f);
+                    }
+                }
+            };
+            request(0);
             mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
             // all accumulator pieces of this warp's 32 rows x 32 columns go to registers first and the TMEM buffer is handed back at once
@@ -267,38 +288,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
             }
-            const int col0 = hsel * 32 + c2;
+            request(1);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                float2 ad[8], zz[8];                        // [column group j][row r8 + 16 hf, + 8]
-                if (addend) {
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        const unsigned long long row = rows4[hf * 2 + (v & 1)];
-                        ad[v] = row != ~0ull ? __ldg(reinterpret_cast<const float2*>(addend + row + col0 + 8 * (v >> 1))) : make_float2(0.f, 0.f);
-                    }
-                }
-                if (fuse.z) {
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        const unsigned long long row = rows4[hf * 2 + (v & 1)];
-                        zz[v] = row != ~0ull ? __ldg(reinterpret_cast<const float2*>(fuse.z + row + col0 + 8 * (v >> 1))) : make_float2(0.f, 0.f);
-                    }
-                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 par[2];
                     if (fuse.z) { par[0] = s_par[col0 + 8 * j];  par[1] = s_par[col0 + 8 * j + 1]; }
 #pragma unroll
                     for (int rs = 0; rs < 2; ++rs) {
-                        const unsigned long long row = rows4[hf * 2 + rs];
-                        if (row == ~0ull || (p.debug & 1)) continue;
+                        const uint32_t row = rows4[hf * 2 + rs];
+                        if (row == ~0u || (p.debug & 1)) continue;
                         float o[2] = {__uint_as_float(ra[hf][4 * j + 2 * rs]), __uint_as_float(ra[hf][4 * j + 2 * rs + 1])};
-                        if (addend) { o[0] += ad[2 * j + rs].x;  o[1] += ad[2 * j + rs].y; }
-                        *reinterpret_cast<float2*>(out + row + col0 + 8 * j) = make_float2(o[0], o[1]);
+                        if (addend) { o[0] += ad[hf][2 * j + rs].x;  o[1] += ad[hf][2 * j + rs].y; }
+                        *reinterpret_cast<float2*>(out + (size_t)row * kPairBN + col0 + 8 * j) = make_float2(o[0], o[1]);
                         if (acc_out) {
                             if (fuse.z) {
-                                const float zv[2] = {zz[2 * j + rs].x, zz[2 * j + rs].y};
+                                const float zv[2] = {zz[hf][2 * j + rs].x, zz[hf][2 * j + rs].y};
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     const float xh = (zv[e] - par[e].x) * par[e].y;
@@ -359,7 +365,7 @@ static bool conv_pair_plan(const avid_conv_shape_t* s, PairParams& p) {
           s->co == 64))
         return false;
     p.frames = s->n * s->ti;  p.T = s->ti;  p.H = s->hi;  p.W = s->wi;  p.Wp = s->wi + 2;
-    if (p.Wp > 256 || p.frames < 2) return false;
+    if (p.Wp > 256 || p.frames < 2 || (int64_t)p.frames * p.H * p.W >= (int64_t)1 << 31) return false;
     const int rows = (p.Wp + 126) / p.Wp + 3;              // input rows a 128-pixel strip tile can touch
     const int slot_tx = rows * p.Wp * 128;
     p.slot_bytes = (slot_tx + 1023) & ~1023;

@@ -39,6 +39,19 @@ def main():
         us = time_it(lambda: ops.conv_forward_tc(shape, x_hi, x_lo, w_hi, w_lo, out=out, bn_stats=stats), iters=1 if dbg & (256 | 512) else 10)
         print("   %-36s %8.1f us  %7.1f TFLOP/s" % (label, us, flops / us / 1e6), flush=True)
     os.environ["AVID_PAIR_DEBUG"] = "0"
+    # input gradient (same kernel, mirrored taps) with the residual addend and the fused BatchNorm-backward sums
+    wt_t = torch.randn(9, ci, co, device=DEV) / (ci * 9) ** 0.5
+    wt_hi, wt_lo = ops.split_bf16(wt_t, True)
+    add = torch.randn(n, t, h, w, ci, device=DEV)
+    z = torch.randn(n, t, h, w, ci, device=DEV)
+    st = ops.BNState(ci, DEV)
+    st.mean.normal_(); st.invstd.fill_(1.0)
+    gamma, beta = torch.ones(ci, device=DEV), torch.zeros(ci, device=DEV)
+    sums = torch.zeros(2, ci, dtype=torch.float64, device=DEV)
+    for label, kw in [("dgrad", {}), ("dgrad + addend", dict(addend=add)), ("dgrad + fused BN sums", dict(bn_fuse=(z, st, gamma, beta, sums))),
+                      ("dgrad + addend + fused BN sums", dict(addend=add, bn_fuse=(z, st, gamma, beta, sums)))]:
+        us = time_it(lambda: ops.conv_dgrad_tc(shape, x_hi, x_lo, wt_hi, wt_lo, out=out, **kw))
+        print("   %-36s %8.1f us  %7.1f TFLOP/s" % (label, us, flops / us / 1e6), flush=True)
     us = time_it(lambda: ops.conv_forward_tc(shape, x_hi, None, w_hi, None, out=out, bn_stats=stats))
     print("   %-36s %8.1f us  %7.1f TFLOP/s" % ("bf16 single pass", us, flops / us / 1e6), flush=True)
 
