@@ -30,16 +30,16 @@ namespace avid {
 using namespace tc;
 
 constexpr int kPairThreads = 320;     // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer (leader CTA), warps 2-9: epilogue
-constexpr int kPairSlots = 3;         // activation plane slots
+constexpr int kPairSlots = 3;         // activation plane slots (2 when three do not fit: wide frames such as the audio tower's 100 x 129)
 constexpr int kPairBN = 64;
 constexpr int kPairAcc = 192;          // TMEM columns of one accumulator buffer: [hi*hi | hi*lo] x 2 channel halves, then lo*hi
 constexpr int kPairBBytes = 9 * 2 * 32 * 128;          // [tap][plane][32 filter rows][64 k] bf16: 72 KB per CTA
 constexpr int kPairStgBytes = 4 * 2 * kPairBN * 4;     // per-CTA reduction of the BatchNorm sums: [4 lane quarters][2 sums][64 columns]
-constexpr int kPairMaxSlot = 45056;
 
 struct PairParams {
     int frames, T, H, W, Wp;          // N * T frames of H x W pixels; strip pitch Wp = W + 2
     int tiles_per_frame, num_pairs;   // 128-pixel strip tiles per frame; (frame pairs) x (tiles per frame)
+    int slots;                        // plane slots in the ring: 3, or 2 for wide frames
     int slot_bytes;                   // pitch of the plane slots: R rows x Wp pixels x 128 B rounded up to 1 KB
     int slot_bytes_tx;                // bytes one strip load delivers (R * Wp * 128)
     uint32_t taps[9];                 // (dw + 1) | (dh + 1) << 8 | filter tap << 24
@@ -97,9 +97,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_smem = smem;                                        // resident filter half: [tap][plane][32 rows][64 k]
     uint8_t* ring = smem + kPairBBytes;                            // [3 slots] activation plane strips
-    float4* s_par = reinterpret_cast<float4*>(ring + kPairSlots * p.slot_bytes);
-    float* s_stage = reinterpret_cast<float*>(ring + kPairSlots * p.slot_bytes + kPairBN * 16);
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + kPairSlots * p.slot_bytes + kPairBN * 16 + kPairStgBytes);
+    float4* s_par = reinterpret_cast<float4*>(ring + p.slots * p.slot_bytes);
+    float* s_stage = reinterpret_cast<float*>(ring + p.slots * p.slot_bytes + kPairBN * 16);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + p.slots * p.slot_bytes + kPairBN * 16 + kPairStgBytes);
     uint64_t* a_empty = a_full + kPairSlots;
     uint64_t* w_full = a_empty + kPairSlots;
     uint64_t* tmem_full = w_full + 1;       // [2]
@@ -153,8 +153,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             if (f >= p.frames) f = p.frames - 1;             // odd frame count: the last pair's second CTA recomputes a tile and stores nothing
             const int r0 = (128 * i) / p.Wp;
             for (int pl = 0; pl < planes; ++pl, ++n_load) {
-                const int slot = n_load % kPairSlots;
-                mbar_wait(&a_empty[slot], ((n_load / kPairSlots) & 1) ^ 1);
+                const int slot = n_load % p.slots;
+                mbar_wait(&a_empty[slot], ((n_load / p.slots) & 1) ^ 1);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * (uint32_t)p.slot_bytes_tx);
                     tma_load_5d_pair(ring + slot * p.slot_bytes, pl ? &map_a_lo : &map_a_hi, &a_full[slot], 0, -1, r0 - 1, f % p.T, f / p.T);
@@ -183,8 +183,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const uint32_t acc = tmem_base + buf * kPairAcc;
 #pragma unroll
             for (int pl = 0; pl < planes; ++pl, ++n_use) {
-                const int slot = n_use % kPairSlots;
-                if (!(p.debug & 8)) mbar_wait(&a_full[slot], (n_use / kPairSlots) & 1);
+                const int slot = n_use % p.slots;
+                if (!(p.debug & 8)) mbar_wait(&a_full[slot], (n_use / p.slots) & 1);
                 tc_fence_after();
                 const uint32_t a_lo32 = ring_lo + (uint32_t)((slot * p.slot_bytes) >> 4) + (uint32_t)(l0 * 8);      // 128 bytes per strip pixel = 8 units
                 if (elect_one()) {
@@ -369,7 +369,9 @@ static bool conv_pair_plan(const avid_conv_shape_t* s, PairParams& p) {
     const int rows = (p.Wp + 126) / p.Wp + 3;              // input rows a 128-pixel strip tile can touch
     const int slot_tx = rows * p.Wp * 128;
     p.slot_bytes = (slot_tx + 1023) & ~1023;
-    if (p.slot_bytes > kPairMaxSlot || rows > 256) return false;
+    constexpr int kFixed = 1024 + kPairBBytes + kPairBN * 16 + kPairStgBytes + 256;       // everything but the ring
+    p.slots = kFixed + kPairSlots * p.slot_bytes <= 232448 ? kPairSlots : 2;
+    if (kFixed + p.slots * p.slot_bytes > 232448 || rows > 256) return false;
     p.slot_bytes_tx = slot_tx;
     p.tiles_per_frame = (p.H * p.Wp + 127) / 128;
     p.num_pairs = ((p.frames + 1) / 2) * p.tiles_per_frame;
@@ -418,7 +420,7 @@ int conv_pair_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_pair: cuTensorMapEncodeTiled (filter) failed (%d)", (int)r); return AVID_ECUDA; }
     }
-    const int smem = 1024 + kPairBBytes + kPairSlots * p.slot_bytes + kPairBN * 16 + kPairStgBytes + 256;
+    const int smem = 1024 + kPairBBytes + p.slots * p.slot_bytes + kPairBN * 16 + kPairStgBytes + 256;
     auto kern = p.x3 ? conv_pair_kernel<true> : conv_pair_kernel<false>;
     static bool configured[2] = {false, false};
     if (!configured[p.x3]) {

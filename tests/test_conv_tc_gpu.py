@@ -23,6 +23,8 @@ TC_CASES = [
     (1, 64, 64, (5, 6, 7), (3, 1, 1), (2, 1, 1), (0, 0, 0)),       # unpadded strided temporal (negative tap offsets)
     (2, 64, 64, (5, 8, 16), (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # temporal, h*w % 64 == 0: frame-fastest k-block order of the filter gradient
     (2, 128, 128, (3, 8, 8), (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # same with two channel blocks
+    (3, 64, 64, (1, 20, 129), (1, 3, 3), (1, 1, 1), (0, 1, 1)),    # CTA-pair kernel, wide 2-D frames (audio block1 width): two-slot ring, odd frame count
+    (1, 64, 64, (5, 7, 6), (1, 3, 3), (1, 1, 1), (0, 1, 1)),       # CTA-pair kernel, tiny frames: one tile per frame, odd frame count
 ]
 
 
@@ -125,6 +127,7 @@ def test_stem_tc_forward_and_wgrad(case, x3):
 FULL_CASES = [
     (8, 64, 64, (8, 56, 56), (1, 3, 3), (1, 1, 1), (0, 1, 1)),       # conv2x spatial
     (8, 64, 64, (8, 56, 56), (3, 1, 1), (1, 1, 1), (1, 0, 0)),       # conv2x temporal
+    (8, 64, 64, (1, 100, 129), (1, 3, 3), (1, 1, 1), (0, 1, 1)),     # audio block1 (CTA-pair kernel, two-slot ring)
     (8, 64, 128, (8, 56, 56), (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # conv3x entry, strided
     (8, 128, 128, (8, 28, 28), (3, 1, 1), (2, 1, 1), (1, 0, 0)),     # conv3x strided temporal
     (4, 3, 64, (8, 224, 224), (3, 7, 7), (1, 2, 2), (1, 3, 3)),      # video stem
