@@ -32,8 +32,7 @@ constexpr int kSlotBytes = kSlotRows * kRowBytes;
 constexpr int kChunkBBytes = kStemCo * 64;   // [64 co][32 k] bf16
 constexpr int kDzBytes = 128 * 128;          // [128 pixels][64 co] bf16
 constexpr int kMaxStages = 14;
-constexpr int kStgLd = 20;                   // row pitch (floats) of the 32 x 16 epilogue staging tiles: 16-byte aligned, conflict-free float4 rows
-constexpr int kStemStgBytes = 4 * 32 * kStgLd * 4;
+constexpr int kStemStgBytes = 4 * 2 * 64 * 4;      // per-CTA reduction of the BatchNorm sums: [4 lane quarters][2 sums][64 channels]
 constexpr int kSmemLimit = 232448 - 1024;    // 227 KB minus alignment slack
 
 struct StemParams {
@@ -68,7 +67,7 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
     const int chunks = p.kt * p.kh, planes = p.x3 ? 2 : 1;
     uint8_t* w_smem = smem;                                          // [chunk][plane][64 co][32 k]: hi | lo of a chunk = one 128-row operand
     uint8_t* ring = smem + planes * chunks * kChunkBBytes;           // [stage][11 rows][16 wo][32 k]
-    float* s_stage = reinterpret_cast<float*>(ring + p.stages * kSlotBytes);       // [4 epilogue warps][32 rows][kStgLd] transpose staging
+    float* s_stage = reinterpret_cast<float*>(ring + p.stages * kSlotBytes);       // [4 lane quarters][2 sums][64]: BatchNorm sums of the CTA
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.stages * kSlotBytes + kStemStgBytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* w_bar = empty_bar + kMaxStages;
@@ -186,88 +185,86 @@ stem_forward_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_c
         // active -- the stores, not the MMAs, paced the kernel.  Now each warp transposes 32 x 16 half-chunks through a padded
         // staging tile and writes 64-byte segments (4 lanes per row, 8 rows per instruction: full sectors, 4x fewer requests), like
         // conv_tc_kernel; the per-channel sums stay in registers across the CTA's tiles and leave once, as fp64 atomics.
+        // Round 2b: the transpose through shared memory is gone as well -- the kernel is bound by shared-memory bandwidth (ncu: MMA operand
+        // reads 62 % + epilogue LSU traffic 23 % + TMA writes of the data pipe), and tcgen05.ld.16x256b already hands the 4 lanes of a row
+        // 32 contiguous bytes (one full sector) per 8-column group: 8 rows per store instruction as before, no staging tile.
         const int q = warp & 3;
-        float* const stg = s_stage + (warp - 2) * (32 * kStgLd);
-        const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+        const int r8 = lane >> 2, c2 = (lane & 3) * 2;
         const int r = q * 32 + lane;
-        float run1[4][4], run2[4][4];      // running column sums: [16-column chunk][4 columns of this lane]
+        float run1[16], run2[16];          // running sums of this lane's 16 columns: [32-column half][column group j][pair element]
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) run1[a][t] = run2[a][t] = 0.f;
+        for (int t = 0; t < 16; ++t) run1[t] = run2[t] = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             int n_i, t_o, h0, w0;
             tile_coords(p, tile, n_i, t_o, h0, w0);
             const int ho = h0 + r / kTileW, wo = w0 + r % kTileW;
-            const unsigned long long my_row = (ho < p.ho && wo < p.wo)
-                                                  ? (unsigned long long)((((size_t)n_i * p.to + t_o) * p.ho + ho) * p.wo + wo) * kStemCo : ~0ull;
-            unsigned long long rows4[4];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
+            const uint32_t my_row = (ho < p.ho && wo < p.wo) ? (uint32_t)(((n_i * p.to + t_o) * p.ho + ho) * p.wo + wo) : ~0u;     // output pixel (< 2^31: host check)
+            uint32_t rows4[4];                      // the rows this lane serves: r8, r8 + 8, r8 + 16, r8 + 24 of the quarter (~0: no row)
 #pragma unroll
             for (int i = 0; i < 4; ++i) rows4[i] = __shfl_sync(0xffffffffu, my_row, i * 8 + r8);
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + buf * ((X3 ? 2 : 1) * kStemCo) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-            for (int hc = 0; hc < 4; ++hc) {
-                uint32_t v[16], v2[16];
-                tmem_ld_32x32b_x16(taddr + hc * 16, v);
-                if (X3) tmem_ld_32x32b_x16(taddr + kStemCo + hc * 16, v2);       // the hi*lo half of the bf16x3 accumulator
-                tmem_ld_wait();
-                if (hc == 3) {          // the accumulator is in registers: the next tile may start
+            for (int hc = 0; hc < 2; ++hc) {        // 32-column halves of the 64 output channels
+                uint32_t v[2][16];                  // [16-row half][4 j + 2 (row + 8) + pair element]
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(taddr + ((uint32_t)(hf * 16) << 16) + hc * 32, v[hf]);
+                if (X3) {
+                    uint32_t v2[2][16];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(taddr + ((uint32_t)(hf * 16) << 16) + kStemCo + hc * 32, v2[hf]);   // the hi*lo half
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) v[hf][u] = __float_as_uint(__uint_as_float(v[hf][u]) + __uint_as_float(v2[hf][u]));
+                } else {
+                    tmem_ld_wait();
+                }
+                if (hc == 1) {          // the accumulator is in registers: the next tile may start
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
-                float4* const srow = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float4 o = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
-                    if (X3) {
-                        o.x += __uint_as_float(v2[4 * u]);  o.y += __uint_as_float(v2[4 * u + 1]);
-                        o.z += __uint_as_float(v2[4 * u + 2]);  o.w += __uint_as_float(v2[4 * u + 3]);
-                    }
-                    srow[u] = o;
-                }
-                __syncwarp();
+                for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 o = *reinterpret_cast<const float4*>(stg + (i * 8 + r8) * kStgLd + c4);
-                    if (rows4[i] == ~0ull) continue;
-                    *reinterpret_cast<float4*>(out + rows4[i] + hc * 16 + c4) = o;
-                    if (stats) {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
+                    for (int j = 0; j < 4; ++j)
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            run1[hc][t] += ov[t];
-                            run2[hc][t] = fmaf(ov[t], ov[t], run2[hc][t]);
+                        for (int rs = 0; rs < 2; ++rs) {
+                            const uint32_t row = rows4[hf * 2 + rs];
+                            if (row == ~0u) continue;
+                            const float o0 = __uint_as_float(v[hf][4 * j + 2 * rs]), o1 = __uint_as_float(v[hf][4 * j + 2 * rs + 1]);
+                            *reinterpret_cast<float2*>(out + (size_t)row * kStemCo + hc * 32 + 8 * j + c2) = make_float2(o0, o1);
+                            if (stats) {
+                                run1[hc * 8 + 2 * j] += o0;      run2[hc * 8 + 2 * j] = fmaf(o0, o0, run2[hc * 8 + 2 * j]);
+                                run1[hc * 8 + 2 * j + 1] += o1;  run2[hc * 8 + 2 * j + 1] = fmaf(o1, o1, run2[hc * 8 + 2 * j + 1]);
+                            }
                         }
-                    }
-                }
-                __syncwarp();                       // the staging tile is rewritten by the next half-chunk
             }
         }
         if (stats) {
-            // lanes with equal (lane & 3) hold partial sums of the same 4 columns: reduce over the 8 row groups of the warp, over the
-            // 4 lane quarters through shared memory (the staging tiles are free now), then ONE fp64 atomic per column and CTA
+            // lanes with equal (lane & 3) hold partial sums of the same columns: reduce over the 8 row groups of the warp, over the
+            // 4 lane quarters through shared memory, then ONE fp64 atomic per column and CTA
             float* const s_red = s_stage;           // [4 quarters][2 sums][64]
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-            for (int hc = 0; hc < 4; ++hc)
+            for (int t = 0; t < 16; ++t) {
+                float a = run1[t], b = run2[t];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    float a = run1[hc][t], b = run2[hc][t];
-#pragma unroll
-                    for (int o = 4; o <= 16; o <<= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        b += __shfl_xor_sync(0xffffffffu, b, o);
-                    }
-                    if (lane < 4) {
-                        s_red[(q * 2 + 0) * kStemCo + hc * 16 + c4 + t] = a;
-                        s_red[(q * 2 + 1) * kStemCo + hc * 16 + c4 + t] = b;
-                    }
+                for (int o = 4; o <= 16; o <<= 1) {         // over the 8 lanes (rows) that own the same columns
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
                 }
+                if (lane < 4) {
+                    const int col = (t >> 3) * 32 + 8 * ((t & 7) >> 1) + c2 + (t & 1);
+                    s_red[(q * 2 + 0) * kStemCo + col] = a;
+                    s_red[(q * 2 + 1) * kStemCo + col] = b;
+                }
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int t = threadIdx.x - 64;      // 0..127 = (which, channel)
             const int which = t >> 6, ch = t & 63;
@@ -522,6 +519,7 @@ int stem_forward_run(const avid_conv_shape_t* s, const void* x_hi, const void* x
     int rc = stem_check(s, wp, &p);
     if (rc) return rc;
     AVID_REQUIRE(x_hi && w_hi && out && (x_lo == nullptr) == (w_lo == nullptr), "stem_forward_tc: NULL pointer / mismatched lo planes");
+    AVID_REQUIRE((int64_t)s->n * s->to * s->ho * s->wo < ((int64_t)1 << 31), "stem_forward_tc: more than 2^31 output pixels");
     p.x3 = x_lo != nullptr;
     const int planes = p.x3 ? 2 : 1, chunks = p.kt * p.kh;
     const int w_bytes = planes * chunks * kChunkBBytes;
