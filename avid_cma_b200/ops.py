@@ -470,7 +470,9 @@ def conv_forward_tc(s, x_hi, x_lo, w_hi, w_lo, addend=None, out=None, ci_real=No
     check(_lib.lib().avid_conv_forward_tc(C.byref(s), _p(x_hi, torch.bfloat16), _p(x_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
                                           _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out),
                                           _p(bn_stats, torch.float64, optional=True), _stream()))
-    _t1(e0, "conv_pair_forward" if e0 is not None and _lib.lib().avid_conv_tc_uses_cta_pairs(C.byref(s), 0) else "conv_forward_tc", _conv_flops(s, ci_real))
+    if e0 is not None:      # bench.py roofline records, one family per kernel instantiation
+        _t1(e0, "conv_pair_forward" if _lib.lib().avid_conv_tc_uses_cta_pairs(C.byref(s), 0) else "conv_forward_tc%d" % (128 if s.co % 128 == 0 else 64),
+            _conv_flops(s, ci_real))
     return out
 
 
@@ -494,7 +496,8 @@ def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None, bn_fuse=None
     check(_lib.lib().avid_conv_dgrad_tc(C.byref(s), _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
                                         _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out),
                                         C.byref(fuse) if fuse is not None else None, _stream()))
-    _t1(e0, "conv_pair_dgrad" if e0 is not None and _lib.lib().avid_conv_tc_uses_cta_pairs(C.byref(s), 1) else "conv_dgrad_tc", _conv_flops(s))
+    if e0 is not None:
+        _t1(e0, "conv_pair_dgrad" if _lib.lib().avid_conv_tc_uses_cta_pairs(C.byref(s), 1) else "conv_dgrad_tc%d" % (128 if s.ci % 128 == 0 else 64), _conv_flops(s))
     return out
 
 

@@ -544,7 +544,8 @@ def run_ours(a):
                 mean = sum(durs) / len(durs)
                 f.write("%3d %-18s %9.1f us  work %10.3e  rate %8.1f (TFLOP/s or GB/s)\n" % (i, name, mean * 1e3, work, work / (mean * 1e-3) / (1e9 if name.startswith("nce") else 1e12)))
     # roofline of the dominant kernel, from CUDA events recorded around every launch of the timed region.  Families are the
-    # instrumented entry points of ops.py; conv_forward_tc and conv_dgrad_tc are the same kernel (conv_tc_kernel) and are merged.
+    # instrumented entry points of ops.py; forward and input gradient of a kernel instantiation (conv_tc_kernel<128>, <64>,
+    # conv_pair_kernel) are merged.
     fam = {}
     for name, work, dur in prof:
         f = fam.setdefault(name, [0.0, 0.0, 0])
@@ -562,7 +563,8 @@ def run_ours(a):
         families[name]["GB/s" if name.startswith("nce") else "TFLOP/s"] = rate / (1e9 if name.startswith("nce") else 1e12)
     kernels = {}
     for name, (work, dur, cnt) in fam.items():
-        kname = {"conv_forward_tc": "conv_tc_kernel", "conv_dgrad_tc": "conv_tc_kernel", "conv_pair_forward": "conv_pair_kernel",
+        kname = {"conv_forward_tc128": "conv_tc_kernel<128>", "conv_dgrad_tc128": "conv_tc_kernel<128>", "conv_forward_tc64": "conv_tc_kernel<64>",
+                 "conv_dgrad_tc64": "conv_tc_kernel<64>", "conv_pair_forward": "conv_pair_kernel",
                  "conv_pair_dgrad": "conv_pair_kernel", "conv_wgrad_tc": "wgrad_tc_kernel",
                  "stem_forward_tc": "stem_forward_kernel", "stem_wgrad_tc": "stem_wgrad_kernel", "conv_forward": "conv_igemm_kernel",
                  "conv_dgrad": "conv_igemm_kernel", "conv_wgrad": "conv_wgrad_kernel"}.get(name)
