@@ -52,6 +52,12 @@ class ConvShape(C.Structure):
     _fields_ = [(n, c_int32) for n in ("n", "ti", "hi", "wi", "ci", "to", "ho", "wo", "co", "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw")]
 
 
+class VideoPrep(C.Structure):
+    """avid_video_prep_t (include/avid_b200.h)."""
+    _fields_ = [(n, c_int32) for n in ("frames", "height", "width", "crop_top", "crop_left", "crop_h", "crop_w", "out_h", "out_w", "flip", "num_ops")] + \
+               [("op_kind", c_int32 * 4), ("op_factor", c_float * 4), ("hue_shift", c_int32), ("normalize", c_int32), ("mean", c_float * 3), ("std", c_float * 3)]
+
+
 _P, _I, _L, _F, _Z, _U, _D = c_void_p, c_int32, c_int64, c_float, c_size_t, c_uint64, C.c_double
 _SIGNATURES = {
     "avid_version": (C.c_int, []),
@@ -72,6 +78,10 @@ _SIGNATURES = {
     "avid_cma_topk_finish": (C.c_int, [_L, _I, _P, _P, _Z, _P]),
     "avid_log_spectrogram_workspace_bytes": (c_size_t, [_I]),
     "avid_log_spectrogram": (C.c_int, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
+    "avid_video_prep_workspace_bytes": (c_size_t, [C.POINTER(VideoPrep)]),
+    "avid_video_prep": (C.c_int, [_P, C.POINTER(VideoPrep), _P, _P, _Z, _P]),
+    "avid_video_prep_batch_workspace_bytes": (c_size_t, [C.POINTER(VideoPrep), _I]),
+    "avid_video_prep_batch": (C.c_int, [C.POINTER(c_void_p), C.POINTER(VideoPrep), _I, C.POINTER(c_void_p), _P, _Z, _P]),
     "avid_cma_to_half": (C.c_int, [_P, _P, _L, _P]),
     "avid_cma_topk_scan_tc": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _P, _Z, _P]),
     "avid_cma_topk_rescore": (C.c_int, [_P, _P, _L, _P, _P, _L, _L, _I, _P, _Z, _P]),

@@ -397,6 +397,37 @@ int avid_log_spectrogram(const float* wave, int32_t batch, int32_t num_samples, 
                          float top_db, const float* mean, const float* stdv, float* out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Video half of the input side: VideoPrep_MSC_CJ.__call__ with augment=True (datasets/preprocessing.py:15-57) for ONE clip of
+ * uint8 RGB frames on the device, with the random decisions already drawn by the host in the reference's order
+ * (RandomResizedCrop.get_params video_transforms.py:330-371, RandomHorizontalFlip :86, ColorJitter.get_params + shuffle :413-463):
+ * crop -> Pillow's BILINEAR Image.resize -> optional left-right flip -> the colour ops in the given order on uint8 images
+ * (torchvision adjust_brightness / adjust_saturation / adjust_hue / adjust_contrast = ImageEnhance blends and an HSV round trip)
+ * -> ClipToTensor (/255, volume_transforms.py:14-70) -> Normalize ((x - mean) / std, tensor_transforms.py:13-38).  Bit-identical to
+ * Pillow 12: fixed-point resampling weights (Resample.c), float32 blends (Blend.c), Convert.c luma / HSV.
+ * frames (T, height, width, 3) uint8 -> out (3, T, out_h, out_w) float32. */
+#define AVID_VIDEO_OP_BRIGHTNESS 0
+#define AVID_VIDEO_OP_SATURATION 1
+#define AVID_VIDEO_OP_HUE        2
+#define AVID_VIDEO_OP_CONTRAST   3
+typedef struct avid_video_prep {
+    int32_t frames, height, width;                    /* the clip */
+    int32_t crop_top, crop_left, crop_h, crop_w;      /* (i, j, h, w) of RandomResizedCrop.get_params */
+    int32_t out_h, out_w;                             /* `crop` of VideoPrep_MSC_CJ */
+    int32_t flip;                                     /* random.random() < 0.5 */
+    int32_t num_ops;                                  /* colour ops in application order (0..4, at most one contrast) */
+    int32_t op_kind[4];                               /* AVID_VIDEO_OP_* */
+    float   op_factor[4];                             /* brightness / saturation / contrast factor, hue_factor in [-0.5, 0.5] */
+    int32_t hue_shift;                                /* np.uint8(hue_factor * 255) of F.adjust_hue, computed by the host in double */
+    int32_t normalize;                                /* 0: stop after /255 */
+    float   mean[3], std[3];
+} avid_video_prep_t;
+size_t avid_video_prep_workspace_bytes(const avid_video_prep_t* p_host);      /* 0 on invalid parameters */
+int avid_video_prep(const uint8_t* frames, const avid_video_prep_t* p_host, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* the same for `count` clips (one loader batch) given as HOST arrays of device pointers / parameter structs: 4 launches per 16 clips */
+size_t avid_video_prep_batch_workspace_bytes(const avid_video_prep_t* params_host, int32_t count);
+int avid_video_prep_batch(const uint8_t* const* frames_host, const avid_video_prep_t* params_host, int32_t count, float* const* out_host,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Sharded optimizer over NVLink peer memory -------------------------------------------------------------------------
  * Replaces DistributedDataParallel's gradient all-reduce (utils/main_utils.py:105-117) followed by torch.optim.Adam.step on every
  * rank (main_utils.py:250-256) for runs with W > 1 ranks on one node: rank r owns elements [r * S, (r + 1) * S) of the flat

@@ -180,3 +180,23 @@ def test_launcher_cli_matches_reference_flags():
     assert a.dist_backend == 'nccl' and a.gpu is None
     args = argparse.Namespace(distributed=False, rank=-1, dist_url='tcp://127.0.0.1:1', multiprocessing_distributed=False)
     assert MU.initialize_distributed_backend(args, 0).rank == 0
+
+
+def test_video_prep_host_logic_draws_like_the_oracle():
+    """datasets.gpu_preprocessing.VideoPrep_MSC_CJ.draw consumes the `random` stream in the reference's order (the oracle's draw_params is
+    pinned to the reference's goldens in tests/test_oracle_video.py)."""
+    import random
+    from avid_cma_b200.datasets.gpu_preprocessing import VideoPrep_MSC_CJ
+    from oracle import video as V
+    prep = VideoPrep_MSC_CJ(crop=(64, 64))
+    for seed, (w, h) in enumerate([(128, 96), (100, 150), (340, 256), (20, 400), (400, 20)]):
+        random.seed(seed)
+        a = prep.draw(w, h)
+        state = random.getstate()
+        random.seed(seed)
+        assert a == V.draw_params(w, h) and random.getstate() == state
+    prep = VideoPrep_MSC_CJ(crop=(64, 64), color=(0.4, 0., 0.4, 0.), min_area=0.5)
+    random.seed(7)
+    a = prep.draw(128, 96)
+    random.seed(7)
+    assert a == V.draw_params(128, 96, min_area=0.5, color=(0.4, 0., 0.4, 0.)) and [o[0] for o in a['ops']] in (['brightness', 'saturation'], ['saturation', 'brightness'])
