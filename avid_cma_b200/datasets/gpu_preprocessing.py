@@ -117,44 +117,55 @@ class VideoPrep_MSC_CJ(object):
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
             raise ValueError("frames must be a (T, H, W, 3) uint8 tensor")
         T, H, W, _ = frames.shape
-        p = _lib.VideoPrep()
-        p.frames, p.height, p.width = T, H, W
-        p.crop_top, p.crop_left, p.crop_h, p.crop_w = params['crop']
-        p.out_h, p.out_w = self.crop
-        p.flip = int(bool(params['flip']))
         ops = params['ops']
-        p.num_ops = len(ops)
+        kinds, factors, hue_shift = [0, 0, 0, 0], [0., 0., 0., 0.], 0
         for k, (name, f) in enumerate(ops):
-            p.op_kind[k], p.op_factor[k] = self.KINDS[name], f
+            kinds[k], factors[k] = self.KINDS[name], f
             if name == 'hue':
                 if not (-0.5 <= f <= 0.5):
                     raise ValueError('hue_factor is not in [-0.5, 0.5].')
-                p.hue_shift = int(f * 255) & 0xFF               # np.uint8(hue_factor * 255) of torchvision's adjust_hue
-        p.normalize = int(self.normalize)
-        for k in range(3):
-            p.mean[k], p.std[k] = self.mean[k], self.std[k]
-        return p
+                hue_shift = int(f * 255) & 0xFF                 # np.uint8(hue_factor * 255) of torchvision's adjust_hue
+        i, j, h, w = params['crop']
+        return _lib.VideoPrep(T, H, W, i, j, h, w, self.crop[0], self.crop[1], int(bool(params['flip'])), len(ops), self._i4(*kinds), self._f4(*factors),
+                              hue_shift, int(self.normalize), self._f3(*self.mean), self._f3(*self.std))
+
+    _i4, _f4, _f3 = C.c_int32 * 4, C.c_float * 4, C.c_float * 3
 
     def apply(self, frames, params):
         """One clip (T, H, W, 3) uint8 -> (3, T, crop_h, crop_w) float32 with the given decisions."""
         return self.apply_batch([frames], [params])[0]
 
-    def apply_batch(self, clips, params):
-        """`clips`: list of (T, H, W, 3) uint8 CUDA tensors (sizes may differ), `params`: one dict of decisions per clip.  One library call:
-        4 kernel launches per 16 clips.  Returns a list of (3, T, crop_h, crop_w) float32 tensors (views of one buffer when the frame
-        counts agree, so that torch.stack is free)."""
-        clips = [c.contiguous() for c in clips]
+    def plan_batch(self, clips, params):
+        """Everything of a batched call that happens on the host: parameter structs, output buffer, workspace, pointer arrays.
+        Returns (run, outs): `run()` enqueues the kernels (one library call: 4 launches per 16 clips) and returns `outs`, a list of
+        (3, T, crop_h, crop_w) float32 tensors -- slices of ONE (B, 3, T, h, w) buffer when the frame counts agree (outs.base)."""
+        clips = [c if c.is_contiguous() else c.contiguous() for c in clips]
         n = len(clips)
         P = (_lib.VideoPrep * n)(*[self._fill(c, q) for c, q in zip(clips, params)])
         dev = clips[0].device
         L_ = _lib.lib()
-        need = int(L_.avid_video_prep_batch_workspace_bytes(P, n))       # 0 on invalid parameters: the call below reports which
+        need = int(L_.avid_video_prep_batch_workspace_bytes(P, n))       # 0 on invalid parameters: the call reports which
         ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
-        outs = [torch.empty(3, c.shape[0], self.crop[0], self.crop[1], dtype=torch.float32, device=dev) for c in clips]
+        T = clips[0].shape[0]
+        if all(c.shape[0] == T for c in clips):
+            base = torch.empty(n, 3, T, self.crop[0], self.crop[1], dtype=torch.float32, device=dev)
+            outs = list(base.unbind(0))
+            p0, step = base.data_ptr(), base.stride(0) * 4
+            op = (C.c_void_p * n)(*[p0 + k * step for k in range(n)])
+        else:
+            outs = [torch.empty(3, c.shape[0], self.crop[0], self.crop[1], dtype=torch.float32, device=dev) for c in clips]
+            op = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
         fp = (C.c_void_p * n)(*[c.data_ptr() for c in clips])
-        op = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
-        check(L_.avid_video_prep_batch(fp, P, n, op, _p(ws, torch.uint8), ws.numel(), _stream()))
-        return outs
+        wp, wn = C.c_void_p(ws.data_ptr()), ws.numel()
+
+        def run(_keep=(clips, ws, P, fp, op)):
+            check(L_.avid_video_prep_batch(fp, P, n, op, wp, wn, _stream()))
+            return outs
+        return run, outs
+
+    def apply_batch(self, clips, params):
+        """`clips`: list of (T, H, W, 3) uint8 CUDA tensors (sizes may differ), `params`: one dict of decisions per clip."""
+        return self.plan_batch(clips, params)[0]()
 
     def __call__(self, frames):
         if isinstance(frames, (list, tuple)) or frames.dim() == 5:      # a loader batch: decisions drawn clip by clip, one library call

@@ -150,6 +150,65 @@ def torch_gpu_baseline(a, steps, warmup, device):
     return out
 
 
+def input_side(a, dev):
+    """SURVEY 8f-3 sub-record: the input-side steps on the GPU with the reference's CPU path (Pillow through torchvision's wrappers, oracle
+    port of the librosa spectrogram) timed beside them on a bounded sample.  Video: one batch of 64 decoded clips (8 x 256 x 340 uint8,
+    the Kinetics short-side-256 frames) -> (3, 8, 224, 224) float32 with VideoPrep_MSC_CJ's crop / flip / jitter / normalise."""
+    import random
+    import time
+    import numpy as np
+    from avid_cma_b200.datasets.gpu_preprocessing import VideoPrep_MSC_CJ
+    from oracle import video as OV
+    B, T, H, W = a.batch, a.frames, 256, 340
+    g = np.random.default_rng(0)
+    host = g.integers(0, 256, (B, T, H, W, 3), dtype=np.uint8)
+    clips = torch.from_numpy(host).to(dev)
+    prep = VideoPrep_MSC_CJ(crop=(a.size, a.size), num_frames=T)
+    random.seed(0)
+    params = [prep.draw(W, H) for _ in range(B)]
+    for _ in range(3):
+        prep.apply_batch(list(clips), params)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        outs = prep.apply_batch(list(clips), params)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    run, _ = prep.plan_batch(list(clips), params)      # the kernels alone: host-side planning (ctypes structs, buffers) outside the timed region
+    run()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_k = e0.elapsed_time(e1) / iters
+    # algorithmic bytes per clip: the crop is read once (uint8), the result written once (float32)
+    alg = sum(T * q['crop'][2] * q['crop'][3] * 3 for q in params) + B * 3 * T * a.size * a.size * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    n_cpu = 4
+    t0 = time.perf_counter()
+    for k in range(n_cpu):
+        ref = OV.video_prep_pil(host[k], params[k], crop=(a.size, a.size))
+    cpu_s = (time.perf_counter() - t0) / n_cpu
+    exact = bool(np.array_equal(outs[n_cpu - 1].cpu().numpy(), ref))
+    return {"video": {"what": "VideoPrep_MSC_CJ (crop + Pillow-exact bilinear resize + flip + colour jitter + normalise), %d clips of %dx%dx%d uint8 -> %dx%d float32, one avid_video_prep_batch call" % (B, T, H, W, a.size, a.size),
+                      "clips_per_s": B / (ms * 1e-3), "ms_per_batch": ms, "ms_per_batch_kernels_only": ms_k, "algorithmic_bytes_per_batch": alg,
+                      "roofline": {"bound": "hbm", "achieved": alg / (ms_k * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (ms_k * 1e-3) / 1e9 / hbm,
+                                   "note": "kernels only (4 launches per 16 clips); the public call adds the per-clip host planning"},
+                      "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "clips/s", "cores": 1, "kind": "reference",
+                                       "sample": "%d clips through Pillow %s (the library the reference's transforms execute), one thread" % (n_cpu, __import__("PIL").__version__)},
+                      "bit_exact_vs_pillow": exact}}
+
+
 def run_torch_gpu(a):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -627,6 +686,10 @@ def run_ours(a):
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_reference(a, 6, 1, a.cpu_sample_batch)
         line["cpu_baseline"] = cb
+        try:   # the input-side steps, measured beside the step they feed (diagnostic sub-record)
+            line["input_side"] = input_side(a, dev)
+        except Exception as e:   # noqa: BLE001
+            line["input_side"] = {"error": repr(e)[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
