@@ -42,6 +42,7 @@ def _run_backward(tower, dpooled, saved):
     ops.defer_filter_gradients(True)          # every filter gradient is brought to the PyTorch layout by ONE launch at the end
     try:
         tower._bwd(dpooled, saved, grads, tower.math)
+        ops.side_join()                       # filter gradients enqueued on the side stream (AVID_WGRAD_STREAM=1)
         ops.flush_filter_gradients()
     finally:
         ops.defer_filter_gradients(False)

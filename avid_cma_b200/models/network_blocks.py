@@ -186,7 +186,11 @@ class ConvBNReLU:
             dz, dgamma, dbeta = ops.bn_relu_backward_act(z, dy, st, bn.weight.detach(), bn.bias.detach(), want_f32=want_f32,
                                                          want_planes=op.tc, x3=op.x3, sums=sums)
         grads[bn.weight], grads[bn.bias] = dgamma, dbeta
-        grads[op.conv.weight] = op.wgrad(x, dz)
+        side = ops.wgrad_stream_enabled() and op.tc and need_dx
+        if side:
+            ready = ops.side_event()          # dz is complete here; the filter gradient is enqueued after the input gradient (below)
+        else:
+            grads[op.conv.weight] = op.wgrad(x, dz)
         dx, sums_below = None, None
         if need_dx:
             fuse = None
@@ -195,6 +199,8 @@ class ConvBNReLU:
                 sums_below = ops.bn_backward_sums(z_b.shape[-1], z_b.device)
                 fuse = (z_b, st_b, bn_b.weight.detach(), bn_b.bias.detach(), sums_below)
             dx = op.dgrad(dz, addend=dx_addend, bn_fuse=fuse) if fuse is not None else op.dgrad(dz, addend=dx_addend)
+        if side:
+            grads[op.conv.weight] = ops.side_run(ready, lambda: op.wgrad(x, dz), keep=(x, dz))
         return dx, dz, sums_below
 
 
