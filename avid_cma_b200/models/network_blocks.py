@@ -187,9 +187,7 @@ class ConvBNReLU:
                                                          want_planes=op.tc, x3=op.x3, sums=sums)
         grads[bn.weight], grads[bn.bias] = dgamma, dbeta
         side = ops.wgrad_stream_enabled() and op.tc and need_dx
-        if side:
-            ready = ops.side_event()          # dz is complete here; the filter gradient is enqueued after the input gradient (below)
-        else:
+        if not side:
             grads[op.conv.weight] = op.wgrad(x, dz)
         dx, sums_below = None, None
         if need_dx:
@@ -200,6 +198,10 @@ class ConvBNReLU:
                 fuse = (z_b, st_b, bn_b.weight.detach(), bn_b.bias.detach(), sums_below)
             dx = op.dgrad(dz, addend=dx_addend, bn_fuse=fuse) if fuse is not None else op.dgrad(dz, addend=dx_addend)
         if side:
+            # The filter gradient starts when the input gradient has DRAINED (event after it, AVID_WGRAD_STREAM=2: before it): two persistent
+            # tensor-core grids cannot share the SMs anyway, and this way the wgrad CTAs and the BatchNorm-backward pass of the next layer
+            # down (main stream, no shared memory) start together instead of the wgrad winning the SMs ahead of the critical path
+            ready = ops.side_event()
             grads[op.conv.weight] = ops.side_run(ready, lambda: op.wgrad(x, dz), keep=(x, dz))
         return dx, dz, sums_below
 

@@ -91,9 +91,9 @@ def _timed(name):
 # ---- filter gradients on a side stream --------------------------------------------------------------------------------------
 # The filter gradient of a layer is off the critical path of the backward pass (nothing but the optimizer reads it), while the
 # BatchNorm-backward apply of the NEXT layer down is on it and is HBM-bound with no shared memory.  With AVID_WGRAD_STREAM=1 (default) every
-# tensor-core filter gradient is enqueued on a side stream AFTER the input gradient of its layer: the persistent wgrad CTAs take the
-# SMs once the input gradient has drained, and the BatchNorm pass that follows it on the main stream shares the SMs with them
-# (measured A/B in one run: 25.12 / 25.17 ms -> 24.90 / 24.93 ms per step).
+# tensor-core filter gradient is enqueued on a side stream behind an event recorded AFTER the input gradient of its layer: the persistent
+# wgrad CTAs start once the input gradient has drained, together with the BatchNorm pass that follows it on the main stream
+# (measured A/B in one run: 24.71 / 24.97 ms -> 24.31 / 24.65 ms per step).
 _side_streams = {}
 _side_keep = []
 
