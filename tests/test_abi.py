@@ -122,3 +122,30 @@ def test_product_code_never_imports_the_oracle():
     body = bench[bench.index("def run_ours"):bench.index("if __name__")]
     calls = [m.start() for m in pat.finditer(body)]
     assert not calls, "run_ours() must not import the oracle (cpu_baseline goes through cpu_reference())"
+
+
+def test_video_prep_planning_is_host_only(lib):
+    """avid_video_prep_workspace_bytes validates the parameters and sizes the workspace without touching a GPU (0 = invalid)."""
+    p = _lib.VideoPrep()
+    p.frames, p.height, p.width = 8, 256, 340
+    p.crop_top, p.crop_left, p.crop_h, p.crop_w = 10, 20, 200, 250
+    p.out_h, p.out_w = 224, 224
+    p.num_ops = 2
+    p.op_kind[0], p.op_factor[0] = 3, 1.2       # contrast
+    p.op_kind[1], p.op_factor[1] = 2, 0.1       # hue
+    need = lib.avid_video_prep_workspace_bytes(C.byref(p))
+    # horizontal-pass image (8 x 200 x 224 x 3) + resized image (8 x 224 x 224 x 3) + weight tables + luma sums
+    assert need >= 8 * 200 * 224 * 3 + 8 * 224 * 224 * 3 and need < 2 * (8 * 200 * 224 * 3 + 8 * 224 * 224 * 3)
+    arr = (_lib.VideoPrep * 3)(p, p, p)
+    assert lib.avid_video_prep_batch_workspace_bytes(arr, 3) == 3 * need
+    bad = _lib.VideoPrep.from_buffer_copy(p)
+    bad.crop_w = 400                              # box outside the frame
+    assert lib.avid_video_prep_workspace_bytes(C.byref(bad)) == 0
+    assert b"crop box" in lib.avid_last_error()
+    bad = _lib.VideoPrep.from_buffer_copy(p)
+    bad.op_kind[1] = 3                            # two contrast ops
+    assert lib.avid_video_prep_workspace_bytes(C.byref(bad)) == 0
+    bad = _lib.VideoPrep.from_buffer_copy(p)
+    bad.op_factor[1] = 0.75                       # hue_factor outside [-0.5, 0.5]: the reference raises too
+    assert lib.avid_video_prep_workspace_bytes(C.byref(bad)) == 0 and b"hue_factor" in lib.avid_last_error()
+    assert lib.avid_video_prep(None, C.byref(p), None, None, 0, None) == 1      # AVID_EINVAL
