@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, 3) bn_relu_backward_apply_kernel(const fl
 // covered by the four pooling windows (a..a+1, b..b+1) only, so one thread loads 4 argmax entries + 4 pooled gradients (all
 // independent, no data-dependent branches) for 4 output pixels instead of walking up to 4 windows per pixel.  Window (oh, ow)
 // holds pixel (ih, iw) at position (ih - 2 oh + 1) * 3 + (iw - 2 ow + 1).
-__global__ void __launch_bounds__(256) bn_relu_pool_backward_apply_kernel(const float* __restrict__ z, const uint8_t* __restrict__ argmax,
+__global__ void __launch_bounds__(256, 3) bn_relu_pool_backward_apply_kernel(const float* __restrict__ z, const uint8_t* __restrict__ argmax,
                                                                           const float* __restrict__ dyp, const float* __restrict__ mean,
                                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                           const float* __restrict__ beta, const double* __restrict__ sums,
