@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(128) video_coeffs_kernel(const VideoBatch b) {
     const int in_size = y_axis ? a.p.crop_h : a.p.crop_w, out_size = y_axis ? a.p.out_h : a.p.out_w, ksize = y_axis ? a.ksize_y : a.ksize_x;
     int* const bounds = y_axis ? a.by : a.bx;
     int* const kk = y_axis ? a.ky : a.kx;
+    if (blockIdx.x == 0 && blockIdx.y == 0)                          // the luma sums of the contrast op start at zero (before any thread leaves)
+        for (int t = threadIdx.x; t < a.p.frames; t += blockDim.x) a.lsum[t] = 0u;
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     if (xx >= out_size) return;
     const double scale = __ddiv_rn((double)in_size, (double)out_size);
@@ -78,8 +80,6 @@ __global__ void __launch_bounds__(128) video_coeffs_kernel(const VideoBatch b) {
     }
     bounds[2 * xx] = xmin;
     bounds[2 * xx + 1] = xmax;
-    if (blockIdx.x == 0 && blockIdx.y == 0)                          // the luma sums of the contrast op start at zero
-        for (int t = threadIdx.x; t < a.p.frames; t += blockDim.x) a.lsum[t] = 0u;
 }
 
 __device__ __forceinline__ uint8_t clip8(int v) {      // Resample.c clip8: lookup of (ss >> PRECISION_BITS) clamped to [0, 255]

@@ -116,6 +116,17 @@ def test_batched_call_equals_clip_by_clip():
     assert tuple(out.shape) == (5, 3, 4, 32, 40) and all(torch.equal(out[k], prep(same[k])) for k in range(5))
 
 
+def test_many_frames_small_output_with_contrast():
+    """More frames than output columns: every frame's luma sum must start at zero (the sums are cleared by the weight kernel)."""
+    frames = _clip(40, 24, 20, seed=11)
+    params = dict(crop=(2, 1, 20, 16), flip=True, ops=[("brightness", 1.2), ("contrast", 0.7), ("hue", 0.1)])
+    prep = _prep((8, 6))
+    dev_frames = torch.from_numpy(frames).to(DEV)
+    want = V.video_prep_np(frames, params, crop=(8, 6))
+    for _ in range(2):                                   # twice: the second call reuses a workspace with stale sums
+        assert np.array_equal(prep.apply(dev_frames, params).cpu().numpy(), want)
+
+
 def test_arguments_and_edges():
     prep = _prep((16, 16), num_frames=5, pad_missing=True)
     frames = torch.from_numpy(_clip(2, 20, 24, seed=5)).to(DEV)
