@@ -8,7 +8,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libavid_b200.so")
+LIB_PATH = os.environ.get("AVID_B200_LIB") or os.path.join(HERE, "libavid_b200.so")      # the override is for A/B probes of a kernel build
 HEADER = os.path.join(os.path.dirname(HERE), "include", "avid_b200.h")
 
 AVID_MAX_KEYS = 8

@@ -92,18 +92,23 @@ __host__ __device__ inline uint64_t uniform_below(uint32_t r0, uint32_t r1, uint
 // The negative for instance b, slot k: reference semantics
 //   AVID     (avid.py:82-86):        r ~ U[0, N-1);            idx = r + (r >= y)
 //   AVID-CMA (avid_cma.py:200-207):  r ~ U[0, N-pos_k);        idx = r + #{j : r >= pos[j] - j}
+// the y- / positive-set-dependent half of a draw, from the 64 random bits of its counter
+__host__ __device__ inline int64_t finish_negative(uint32_t r0, uint32_t r1, int64_t N, int64_t y, const int32_t* pos_row, int pos_k) {
+    if (pos_row == nullptr) {
+        int64_t r = (int64_t)uniform_below(r0, r1, (uint64_t)(N - 1));
+        return r + (r >= y ? 1 : 0);
+    }
+    int64_t r = (int64_t)uniform_below(r0, r1, (uint64_t)(N - pos_k));
+    int shift = 0;
+    for (int j = 0; j < pos_k; ++j) shift += (r >= (int64_t)pos_row[j] - j) ? 1 : 0;
+    return r + shift;
+}
+
 __host__ __device__ inline int64_t draw_negative(uint64_t seed, uint64_t offset, int b, int k, int K,
                                                  int64_t N, int64_t y, const int32_t* pos_row, int pos_k) {
     uint32_t rnd[4];
     Philox::generate(seed, offset + (uint64_t)b * (uint64_t)K + (uint64_t)k, rnd);
-    if (pos_row == nullptr) {
-        int64_t r = (int64_t)uniform_below(rnd[0], rnd[1], (uint64_t)(N - 1));
-        return r + (r >= y ? 1 : 0);
-    }
-    int64_t r = (int64_t)uniform_below(rnd[0], rnd[1], (uint64_t)(N - pos_k));
-    int shift = 0;
-    for (int j = 0; j < pos_k; ++j) shift += (r >= (int64_t)pos_row[j] - j) ? 1 : 0;
-    return r + shift;
+    return finish_negative(rnd[0], rnd[1], N, y, pos_row, pos_k);
 }
 
 }  // namespace avid

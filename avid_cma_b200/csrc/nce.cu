@@ -4,10 +4,11 @@
 // bank row is read from HBM exactly once (one coalesced 512-byte request per warp) and serves the
 // forward score, the loss term and the gradient w.r.t. the embedding in the same pass.
 //
-// Kernel 1  nce_gather_kernel   grid (B, splits) x 128 threads.  A warp streams rows 8 at a time:
-//           groups of 8 lanes own one row each (16 columns per lane, 128-byte coalesced group loads), 2 x 4 rows x
-//           2 banks in flight per warp; dot product = 16 FMAs + 3 shuffles, the NCE math runs per group, the
-//           gradient axpy needs no broadcast.  Partial (grad_hat, loss) per split go to the workspace.
+// Kernel 1  nce_gather_kernel   grid (B, splits) x 128 threads.  A warp streams its contiguous range of rows in quads:
+//           groups of 8 lanes own one row each (16 columns per lane, 128-byte coalesced group loads), a ring of 2 quads x
+//           2 banks in flight per warp (the next quad is requested before the current one is scored); dot product = 16 FMAs
+//           + 3 shuffles, the NCE math runs per group (lane l8 = key l8), the gradient axpy needs no broadcast.  Partial
+//           (grad_hat, loss) per split go to the workspace.
 //           The LAST split CTA of a query (ticket counter) sums the partials in a fixed order (deterministic) and applies
 //           the backward of F.normalize; the last query forms the batch means and the coefficient mix: one launch per step.
 //           The B + 1 ticket counters live at the start of the workspace, must be zero on entry and are left zero.
@@ -51,6 +52,8 @@ struct NceParams {
     int64_t* neg_idx_out;
     unsigned int* counter;      // [B + 1] tickets: splits done per query, queries done; zero on entry, left zero
     bool need[2][2];    // need[bank][ctx]: some key scores this bank against this context
+    unsigned long long* dbg;    // AVID_NCE_DEBUG: 8 %globaltimer stamps per CTA (first 1024 CTAs), else nullptr
+    int coef_lane[4];   // pair 2 * bank + ctx: the one key that scores it, or -1 (none, or several: summed over the group)
     bool bank_used[2];
     // tail of the fused kernel: the last split of a query reduces it, the last query forms the batch means
     float* grad_hat[2];         // optional (B,128): reduced gradient w.r.t. the normalised embedding (sharded protocol)
@@ -87,202 +90,217 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 __device__ __forceinline__ float dot16(const float4 (&a)[4], const float4 (&b)[4]) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s += dot4(a[j], b[j]);
-    return s;
+    return (dot4(a[0], b[0]) + dot4(a[1], b[1])) + (dot4(a[2], b[2]) + dot4(a[3], b[3]));      // four independent FMA chains
 }
 
-// x / max(||x||, 1e-12) for the row `b` of a (B,128) matrix in the group layout (avid.py:52-53)
-__device__ __forceinline__ void load_normalized(const float* emb, int b, int l8, float4 (&out)[4]) {
-    const float4* src = reinterpret_cast<const float4*>(emb + (size_t)b * kD);
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        out[j] = src[l8 + 8 * j];
-        ss += dot4(out[j], out[j]);
-    }
-    const float inv = 1.0f / fmaxf(sqrtf(group_sum(ss)), 1e-12f);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = make_float4(out[j].x * inv, out[j].y * inv, out[j].z * inv, out[j].w * inv);
-}
-
-// a warp keeps 2 row quads (4 rows each) per bank in flight: 2 x 4 rows x 2 banks x 512 B = 8 KB.
+// A warp keeps TWO row quads (4 rows x 2 banks x 512 B = 4 KB each) in flight in registers and walks them as a ring: the next
+// request of a slot is issued as soon as its quad is scored.  What the %globaltimer stamps of scripts/debug_nce_timeline.py show
+// at B = 64, K = 1024 (384 CTAs, 11 quads per warp): 2.0 us until the first rows are requested, 14 us in the loop -- 67 MB at
+// 4.8 TB/s with 12.6 MB in flight, i.e. the loop is bound by the bytes in flight (Little: ~2.6 us per round trip under that
+// load), NOT by the order of requests and scoring (requesting both quads together after scoring both gives the same times at
+// every K) -- then 6 us of tail (partials, fence, ticket, last split reduces, fence, ticket, last query) and ~6 us between the
+// events and the first / last instruction.  Second session of round 2: the per-quad instruction count went from ~290 to ~170
+// (key constants folded per lane, (bank, ctx) pairs as template parameter, rcp / lg2 approximations behind a series for
+// log1p, packed item descriptors, coefficient by one shuffle), the Philox rounds of the first chunk run while y is in flight,
+// the last split CTA finalises a query with one warp per context and no block barrier: 36.9 -> 30.7 us at K = 1024 (same box,
+// A/B), 75.8 -> 73.7 us at K = 4096, 213.9 -> 228.2 us at K = 16384 (0.77 -> 0.72 of the measured HBM rate: not understood).
 // Measured and dropped (round 2): landing the rows in a per-warp shared-memory ring instead of registers -- with per-row
 // cp.async.bulk copies (request-rate bound: ~35 cycles per 512-byte request and SM; K = 1024: 49 us vs 39 us) and with cp.async
-// 16 B per lane (58 us; K = 16384: 0.60 instead of 0.77 of the HBM peak): the extra shared-memory hop costs more than the deeper
-// queue gives, because the kernel is bound by its few dependent round trips, not by bytes in flight.  Also dropped: a per-lane
-// prefetch.global.L2 of the chunk's rows before scoring it (32 scattered lines per instruction: K = 1024 47 us, K = 16384 0.52),
-// and TMA tile::gather4 requests (4 rows per request, scripts/probes/gather4_tma.cu: correct, but the TMA unit serves ~one 512-byte
-// row per ~60 cycles and SM: K = 1024 49 us, K = 16384 0.35 of the HBM peak with a 6-stage ring).  Same box, register path:
-// 37 us / 0.54 (K = 4096) / 0.77 (K = 16384).  Little's law on those numbers: ~96 KB in flight per SM at 5.0 TB/s is an
-// effective round trip of ~2.8 us for random 512-byte rows, so K = 1024 (8 dependent round trips per warp) cannot go below ~25 us
-// in this structure.
+// 16 B per lane (58 us; K = 16384: 0.60 instead of 0.77 of the HBM peak).  Also dropped: a per-lane prefetch.global.L2 of the
+// chunk's rows before scoring it (32 scattered lines per instruction: K = 1024 47 us, K = 16384 0.52), and TMA tile::gather4
+// requests (4 rows per request, scripts/probes/gather4_tma.cu: correct, but the TMA unit serves ~one 512-byte row per ~60 cycles
+// and SM: K = 1024 49 us, K = 16384 0.35 of the HBM peak with a 6-stage ring).
 constexpr int kGatherSmem = 0;
 
-__global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {
-    const int b = blockIdx.x, split = blockIdx.y;
+__device__ __forceinline__ void stamp(const NceParams& p, int slot) {
+    if (p.dbg && threadIdx.x == 0) {
+        const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+        if (cta < 1024u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.dbg[cta * 8 + slot] = t;
+        }
+    }
+}
+
+// lane-parallel description of 32 consecutive items of a warp's range, packed for the shuffles that hand it to the groups:
+// off = row index inside this rank's shard; tag = (kk << 2) | (kind + 1) with kind 0 = negative kk, 1 = self, 2 = positive-set
+// entry kk; tag 0 = nothing to score (past the range, or a row another shard holds)
+struct ItemDesc {
+    int off, tag;
+};
+
+struct GatherCtx {
+    int b, npos, k_begin, w_end;
+    int64_t y;
+    const int32_t* pos_row;
+    const int64_t* negs;
+};
+
+// `bits`: the Philox output of the item's counter when the caller drew it ahead of time (the first chunk, before y arrived)
+__device__ __forceinline__ ItemDesc describe_item(const NceParams& p, const GatherCtx& g, int item, const uint32_t* bits = nullptr) {
+    ItemDesc d{0, 0};
+    if (item < g.w_end) {
+        int kind, kk;
+        int64_t idx;
+        if (item < g.npos) {
+            kind = item == 0 ? 1 : 2;
+            kk = item - 1;
+            idx = item == 0 ? g.y : (g.pos_row ? (int64_t)g.pos_row[item - 1] : -1);
+        } else {
+            kind = 0;
+            kk = g.k_begin + (item - g.npos);
+            if (g.negs) idx = g.negs[kk];
+            else if (bits) idx = finish_negative(bits[0], bits[1], p.N, g.y, g.pos_row, p.pos_k);
+            else idx = draw_negative(p.seed, p.offset, g.b, kk, p.K, p.N, g.y, g.pos_row, p.pos_k);
+            if (p.neg_idx_out) p.neg_idx_out[(size_t)g.b * p.K + kk] = idx;
+        }
+        if (idx >= p.row_begin && idx < p.row_end) {      // rows another shard holds are scored there
+            d.off = (int)(idx - p.row_begin);
+            d.tag = (kk << 2) | (kind + 1);
+        }
+    }
+    return d;
+}
+
+// request quad q (0..7) of the described chunk: group grp of the warp takes item 4 q + grp
+__device__ __forceinline__ void request_quad(const NceParams& p, const ItemDesc& d, int q, int grp, int l8, float4 (&rv)[4], float4 (&ra)[4],
+                                             int& tag) {
+    const int src = 4 * q + grp;
+    const int off = __shfl_sync(0xffffffffu, d.off, src);
+    tag = __shfl_sync(0xffffffffu, d.tag, src);
+    if (tag != 0) {      // otherwise the registers keep the (finite) rows of an earlier quad: they are scored with coefficient 0
+        const size_t o = (size_t)off * kD;
+        if (p.bank_used[0]) {
+            const float4* r = reinterpret_cast<const float4*>(p.bank[0] + o) + l8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = ld_stream(r + 8 * j);
+        }
+        if (p.bank_used[1]) {
+            const float4* r = reinterpret_cast<const float4*>(p.bank[1] + o) + l8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ra[j] = ld_stream(r + 8 * j);
+        }
+    }
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {      // x normal and positive here: 1 ulp, no denormal scaling code
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// log(1 + x) for x >= 0 without the libm slow paths: the alternating series below 2^-4 (truncation < 1e-8 relative), lg2.approx
+// above (absolute error 1.7e-7 on a value >= 0.06).  The loss terms of the negatives are ~1/K each, where log(1 + x) formed from
+// a rounded 1 + x would lose 4 digits.
+__device__ __forceinline__ float log1p_pos(float x) {
+    const float small = x * fmaf(-x, fmaf(-x, fmaf(-x, fmaf(-x, fmaf(-x, 1.0f / 6.0f, 0.2f), 0.25f), 1.0f / 3.0f), 0.5f), 1.0f);
+    return x < 0.0625f ? small : 0.69314718056f * lg2_approx(1.0f + x);
+}
+
+// what lane l8 of every group needs of "its" key (key l8), folded once per kernel
+struct LaneKey {
+    int sel;            // 2 * bank + ctx: which of the four dot products the key scores
+    int neg_limit;      // negatives kk < neg_limit count for the key (0: key slot unused)
+    int pos_ok;         // bit 0: scores the self positive, bit 1: scores the positive-set entries
+    float c, inv_c;     // K_key * Z (nce.py:42-57) and its reciprocal
+    float w_neg, w_pos; // weight / mean_batch / T, and the same * -(1 / number of positives the key averages over)
+    float inv_p;
+};
+
+// NEED >= 0: the (bank, ctx) pairs the keys score, bit 2 * bank + ctx, known at compile time (6 = cross, 9 = self, 15 = joint:
+// no uniform branches in the hot loop); NEED < 0: read from the parameters
+template <int NEED>
+__device__ __forceinline__ bool needs(const NceParams& p, int bank, int ctx) {
+    return NEED >= 0 ? ((NEED >> (2 * bank + ctx)) & 1) != 0 : p.need[bank][ctx];
+}
+
+// coefficient of the pair `sel` for this group's row: every key's coefficient sits on lane (key) of the group
+template <int NEED>
+__device__ __forceinline__ float pair_coef(const NceParams& p, int sel, float coef, int my_sel, int lane) {
+    if (!needs<NEED>(p, sel >> 1, sel & 1)) return 0.f;
+    if (p.coef_lane[sel] >= 0) return __shfl_sync(0xffffffffu, coef, (lane & 24) | p.coef_lane[sel]);      // one key scores the pair
+    return group_sum(my_sel == sel ? coef : 0.f);
+}
+
+// score one quad: lane l8 of a group evaluates key l8 for the group's row (the transcendental NCE math is lane-parallel over
+// the keys), the coefficients are handed to the 8 lanes of the group, the gradient axpy needs no broadcast of the row.
+template <int NEED, bool TRAIN>
+__device__ __forceinline__ void score_quad(const NceParams& p, const float4 (&rv)[4], const float4 (&ra)[4], int tag,
+                                           const float4 (&e_ctx)[2][4], float4 (&acc)[2][4], float& loss_acc, const LaneKey& key,
+                                           int my_key, int b, int lane) {
+    if (__all_sync(0xffffffffu, tag == 0)) return;      // a quad of rows other shards hold (or the padding of the last quad)
+    const float d00 = needs<NEED>(p, 0, 0) ? group_sum(dot16(rv, e_ctx[0])) : 0.f;      // d[bank][ctx]
+    const float d01 = needs<NEED>(p, 0, 1) ? group_sum(dot16(rv, e_ctx[1])) : 0.f;
+    const float d10 = needs<NEED>(p, 1, 0) ? group_sum(dot16(ra, e_ctx[0])) : 0.f;
+    const float d11 = needs<NEED>(p, 1, 1) ? group_sum(dot16(ra, e_ctx[1])) : 0.f;
+    const int kind = (tag & 3) - 1, kk = tag >> 2;
+    const bool applies = kind == 0 ? kk < key.neg_limit : (kind > 0 && ((key.pos_ok >> (kind - 1)) & 1));
+    float coef = 0.f;
+    if (applies) {
+        float d;
+        if (NEED == 6) d = key.sel == 1 ? d01 : d10;
+        else if (NEED == 9) d = key.sel == 0 ? d00 : d11;
+        else d = key.sel < 2 ? (key.sel == 0 ? d00 : d01) : (key.sel == 2 ? d10 : d11);
+        const float s = d * p.inv_T;
+        if (p.scores) {      // optional raw scores (always on in the partition-function pass)
+            const int slot = kind == 1 ? 0 : (kind == 2 ? 1 + kk : 1 + p.score_pos_k + kk);
+            p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot] = s;
+        }
+        if (TRAIN) {
+            // nce.py:42-57 with c = K_key * Z: a negative contributes log(1 + e / c) and pulls with e / (e + c), a positive
+            // contributes log(1 + c / e) (averaged over the positive set) and pushes with c / (e + c)
+            const float e = expf(s);
+            const float inv_ec = rcp_approx(e + key.c);
+            const bool neg = kind == 0;
+            const float x = neg ? e * key.inv_c : key.c * rcp_approx(e);
+            const float term = log1p_pos(x);
+            loss_acc += neg ? term : key.inv_p * term;
+            coef = neg ? key.w_neg * (e * inv_ec) : key.w_pos * (key.c * inv_ec);
+        }
+    }
+    if (!TRAIN) return;
+    const float cf00 = pair_coef<NEED>(p, 0, coef, key.sel, lane), cf01 = pair_coef<NEED>(p, 1, coef, key.sel, lane);
+    const float cf10 = pair_coef<NEED>(p, 2, coef, key.sel, lane), cf11 = pair_coef<NEED>(p, 3, coef, key.sel, lane);
+    if (needs<NEED>(p, 0, 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy4(acc[0][j], cf00, rv[j]);
+    }
+    if (needs<NEED>(p, 1, 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy4(acc[0][j], cf10, ra[j]);
+    }
+    if (needs<NEED>(p, 0, 1)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy4(acc[1][j], cf01, rv[j]);
+    }
+    if (needs<NEED>(p, 1, 1)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy4(acc[1][j], cf11, ra[j]);
+    }
+}
+
+// x / max(||x||, 1e-12) in place for a row held in the group layout (avid.py:52-53)
+__device__ __forceinline__ void normalize_group(float4 (&e)[4]) {
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ss += dot4(e[j], e[j]);
+    const float inv = 1.0f / fmaxf(sqrtf(group_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = make_float4(e[j].x * inv, e[j].y * inv, e[j].z * inv, e[j].w * inv);
+}
+
+// tail of the training kernel: partial (grad_hat, loss) of this CTA to the workspace; the last split CTA of a query reduces it,
+// the last query forms the batch means
+__device__ __forceinline__ void finish_query(const NceParams& p, float4 (&acc)[2][4], float loss_acc, int b, int bl, int g_i, int split,
+                                             const float* emb0, const float* emb1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, l8 = lane & 7;
-    // gathered queries of a sharded step arrive as one packed record per rank (group): query b = (group g, row bl)
-    const int g_i = p.group_batch > 0 ? b / p.group_batch : 0, bl = p.group_batch > 0 ? b - g_i * p.group_batch : b;
-    const size_t in_off = (size_t)g_i * p.in_group_stride;          // bytes
-    const float* emb0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[0]) + in_off);
-    const float* emb1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[1]) + in_off);
-    const int64_t* negs = p.neg_idx ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg_idx) + in_off) + (size_t)bl * p.K : nullptr;
-
-    float4 e_ctx[2][4];
-    load_normalized(emb0, bl, l8, e_ctx[0]);
-    load_normalized(emb1, bl, l8, e_ctx[1]);
-    int64_t y = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.y) + in_off)[bl];
-    if (y < 0 || y >= p.N) {       // the reference raises IndexError here (avid.py:57-58): report it, score no positive, read nothing
-        if (p.bad_index && threadIdx.x == 0 && split == 0) *p.bad_index = 1;
-        y = -1;
-    }
-    const float Z = p.Z ? *p.Z : 1.0f;
-    const int32_t* pos_row = (p.positive_set && p.pos_k > 0 && y >= 0) ? p.positive_set + (size_t)y * p.pos_k : nullptr;
-
-    // item stream of this CTA: [self, positives...] (split 0 only) then negatives [k_begin, k_end)
-    const int npos = (split == 0) ? 1 + (pos_row ? p.pos_k : 0) : 0;
-    const int k_begin = split * p.kc, k_end = min(p.K, k_begin + p.kc);
-    const int n_items = npos + max(0, k_end - k_begin);
-
-    float4 acc[2][4];                 // grad_hat for ctx video / audio, this lane's 16 columns
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // the transcendental NCE math is lane-parallel inside a group: lane l8 evaluates (row quad l8 >> 2, key (l8 & 3) + 4 * pass)
-    float loss_acc[2] = {0.f, 0.f};
-    const int key_passes = (p.num_keys + 3) >> 2;
-    const int u_sel = l8 >> 2;
-
-    for (int c0 = warp * 32; c0 < n_items; c0 += kGatherWarps * 32) {
-        // each lane describes one item of the chunk: kind 0 = negative k, 1 = self, 2 = positive-set entry
-        const int item = c0 + lane;
-        int kind = -1, kk = 0;
-        int64_t idx = -1;
-        if (item < n_items) {
-            if (item < npos) {
-                kind = item == 0 ? 1 : 2;
-                kk = item - 1;
-                idx = item == 0 ? y : (int64_t)pos_row[item - 1];
-            } else {
-                kind = 0;
-                kk = k_begin + (item - npos);
-                idx = negs ? negs[kk] : draw_negative(p.seed, p.offset, b, kk, p.K, p.N, y, pos_row, p.pos_k);
-                if (p.neg_idx_out) p.neg_idx_out[(size_t)b * p.K + kk] = idx;
-            }
-        }
-        if (!(idx >= p.row_begin && idx < p.row_end)) kind = -1;      // rows another shard holds are scored there
-        const int n_chunk = min(32, n_items - c0);
-
-        for (int j0 = 0; j0 < n_chunk; j0 += 8) {
-            float4 rv[2][4], ra[2][4];
-            int kind_u[2], kk_u[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int src = (j0 + 4 * u + grp) & 31;          // the item this group scores in quad u
-                const int64_t idx_u = __shfl_sync(0xffffffffu, idx, src);
-                kind_u[u] = __shfl_sync(0xffffffffu, kind, src);
-                kk_u[u] = __shfl_sync(0xffffffffu, kk, src);
-                if (j0 + 4 * u + grp >= n_chunk) kind_u[u] = -1;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    rv[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ra[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (kind_u[u] >= 0) {
-                    const size_t off = (size_t)(idx_u - p.row_begin) * kD;
-                    if (p.bank_used[0]) {
-                        const float4* r = reinterpret_cast<const float4*>(p.bank[0] + off) + l8;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) rv[u][j] = ld_stream(r + 8 * j);
-                    }
-                    if (p.bank_used[1]) {
-                        const float4* r = reinterpret_cast<const float4*>(p.bank[1] + off) + l8;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ra[u][j] = ld_stream(r + 8 * j);
-                    }
-                }
-            }
-            // d[u][bank][ctx] of this group's two rows, on all 8 lanes of the group
-            float d[2][2][2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                d[u][0][0] = p.need[0][0] ? group_sum(dot16(rv[u], e_ctx[0])) : 0.f;
-                d[u][0][1] = p.need[0][1] ? group_sum(dot16(rv[u], e_ctx[1])) : 0.f;
-                d[u][1][0] = p.need[1][0] ? group_sum(dot16(ra[u], e_ctx[0])) : 0.f;
-                d[u][1][1] = p.need[1][1] ? group_sum(dot16(ra[u], e_ctx[1])) : 0.f;
-            }
-            const int kind_m = u_sel ? kind_u[1] : kind_u[0];
-            const int kk_m = u_sel ? kk_u[1] : kk_u[0];
-            float cf[2][2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};      // [u][bank][ctx]: dL/ds / T summed over keys
-#pragma unroll
-            for (int kp = 0; kp < 2; ++kp) {
-                if (kp >= key_passes) break;
-                const int my_key = (l8 & 3) + 4 * kp;
-                float coef = 0.f;
-                if (my_key < p.num_keys && kind_m >= 0) {
-                    const KeyDev key = p.keys[my_key];
-                    const bool applies = (kind_m == 0 && kk_m < key.num_neg) || (kind_m == 1 && key.pos_mode == 0) ||
-                                         (kind_m == 2 && key.pos_mode == 1);
-                    if (applies) {
-                        const float d0 = key.bank == 0 ? (key.ctx == 0 ? d[0][0][0] : d[0][0][1]) : (key.ctx == 0 ? d[0][1][0] : d[0][1][1]);
-                        const float d1 = key.bank == 0 ? (key.ctx == 0 ? d[1][0][0] : d[1][0][1]) : (key.ctx == 0 ? d[1][1][0] : d[1][1][1]);
-                        const float s = (u_sel ? d1 : d0) * p.inv_T;
-                        if (p.scores) {
-                            const int slot = kind_m == 1 ? 0 : (kind_m == 2 ? 1 + kk_m : 1 + p.score_pos_k + kk_m);
-                            p.scores[((size_t)my_key * p.B + b) * (size_t)(1 + p.score_pos_k + p.K) + slot] = s;
-                        }
-                        if (p.Z) {
-                            // nce.py:42-57 with c = K_key * Z
-                            const float c = (float)key.num_neg * Z;
-                            const float e = expf(s);
-                            if (kind_m == 0) {
-                                loss_acc[kp] += log1pf(e / c);
-                                coef = key.weight * p.inv_mean_batch * (e / (e + c));
-                            } else {
-                                const float inv_p = key.pos_mode == 0 ? 1.0f : 1.0f / (float)p.pos_k;
-                                loss_acc[kp] += inv_p * log1pf(c / e);
-                                coef = -key.weight * p.inv_mean_batch * inv_p * (c / (e + c));
-                            }
-                            coef *= p.inv_T;
-                        }
-                    }
-                }
-                if (!p.Z) continue;
-                // hand every (quad, key) coefficient to the 8 lanes of the group
-                const int nk = min(4, p.num_keys - 4 * kp);
-                for (int q = 0; q < nk; ++q) {
-                    const int bank = p.keys[q + 4 * kp].bank, ctx = p.keys[q + 4 * kp].ctx;      // uniform
-                    const float c0 = __shfl_sync(0xffffffffu, coef, (lane & 24) | q);
-                    const float c1 = __shfl_sync(0xffffffffu, coef, (lane & 24) | 4 | q);
-                    if (bank == 0) {
-                        if (ctx == 0) { cf[0][0][0] += c0; cf[1][0][0] += c1; } else { cf[0][0][1] += c0; cf[1][0][1] += c1; }
-                    } else {
-                        if (ctx == 0) { cf[0][1][0] += c0; cf[1][1][0] += c1; } else { cf[0][1][1] += c0; cf[1][1][1] += c1; }
-                    }
-                }
-            }
-            if (!p.Z) continue;
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (p.need[0][c]) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) axpy4(acc[c][j], cf[u][0][c], rv[u][j]);
-                    }
-                    if (p.need[1][c]) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) axpy4(acc[c][j], cf[u][1][c], ra[u][j]);
-                    }
-                }
-        }
-    }
-    if (!p.Z) return;
-
     // sum the 4 groups of the warp (lanes with equal l8), then the 4 warps of the CTA in a fixed order
     __shared__ float4 s_acc[kGatherWarps][2][32];
     __shared__ float s_loss[kGatherWarps][AVID_MAX_KEYS];
@@ -300,13 +318,11 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
             }
             if (grp == 0) s_acc[warp][c][l8 + 8 * j] = v;
         }
-#pragma unroll
-    for (int kp = 0; kp < 2; ++kp) {
-        float v = loss_acc[kp];         // lane l8 holds the terms of key (l8 & 3) + 4 * kp: sum over quads (xor 4) and groups (xor 8, 16)
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
+    {
+        float v = loss_acc;             // lane l8 holds the terms of key l8: sum over the 4 groups (xor 8, 16)
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (lane < 4) s_loss[warp][lane + 4 * kp] = v;
+        if (lane < AVID_MAX_KEYS) s_loss[warp][lane] = v;
     }
     __syncthreads();
     if (threadIdx.x < 64) {
@@ -328,54 +344,59 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
 
     // ---- the last split CTA of this query reduces it (fixed order over splits: deterministic) ----
     __shared__ unsigned int s_ticket;
-    __shared__ float s_red[8];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(p.counter + b, 1u);
     __syncthreads();
+    stamp(p, 3);
     if (s_ticket != (unsigned)(p.splits - 1)) return;
     __threadfence();
-    const int e = threadIdx.x;          // 0..127: one embedding column, both contexts
+    // warp 0 / 1: context video / audio, lane = 4 embedding columns (no block-wide synchronisation on this path); warp 2: loss terms
     const size_t out_off = (size_t)g_i * p.out_group_stride;
-    float g[2];
-#pragma unroll
-    for (int ctx = 0; ctx < 2; ++ctx) {
-        float a = 0.f;
-        for (int s = 0; s < p.splits; ++s) a += __ldcg(p.part_grad + ((size_t)(s * 2 + ctx) * p.B + b) * kD + e);
-        g[ctx] = a;
-        if (p.grad_hat[ctx]) reinterpret_cast<float*>(reinterpret_cast<char*>(p.grad_hat[ctx]) + out_off)[(size_t)bl * kD + e] = a;
+    if (warp < 2) {
+        const int ctx = warp;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.do_finalize) x = reinterpret_cast<const float4*>((ctx ? emb1 : emb0) + (size_t)bl * kD)[lane];
+        const float4* src = reinterpret_cast<const float4*>(p.part_grad + ((size_t)ctx * p.B + b) * kD) + lane;
+        const size_t split_stride = (size_t)2 * p.B * (kD / 4);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < p.splits; ++s) {
+            const float4 o = __ldcg(src + s * split_stride);
+            g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+        }
+        if (p.grad_hat[ctx]) {
+            float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(p.grad_hat[ctx]) + out_off) + (size_t)bl * kD + 4 * lane;
+            dst[0] = g.x; dst[1] = g.y; dst[2] = g.z; dst[3] = g.w;
+        }
+        if (p.do_finalize) {
+            // backward of x -> x / max(||x||, eps):  (g - ehat <ehat, g>) / ||x||   (g / eps when clamped)
+            const float n = sqrtf(warp_sum(dot4(x, x)));
+            const bool clamped = !(n > 1e-12f);
+            const float4 eh = clamped ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(x.x / n, x.y / n, x.z / n, x.w / n);
+            const float dotp = warp_sum(dot4(eh, g));
+            float* dst = p.grad[ctx] + (size_t)b * kD + 4 * lane;      // packed behind the loss scalars: not 16-byte aligned
+            dst[0] = clamped ? g.x / 1e-12f : (g.x - eh.x * dotp) / n;
+            dst[1] = clamped ? g.y / 1e-12f : (g.y - eh.y * dotp) / n;
+            dst[2] = clamped ? g.z / 1e-12f : (g.z - eh.z * dotp) / n;
+            dst[3] = clamped ? g.w / 1e-12f : (g.w - eh.w * dotp) / n;
+        }
+    } else if (warp == 2) {
+        if (lane < p.num_keys) {
+            float l = 0.f;
+            for (int s = 0; s < p.splits; ++s) l += __ldcg(p.part_loss + ((size_t)s * p.num_keys + lane) * p.B + b);
+            reinterpret_cast<float*>(reinterpret_cast<char*>(p.loss_part) + out_off)[(size_t)lane * (p.group_batch > 0 ? p.group_batch : p.B) + bl] = l;
+        }
+        if (lane == 0) p.counter[b] = 0u;      // ready for the next launch
     }
-    if (e < p.num_keys) {
-        float l = 0.f;
-        for (int s = 0; s < p.splits; ++s) l += __ldcg(p.part_loss + ((size_t)s * p.num_keys + e) * p.B + b);
-        reinterpret_cast<float*>(reinterpret_cast<char*>(p.loss_part) + out_off)[(size_t)e * (p.group_batch > 0 ? p.group_batch : p.B) + bl] = l;
-    }
-    if (e == 0) p.counter[b] = 0u;      // ready for the next launch
     if (!p.do_finalize) return;
-
-    // backward of x -> x / max(||x||, eps):  (g - ehat <ehat, g>) / ||x||   (g / eps when clamped)
-#pragma unroll
-    for (int ctx = 0; ctx < 2; ++ctx) {
-        const float x = (ctx ? emb1 : emb0)[(size_t)bl * kD + e];
-        const float xx = warp_sum(x * x);
-        __syncthreads();
-        if (lane == 0) s_red[warp] = xx;
-        __syncthreads();
-        const float n = sqrtf(s_red[0] + s_red[1] + s_red[2] + s_red[3]);
-        const bool clamped = !(n > 1e-12f);
-        const float eh = clamped ? 0.f : x / n;
-        const float pg = warp_sum(eh * g[ctx]);
-        if (lane == 0) s_red[4 + warp] = pg;
-        __syncthreads();
-        const float dotp = s_red[4] + s_red[5] + s_red[6] + s_red[7];
-        p.grad[ctx][(size_t)b * kD + e] = clamped ? g[ctx] / 1e-12f : (g[ctx] - eh * dotp) / n;
-    }
 
     // ---- the last query: batch means + coefficient mix (avid.py:216-233 / avid_cma.py:338-359) ----
     __threadfence();
     __syncthreads();
+    stamp(p, 4);
     if (threadIdx.x == 0) s_ticket = atomicAdd(p.counter + p.B, 1u);
     __syncthreads();
+    stamp(p, 5);
     if (s_ticket != (unsigned)(p.B - 1)) return;
     __threadfence();
     __shared__ float s_keyloss[AVID_MAX_KEYS];
@@ -395,6 +416,103 @@ __global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const Nce
         *p.loss_total = tot;
         p.counter[p.B] = 0u;
     }
+    stamp(p, 6);
+}
+
+template <int NEED, bool TRAIN>
+__global__ void __launch_bounds__(kGatherThreads, 3) nce_gather_kernel(const NceParams p) {
+    const int b = blockIdx.x, split = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, l8 = lane & 7;
+    // gathered queries of a sharded step arrive as one packed record per rank (group): query b = (group g, row bl)
+    const int g_i = p.group_batch > 0 ? b / p.group_batch : 0, bl = p.group_batch > 0 ? b - g_i * p.group_batch : b;
+    const size_t in_off = (size_t)g_i * p.in_group_stride;          // bytes
+    const float* emb0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[0]) + in_off);
+    const float* emb1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.emb[1]) + in_off);
+
+    stamp(p, 0);
+    // everything the first row requests depend on is asked for first (y), the embeddings are requested before and
+    // normalised after the first two quads are on their way, and the Philox rounds of the first chunk run while y is in flight
+    GatherCtx gc;
+    gc.b = b;
+    gc.y = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.y) + in_off)[bl];
+    gc.negs = p.neg_idx ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg_idx) + in_off) + (size_t)bl * p.K : nullptr;
+    float4 e_ctx[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        e_ctx[0][j] = reinterpret_cast<const float4*>(emb0 + (size_t)bl * kD)[l8 + 8 * j];
+        e_ctx[1][j] = reinterpret_cast<const float4*>(emb1 + (size_t)bl * kD)[l8 + 8 * j];
+    }
+    const float Z = TRAIN ? *p.Z : 1.0f;
+
+    // item stream of this CTA: [self, positives...] (split 0 only) then negatives [k_begin, k_end); warp w owns a contiguous
+    // range of it (a multiple of 4 items, so quads never straddle two warps).  The layout does not depend on y: with an
+    // out-of-range y the positive slots stay in the stream and score nothing.
+    gc.npos = (split == 0) ? 1 + ((p.positive_set && p.pos_k > 0) ? p.pos_k : 0) : 0;
+    gc.k_begin = split * p.kc;
+    const int n_items = gc.npos + max(0, min(p.K, gc.k_begin + p.kc) - gc.k_begin);
+    const int per_warp = (((n_items + kGatherWarps - 1) / kGatherWarps) + 3) & ~3;
+    const int w_begin = warp * per_warp;
+    gc.w_end = min(n_items, w_begin + per_warp);
+    const int nq = gc.w_end > w_begin ? (gc.w_end - w_begin + 3) >> 2 : 0;
+    uint32_t bits[4] = {0u, 0u, 0u, 0u};
+    {
+        const int item = w_begin + lane;
+        if (!gc.negs && item >= gc.npos && item < gc.w_end)
+            Philox::generate(p.seed, p.offset + (uint64_t)b * (uint64_t)p.K + (uint64_t)(gc.k_begin + (item - gc.npos)), bits);
+    }
+
+    if (gc.y < 0 || gc.y >= p.N) {       // the reference raises IndexError here (avid.py:57-58): report it, score no positive, read nothing
+        if (p.bad_index && threadIdx.x == 0 && split == 0) *p.bad_index = 1;
+        gc.y = -1;
+    }
+    gc.pos_row = (p.positive_set && p.pos_k > 0 && gc.y >= 0) ? p.positive_set + (size_t)gc.y * p.pos_k : nullptr;
+
+    float4 acc[2][4];                 // grad_hat for ctx video / audio, this lane's 16 columns
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[c][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float loss_acc = 0.f;             // lane l8: the terms of key l8 over this group's rows
+    const int my_key = l8;
+    LaneKey key;
+    {
+        const bool on = my_key < p.num_keys;
+        const KeyDev k = p.keys[on ? my_key : 0];
+        key.sel = on ? 2 * k.bank + k.ctx : -1;
+        key.neg_limit = on ? k.num_neg : 0;
+        key.pos_ok = on ? (k.pos_mode == 0 ? 1 : 2) : 0;
+        key.c = (float)k.num_neg * Z;
+        key.inv_c = 1.0f / key.c;
+        key.inv_p = k.pos_mode == 0 ? 1.0f : 1.0f / (float)p.pos_k;
+        key.w_neg = k.weight * p.inv_mean_batch * p.inv_T;
+        key.w_pos = -key.w_neg * key.inv_p;
+    }
+
+    float4 rv0[4], ra0[4], rv1[4], ra1[4];      // the two quads in flight
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rv0[j] = ra0[j] = rv1[j] = ra1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int tag0 = 0, tag1 = 0;
+    ItemDesc desc = describe_item(p, gc, w_begin + lane, bits);
+    if (nq > 0) request_quad(p, desc, 0, grp, l8, rv0, ra0, tag0);
+    if (nq > 1) request_quad(p, desc, 1, grp, l8, rv1, ra1, tag1);
+    normalize_group(e_ctx[0]);
+    normalize_group(e_ctx[1]);
+    stamp(p, 1);
+
+    for (int t = 0; t < nq; t += 2) {
+        score_quad<NEED, TRAIN>(p, rv0, ra0, tag0, e_ctx, acc, loss_acc, key, my_key, b, lane);
+        if (t + 2 < nq) {
+            if (((t + 2) & 7) == 0) desc = describe_item(p, gc, w_begin + 4 * (t + 2) + lane);      // the next 32 items
+            request_quad(p, desc, (t + 2) & 7, grp, l8, rv0, ra0, tag0);
+        }
+        if (t + 1 < nq) {
+            score_quad<NEED, TRAIN>(p, rv1, ra1, tag1, e_ctx, acc, loss_acc, key, my_key, b, lane);
+            if (t + 3 < nq) request_quad(p, desc, (t + 3) & 7, grp, l8, rv1, ra1, tag1);
+        }
+    }
+    stamp(p, 2);
+    if constexpr (TRAIN) finish_query(p, acc, loss_acc, b, bl, g_i, split, emb0, emb1);
 }
 
 struct FinalizeParams {
@@ -512,7 +630,7 @@ __global__ void sample_negatives_kernel(const int64_t* y, int B, int K, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Items per CTA (a multiple of 128 = 4 warps x 32-item chunks) chosen to minimise waves x (items + fixed per-CTA cost) with
+// Negatives per CTA (a multiple of 16 = 4 warps x one quad) chosen to minimise waves x (items + fixed per-CTA cost) with
 // 3 resident CTAs per SM, so the grid neither ends in a thin second wave nor starves the SMs.
 static void choose_split(int B, int K, int* splits, int* kc) {
     static const int forced = [] { const char* e = getenv("AVID_NCE_KC"); return e ? atoi(e) : 0; }();     // tuning experiments only
@@ -523,10 +641,10 @@ static void choose_split(int B, int K, int* splits, int* kc) {
     }
     const int slots = 3 * kNumSMs;
     long best_cost = -1;
-    int best_c = 128;
-    const int max_m = (K + 127) / 128;
+    int best_c = 16;
+    const int max_m = (K + 15) / 16;
     for (int m = 1; m <= max_m; ++m) {
-        const int c = 128 * m;
+        const int c = 16 * m;
         const int sp = (K + c - 1) / c;
         if (sp > 256) continue;
         const long ctas = (long)B * sp;
@@ -542,6 +660,7 @@ static void choose_split(int B, int K, int* splits, int* kc) {
 struct Workspace {
     float *part_grad, *part_loss, *grad_hat[2], *loss_part, *scores;
     unsigned int* counter;
+    unsigned long long* dbg;
     size_t bytes;
 };
 
@@ -557,6 +676,7 @@ static Workspace carve(void* base, int B, int K, int pos_k, int num_keys, bool w
         return r;
     };
     w.counter = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * (size_t)(B + 1)));      // zero on entry, left zero
+    w.dbg = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 1024 * 8));      // AVID_NCE_DEBUG stamps
     w.part_grad = reinterpret_cast<float*>(take(sizeof(float) * (size_t)splits * 2 * B * kD));
     w.part_loss = reinterpret_cast<float*>(take(sizeof(float) * (size_t)splits * AVID_MAX_KEYS * B));
     w.grad_hat[0] = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * kD));
@@ -568,14 +688,16 @@ static Workspace carve(void* base, int B, int K, int pos_k, int num_keys, bool w
     return w;
 }
 
-static int configure_gather() {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(nce_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem);
-        if (e != cudaSuccess) { set_error("nce: shared-memory attribute: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
-        configured = true;
-    }
-    return AVID_OK;
+// the instantiation for the (bank, ctx) pairs the keys score: cross / self / joint are compile-time, anything else generic
+static int launch_gather(const NceParams& p, bool train, cudaStream_t st) {
+    const dim3 grid(p.B, p.splits);
+    const int mask = (p.need[0][0] ? 1 : 0) | (p.need[0][1] ? 2 : 0) | (p.need[1][0] ? 4 : 0) | (p.need[1][1] ? 8 : 0);
+    if (!train) nce_gather_kernel<-1, false><<<grid, kGatherThreads, kGatherSmem, st>>>(p);
+    else if (mask == 6) nce_gather_kernel<6, true><<<grid, kGatherThreads, kGatherSmem, st>>>(p);
+    else if (mask == 9) nce_gather_kernel<9, true><<<grid, kGatherThreads, kGatherSmem, st>>>(p);
+    else if (mask == 15) nce_gather_kernel<15, true><<<grid, kGatherThreads, kGatherSmem, st>>>(p);
+    else nce_gather_kernel<-1, true><<<grid, kGatherThreads, kGatherSmem, st>>>(p);
+    return check_launch(train ? "nce_gather_kernel" : "nce_gather_kernel(scores)");
 }
 
 static int fill_params(const avid_nce_args_t* a, NceParams* p) {
@@ -588,12 +710,16 @@ static int fill_params(const avid_nce_args_t* a, NceParams* p) {
     AVID_REQUIRE(a->temperature > 0.f, "nce: temperature must be positive");
     bool any_set = false;
     p->need[0][0] = p->need[0][1] = p->need[1][0] = p->need[1][1] = false;
+    int pair_keys[4] = {0, 0, 0, 0};
+    for (int s = 0; s < 4; ++s) p->coef_lane[s] = -1;
+    AVID_REQUIRE(a->row_end - a->row_begin < (int64_t)1 << 31 && a->num_neg < (1 << 28), "nce: more than 2^31 rows per shard or 2^28 negatives");
     for (int k = 0; k < a->num_keys; ++k) {
         const avid_nce_key_t& key = a->keys[k];
         AVID_REQUIRE((key.ctx | 1) == 1 && (key.bank | 1) == 1 && (key.pos_mode | 1) == 1, "nce: key %d has bad ctx/bank/pos_mode", k);
         AVID_REQUIRE(key.num_neg > 0 && key.num_neg <= a->num_neg, "nce: key %d num_neg %d not in (0,%d]", k, key.num_neg, a->num_neg);
         p->keys[k] = KeyDev{key.ctx, key.bank, key.pos_mode, key.num_neg, key.weight};
         p->need[key.bank][key.ctx] = true;
+        p->coef_lane[2 * key.bank + key.ctx] = pair_keys[2 * key.bank + key.ctx]++ == 0 ? k : -1;
         any_set |= key.pos_mode == 1;
     }
     AVID_REQUIRE(!any_set || (a->positive_set && a->pos_k > 0 && a->pos_k <= 64), "nce: a positive-set key needs positive_set and 0 < pos_k <= 64");
@@ -654,6 +780,8 @@ int avid_nce_forward_backward(const avid_nce_args_t* a, void* workspace, size_t 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     p.part_grad = w.part_grad;  p.part_loss = w.part_loss;  p.counter = w.counter;
+    static const bool debug = getenv("AVID_NCE_DEBUG") != nullptr;
+    p.dbg = debug ? w.dbg : nullptr;
     p.grad_hat[0] = a->grad_hat_video;  p.grad_hat[1] = a->grad_hat_audio;
     p.loss_part = a->loss_part ? a->loss_part : w.loss_part;
     p.grad[0] = a->grad_video;  p.grad[1] = a->grad_audio;
@@ -661,9 +789,7 @@ int avid_nce_forward_backward(const avid_nce_args_t* a, void* workspace, size_t 
     for (int k = 0; k < AVID_MAX_KEYS; ++k) p.weights[k] = k < a->num_keys ? a->keys[k].weight : 0.f;
     p.do_finalize = sharded ? 0 : 1;
     AVID_REQUIRE(sharded || a->group_batch == 0, "nce: packed per-rank records (group_batch) are for the sharded protocol only");
-    if ((rc = configure_gather())) return rc;
-    nce_gather_kernel<<<dim3(a->batch, p.splits), kGatherThreads, kGatherSmem, st>>>(p);
-    return check_launch("nce_gather_kernel");
+    return launch_gather(p, true, st);
 }
 
 int avid_nce_finalize(const avid_nce_args_t* a, void* workspace, size_t workspace_bytes, void* stream) {
@@ -712,15 +838,16 @@ int avid_nce_partition_mean(const avid_nce_args_t* a, int32_t key, float* out_me
     q.Z = nullptr;
     q.scores = w.scores;
     q.counter = nullptr;
+    q.dbg = nullptr;
     q.part_grad = nullptr;  q.part_loss = nullptr;
     q.neg_idx_out = nullptr;
     const int stride = 1 + q.score_pos_k + a->num_neg;
     const size_t n = (size_t)a->batch * stride;
     fill_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(w.scores, n, -INFINITY);
     if ((rc = check_launch("fill_kernel"))) return rc;
-    if ((rc = configure_gather())) return rc;
-    nce_gather_kernel<<<dim3(a->batch, q.splits), kGatherThreads, kGatherSmem, st>>>(q);
-    if ((rc = check_launch("nce_gather_kernel(scores)"))) return rc;
+    for (int s = 0; s < 4; ++s) q.coef_lane[s] = -1;
+    q.coef_lane[2 * q.keys[0].bank + q.keys[0].ctx] = 0;
+    if ((rc = launch_gather(q, false, st))) return rc;
     const bool sharded = a->row_begin != 0 || a->row_end != a->num_rows;
     const int kn = q.keys[0].num_neg;
     const float scale = sharded ? 1.0f : 1.0f / ((float)a->batch * (float)kn);

@@ -28,6 +28,10 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--flush", choices=["write", "read", "none"], default="write",
+                    help="between timed calls: write 256 MB (L2 left full of DIRTY lines: the kernel's first misses each evict one), "
+                         "read 256 MB (L2 left full of clean lines), or nothing (only meaningful with banks much larger than L2)")
+    ap.add_argument("--group", type=int, default=1, help="launches per timed event pair (each with fresh y and a fresh Philox offset)")
     a = ap.parse_args()
     from avid_cma_b200 import ops
     dev = torch.device("cuda", 0)
@@ -37,7 +41,8 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+    sink = torch.zeros((), dtype=torch.int64, device=dev)
     B = a.batch
     results = []
     for N in a.banks:
@@ -54,23 +59,31 @@ def main():
             gv, ga = out[1 + len(keys):1 + len(keys) + B * 128].view(B, 128), out[1 + len(keys) + B * 128:].view(B, 128)
             times = []
             for it in range(a.warmup + a.iters):
-                y = torch.randint(0, N, (B,), device=dev, generator=g)
-                args = ops.make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, K, Z, seed=1234, offset=it * B * K,
-                                         loss_keys=lk, loss_total=lt, grad_v=gv, grad_a=ga)
-                flush.fill_(it & 0xFF)
+                calls = []
+                for gi in range(a.group):
+                    y = torch.randint(0, N, (B,), device=dev, generator=g)
+                    calls.append(ops.make_nce_args(emb_v, emb_a, y, bank_v, bank_a, keys, K, Z, seed=1234, offset=(it * a.group + gi) * B * K,
+                                                   loss_keys=lk, loss_total=lt, grad_v=gv, grad_a=ga))
+                if a.flush == "write":
+                    flush.fill_(it & 0xFF)
+                elif a.flush == "read":
+                    sink.copy_(flush.view(torch.int64).sum())
+                else:
+                    torch.cuda._sleep(200000)       # keeps the GPU busy while the host enqueues: no launch latency inside the event pair
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ops.nce_forward_backward(args, ws)
+                for args in calls:
+                    ops.nce_forward_backward(args, ws)
                 e1.record()
                 torch.cuda.synchronize()
                 if it >= a.warmup:
-                    times.append(e0.elapsed_time(e1))
+                    times.append(e0.elapsed_time(e1) / a.group)
             times.sort()
             ms = times[len(times) // 2]
             bytes_ = 2.0 * B * (K + 1) * 512
             r = {"bank_rows": N, "K": K, "batch": B, "ms_median": ms, "ms_min": times[0], "algorithmic_MB": bytes_ / 1e6,
                  "GB/s": bytes_ / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": bytes_ / (ms * 1e-3) / 1e9 / peak, "hbm_peak_GB/s": peak,
-                 "loss": float(lt)}
+                 "flush": a.flush, "launches_per_event_pair": a.group, "loss": float(lt)}
             results.append(r)
             print(json.dumps(r), flush=True)
         del bank_v, bank_a
