@@ -57,22 +57,55 @@ constexpr int kMaxTaps = 32;
 constexpr int kStgLd = 20;      // row pitch (floats) of the 32 x 16 epilogue staging tiles: 16-byte aligned, conflict-free for float4 rows
 constexpr int kConvThreads = 320; // conv_tc_kernel: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-9 epilogue
 
+constexpr int kMaxCls = 8;      // stride-parity classes of one launch (2 x 2 x 2)
+
+// One stride-parity class of a strided input gradient (the only class of every other launch): which destination pixels it
+// enumerates, where their taps read the source, which filter taps it uses.
+struct TcClass {
+    int M;                          // destination pixels of the class, enumerated ((n * tq + t) * hq + h) * wq + w
+    int tq, hq, wq;                 // extents of that enumeration
+    int bt, bh, bw;                 // source coordinate read by tap offset 0 for destination pixel 0 (forward: -padding)
+    int tap0, ntaps;                // its entries of TcConvParams::taps
+    int rt, rh, rw;                 // residues: enumerated pixel (n, t, h, w) -> ((n * Td + t * ot + rt) * Hd + h * oh + rh) * Wd + w * ow + rw
+};
+
 struct TcConvParams {
-    int M;                          // destination pixels of this launch, enumerated ((n * tq + t) * hq + h) * wq + w
-    int tq, hq, wq;                 // extents of that enumeration (the whole output, or one stride-parity class of a strided dgrad)
+    int ncls;
+    TcClass cls[kMaxCls];
+    int mtiles;                     // 128-pixel tiles of the largest class
     int cd;                         // destination channels (GEMM N total)
     int cs;                         // source channels (GEMM K per tap)
     int st, sh, sw;                 // source traversal strides (forward conv stride; 1 for dgrad)
-    int bt, bh, bw;                 // source coordinate read by tap offset 0 for destination pixel 0 (forward: -padding)
-    int ntaps;
-    uint32_t taps[kMaxTaps];        // off_w | off_h << 8 | off_t << 16 | filter tap << 24 (offsets relative to bt/bh/bw)
+    uint32_t taps[kMaxTaps];        // off_w | off_h << 8 | off_t << 16 | filter tap << 24 (offsets relative to bt/bh/bw of the class)
     int x3;                         // 1: hi/lo planes, 3 MMAs per k-step; 0: hi only
-    // destination addressing: enumerated pixel (n, t, h, w) -> ((n * Td + t * ot + rt) * Hd + h * oh + rh) * Wd + w * ow + rw
-    int strided_out;
-    int Td, Hd, Wd, ot, oh, ow, rt, rh, rw;
+    int strided_out;                // destination rows are scattered to the pixels of their class
+    int Td, Hd, Wd, ot, oh, ow;
     int debug;                      // AVID_TC_DEBUG probe bits (scripts/probe_conv.py; 0 in production): 1 no global stores, 2 no
                                     // statistics, 4 epilogue only hands the accumulator back, 8 no MMAs, 64 no per-tile atomics
 };
+
+struct alignas(64) TcConvMaps {
+    CUtensorMap a[kMaxCls][2];      // im2col maps of the source planes (hi, lo) per class: the box corners depend on the class
+    CUtensorMap b[2];               // filter planes
+};
+
+// tile -> (class, 128-pixel tile of the class, channel block); the channel block is the fastest index (all tiles of a CTA share it),
+// then the class: the classes of a strided input gradient read the SAME source pixels through different taps, so tiles that run
+// at the same time share them in L2 (one launch per class read the source once per class: 4 x 205 MB for the conv3x entry)
+struct TcTile {
+    int cls, m0, n0;
+    bool valid;
+};
+template <int BN>
+__device__ __forceinline__ TcTile decode_tile(const TcConvParams& p, int tile, int nblocks) {
+    TcTile t;
+    t.n0 = (tile % nblocks) * BN;
+    const int rest = tile / nblocks;
+    t.cls = rest % p.ncls;
+    t.m0 = (rest / p.ncls) * kBM;
+    t.valid = t.m0 < p.cls[t.cls].M;
+    return t;
+}
 
 template <int BN>
 struct TcSmem {
@@ -91,8 +124,7 @@ struct TcSmem {
 // tile k + 1.
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcConvParams p,
+conv_tc_kernel(const __grid_constant__ TcConvMaps maps, const __grid_constant__ TcConvParams p,
                const float* __restrict__ addend, float* __restrict__ out, double* __restrict__ stats, const BnBwdFuse fuse) {
     using S = TcSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -109,17 +141,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
     const int cblocks = p.cs / kBK;
-    const int nkb = p.ntaps * cblocks;
     const int nblocks = p.cd / BN;
-    const int num_tiles = ((p.M + kBM - 1) / kBM) * nblocks;
+    const int num_tiles = p.mtiles * p.ncls * nblocks;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&map_a_hi);
-        prefetch_tensormap(&map_b_hi);
-        if (p.x3) {
-            prefetch_tensormap(&map_a_lo);
-            prefetch_tensormap(&map_b_lo);
+        for (int c = 0; c < p.ncls; ++c) {
+            prefetch_tensormap(&maps.a[c][0]);
+            if (p.x3) prefetch_tensormap(&maps.a[c][1]);
         }
+        prefetch_tensormap(&maps.b[0]);
+        if (p.x3) prefetch_tensormap(&maps.b[1]);
         for (int s = 0; s < S::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -145,27 +176,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t tx = (uint32_t)(S::kABytes + S::kBBytes) * (p.x3 ? 2u : 1u);
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int n0 = (tile % nblocks) * BN;
-            int m = (tile / nblocks) * kBM;
-            const int w_o = m % p.wq;  m /= p.wq;
-            const int h_o = m % p.hq;  m /= p.hq;
-            const int t_o = m % p.tq;
-            const int n_i = m / p.tq;
-            const int bw = w_o * p.sw + p.bw, bh = h_o * p.sh + p.bh, bt = t_o * p.st + p.bt;   // source pixel read by tap offset 0
+            const TcTile tl = decode_tile<BN>(p, tile, nblocks);
+            if (!tl.valid) continue;
+            const TcClass& cl = p.cls[tl.cls];
+            const CUtensorMap* const map_a_hi = &maps.a[tl.cls][0];
+            const CUtensorMap* const map_a_lo = &maps.a[tl.cls][1];
+            const int n0 = tl.n0;
+            int m = tl.m0;
+            const int w_o = m % cl.wq;  m /= cl.wq;
+            const int h_o = m % cl.hq;  m /= cl.hq;
+            const int t_o = m % cl.tq;
+            const int n_i = m / cl.tq;
+            const int bw = w_o * p.sw + cl.bw, bh = h_o * p.sh + cl.bh, bt = t_o * p.st + cl.bt;   // source pixel read by tap offset 0
+            const int nkb = cl.ntaps * cblocks;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * kBK;
-                const uint32_t tp = p.taps[tap];
+                const uint32_t tp = p.taps[cl.tap0 + tap];
                 const uint16_t c = tp & 0xFF, b = (tp >> 8) & 0xFF, a = (tp >> 16) & 0xFF;
                 const int ftap = tp >> 24;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + stage * S::kStageBytes;
                 if (elect_one()) {
                     mbar_expect_tx(&full_bar[stage], tx);
-                    tma_load_im2col_5d(st, &map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
-                    tma_load_2d(st + 2 * S::kABytes, &map_b_hi, &full_bar[stage], c0, ftap * p.cd + n0);
+                    tma_load_im2col_5d(st, map_a_hi, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
+                    tma_load_2d(st + 2 * S::kABytes, &maps.b[0], &full_bar[stage], c0, ftap * p.cd + n0);
                     if (p.x3) {
-                        tma_load_im2col_5d(st + S::kABytes, &map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
-                        tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &map_b_lo, &full_bar[stage], c0, ftap * p.cd + n0);
+                        tma_load_im2col_5d(st + S::kABytes, map_a_lo, &full_bar[stage], c0, bw, bh, bt, n_i, c, b, a);
+                        tma_load_2d(st + 2 * S::kABytes + S::kBBytes, &maps.b[1], &full_bar[stage], c0, ftap * p.cd + n0);
                     }
                 }
                 __syncwarp();
@@ -186,7 +223,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
         const bool x3 = p.x3 != 0;
         int stage = 0, phase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const TcTile tl = decode_tile<BN>(p, tile, nblocks);
+            if (!tl.valid) continue;
+            const int nkb = p.cls[tl.cls].ntaps * cblocks;
             const int buf = it & 1;
             mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
             tc_fence_after();
@@ -214,6 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 __syncwarp();
                 if (++stage == S::kStages) { stage = 0; phase ^= 1; }
             }
+            ++it;
         }
     } else if (warp >= 2) {
         // ===== epilogue: TMEM -> registers -> per-warp shared-memory transpose -> coalesced global rows, optional BatchNorm statistics =====
@@ -246,28 +287,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                 for (int t = 0; t < 4; ++t) run1[a][b][t] = run2[a][b][t] = 0.f;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const int m = (tile / nblocks) * kBM + q * 32 + lane;
+        // element offset of the destination row this lane reads from TMEM in `tile` (~0: none)
+        auto row_of = [&](int tile) -> unsigned long long {
+            if (tile >= num_tiles) return ~0ull;
+            const TcTile tl = decode_tile<BN>(p, tile, nblocks);
+            if (!tl.valid) return ~0ull;
+            const TcClass& cl = p.cls[tl.cls];
+            const int m = tl.m0 + q * 32 + lane;
             size_t pix = (size_t)m;
-            if (p.strided_out) {        // one stride-parity class of a strided input gradient: scatter rows to their pixels
+            if (p.strided_out) {        // a stride-parity class of a strided input gradient: scatter rows to their pixels
                 int r = m;
-                const int w_o = r % p.wq;  r /= p.wq;
-                const int h_o = r % p.hq;  r /= p.hq;
-                const int t_o = r % p.tq;
-                const int n_i = r / p.tq;
-                pix = (((size_t)n_i * p.Td + t_o * p.ot + p.rt) * p.Hd + h_o * p.oh + p.rh) * p.Wd + w_o * p.ow + p.rw;
+                const int w_o = r % cl.wq;  r /= cl.wq;
+                const int h_o = r % cl.hq;  r /= cl.hq;
+                const int t_o = r % cl.tq;
+                const int n_i = r / cl.tq;
+                pix = (((size_t)n_i * p.Td + t_o * p.ot + cl.rt) * p.Hd + h_o * p.oh + cl.rh) * p.Wd + w_o * p.ow + cl.rw;
             }
-            const unsigned long long my_row = m < p.M ? (unsigned long long)(pix * p.cd + n0) : ~0ull;
+            return m < cl.M ? (unsigned long long)(pix * p.cd + n0) : ~0ull;
+        };
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const unsigned long long my_row = row_of(tile);
+            if (!decode_tile<BN>(p, tile, nblocks).valid) continue;
+            const int buf = it & 1;
+            if (addend || fuse.z) {
+                // the rows of the CTA's NEXT tile on their way to L2 (a 32-column chunk of a row is one 128-byte line)
+                const unsigned long long nxt = row_of(tile + gridDim.x);
+                if (nxt != ~0ull) {
+#pragma unroll
+                    for (int jj = 0; jj < kChunks; ++jj) {
+                        if (addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + nxt + (hsel * kChunks + jj) * 32));
+                        if (fuse.z) asm volatile("prefetch.global.L2 [%0];" ::"l"(fuse.z + nxt + (hsel * kChunks + jj) * 32));
+                    }
+                }
+            }
             unsigned long long rows4[4];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
 #pragma unroll
             for (int i = 0; i < 4; ++i) rows4[i] = __shfl_sync(0xffffffffu, my_row, i * 8 + r8);
+            // BN = 64 (two half-chunks per warp, registers to spare): the residual addend and the z tile of the fused BatchNorm
+            // backward of the WHOLE tile are requested before the accumulator wait -- their addresses depend on the tile index
+            // only.  Requested per half-chunk behind the wait, the strided conv3x-entry input gradient (both operands, 85 tiles per
+            // CTA) spent ~5 us per tile in two serial [DRAM round trip + 300 instructions] periods per warp: 421 us for 1.4 GB.
+            constexpr bool kPre = BN == 64;
+            float4 ad_pre[kPre ? 2 : 1][4], zz_pre[kPre ? 2 : 1][4];
+            if (kPre) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int col = hsel * 32 + hh * 16;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ad_pre[hh][i] = (addend && rows4[i] != ~0ull) ? __ldg(reinterpret_cast<const float4*>(addend + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        zz_pre[hh][i] = (fuse.z && rows4[i] != ~0ull) ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
             mbar_wait_sleep(&tmem_full[buf], (it >> 1) & 1, 128);
             tc_fence_after();
             if (p.debug & 4) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                ++it;
                 continue;
             }
 #pragma unroll
@@ -280,15 +359,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (p.x3) tmem_ld_32x32b_x16(taddr + BN, r2);       // the hi*lo half of the bf16x3 accumulator
                 // global operands of this half-chunk are requested while the TMEM loads are in flight
                 float4 ad[4], zz[4];
-                if (addend) {
+                if (kPre) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        ad[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (fuse.z) {
+                    for (int i = 0; i < 4; ++i) {
+                        ad[i] = ad_pre[kPre ? hh : 0][i];
+                        zz[i] = zz_pre[kPre ? hh : 0][i];
+                    }
+                } else {
+                    if (addend) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        zz[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 4; ++i)
+                            ad[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (fuse.z) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            zz[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
                 tmem_ld_wait();
                 if (hc == 2 * kChunks - 1) {        // this warp's part of the accumulator is in registers: hand the TMEM buffer back
@@ -343,6 +430,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
                 __syncwarp();                       // the staging tile is rewritten by the next half-chunk
             }
+            ++it;
         }
         if (acc_out && !(p.debug & 64)) {
             // lanes with equal (lane & 3) hold partial sums of the same 4 columns: reduce over the 8 row groups of the warp, over the
@@ -647,7 +735,7 @@ static int encode_tiled_2d(CUtensorMap* map, const void* base, uint64_t rows, ui
 }
 
 template <int BN>
-static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const float* addend, float* out, double* stats, const BnBwdFuse& fuse,
+static int launch_conv_tc(const TcConvMaps& maps, const TcConvParams& p, const float* addend, float* out, double* stats, const BnBwdFuse& fuse,
                           cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -656,11 +744,11 @@ static int launch_conv_tc(const CUtensorMap* maps, const TcConvParams& p, const 
         configured = true;
     }
     const int nblocks = p.cd / BN;
-    const int tiles = ((p.M + kBM - 1) / kBM) * nblocks;
+    const int tiles = p.mtiles * p.ncls * nblocks;
     // a multiple of the channel-block count, so that every tile of a CTA has the same channel block (running statistics)
     const int grid = tiles < kNumSMs ? tiles : (kNumSMs / nblocks) * nblocks;
     AVID_REQUIRE(grid > 0, "conv_tc: %d channel blocks exceed the SM count", nblocks);
-    conv_tc_kernel<BN><<<grid, kConvThreads, TcSmem<BN>::kBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p, addend, out, stats, fuse);
+    conv_tc_kernel<BN><<<grid, kConvThreads, TcSmem<BN>::kBytes, st>>>(maps, p, addend, out, stats, fuse);
     return check_launch("conv_tc_kernel");
 }
 
@@ -705,7 +793,8 @@ static DimPlan plan_dgrad(int dst, int src, int k, int s, int pad, int r) {
 
 // dgrad == 0: out[n,to,ho,wo,co] = conv(in, filt);  a_* = input planes [n,ti,hi,wi,ci], b_* = filter planes [taps][co][ci]
 // dgrad == 1: out[n,ti,hi,wi,ci] = conv_transpose(dout, filt); a_* = dout planes, b_* = filter planes [taps][ci][co].  A strided
-//             input gradient is one launch per stride-parity class (st * sh * sw of them), each a stride-1 correlation.
+//             input gradient is st * sh * sw stride-parity classes, each a stride-1 correlation with its own taps and im2col
+//             box; all classes run in ONE launch (tile -> class, see decode_tile).
 int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                 const float* addend, float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
     AVID_REQUIRE(s && a_hi && b_hi && out, "conv_tc: NULL pointer");
@@ -730,12 +819,13 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     // the 64 -> 64 channel 1x3x3 stride-1 layers (forward and input gradient) run on CTA pairs with a halo tile and a resident filter
     rc = conv_pair_run(s, dgrad, a_hi, a_lo, b_hi, b_lo, addend, out, stats, fuse, st);
     if (rc != AVID_EUNSUPPORTED) return rc;
-    CUtensorMap map_b[2];
-    if ((rc = encode_tiled_2d(&map_b[0], b_hi, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
-    map_b[1] = map_b[0];
-    if (x3 && (rc = encode_tiled_2d(&map_b[1], b_lo, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
+    TcConvMaps maps;
+    if ((rc = encode_tiled_2d(&maps.b[0], b_hi, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
+    maps.b[1] = maps.b[0];
+    if (x3 && (rc = encode_tiled_2d(&maps.b[1], b_lo, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
 
     const int classes[3] = {dgrad ? ss[0] : 1, dgrad ? ss[1] : 1, dgrad ? ss[2] : 1};
+    AVID_REQUIRE(classes[0] * classes[1] * classes[2] <= kMaxCls, "conv_tc: stride %dx%dx%d has more than %d parity classes", ss[2], ss[1], ss[0], kMaxCls);
     // classes whose residue meets no filter tap (filter smaller than the stride) receive no gradient: zero fill first
     bool any_empty = false;
     if (dgrad)
@@ -746,6 +836,20 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
         cudaError_t e = cudaMemsetAsync(out, 0, (size_t)dst_pixels * cd * sizeof(float), st);
         if (e != cudaSuccess) { set_error("conv_tc: memset: %s", cudaGetErrorString(e)); return AVID_ECUDA; }
     }
+    TcConvParams p;
+    p.ncls = 0;
+    p.mtiles = 0;
+    p.cd = cd;  p.cs = cs;
+    p.x3 = x3;
+    {
+        const char* dbg = getenv("AVID_TC_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
+    p.strided_out = dgrad && (ss[0] > 1 || ss[1] > 1 || ss[2] > 1);
+    p.Wd = dst[0];  p.Hd = dst[1];  p.Td = dst[2];
+    p.ow = classes[0];  p.oh = classes[1];  p.ot = classes[2];
+    p.sw = dgrad ? 1 : ss[0];  p.sh = dgrad ? 1 : ss[1];  p.st = dgrad ? 1 : ss[2];
+    int ntaps_all = 0;
     for (int rt = 0; rt < classes[2]; ++rt)
         for (int rh = 0; rh < classes[1]; ++rh)
             for (int rw = 0; rw < classes[0]; ++rw) {
@@ -757,28 +861,20 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                     empty |= d[i].ntap == 0 || d[i].cnt == 0;
                 }
                 if (empty) continue;
-                TcConvParams p;
-                p.wq = d[0].cnt;  p.hq = d[1].cnt;  p.tq = d[2].cnt;
-                p.M = s->n * p.tq * p.hq * p.wq;
-                p.cd = cd;  p.cs = cs;
-                p.sw = d[0].trav;  p.sh = d[1].trav;  p.st = d[2].trav;
-                p.bw = d[0].base;  p.bh = d[1].base;  p.bt = d[2].base;
-                p.ntaps = 0;
+                TcClass& c = p.cls[p.ncls];
+                c.wq = d[0].cnt;  c.hq = d[1].cnt;  c.tq = d[2].cnt;
+                c.M = s->n * c.tq * c.hq * c.wq;
+                c.bw = d[0].base;  c.bh = d[1].base;  c.bt = d[2].base;
+                c.rw = d[0].r;  c.rh = d[1].r;  c.rt = d[2].r;
+                c.tap0 = ntaps_all;
+                c.ntaps = d[2].ntap * d[1].ntap * d[0].ntap;
+                AVID_REQUIRE(ntaps_all + c.ntaps <= kMaxTaps, "conv_tc: more than %d taps", kMaxTaps);
                 for (int a = 0; a < d[2].ntap; ++a)
                     for (int b = 0; b < d[1].ntap; ++b)
-                        for (int c = 0; c < d[0].ntap; ++c) {
-                            const uint32_t ftap = (uint32_t)((d[2].ftap[a] * s->kh + d[1].ftap[b]) * s->kw + d[0].ftap[c]);
-                            p.taps[p.ntaps++] = (uint32_t)d[0].off[c] | ((uint32_t)d[1].off[b] << 8) | ((uint32_t)d[2].off[a] << 16) | (ftap << 24);
+                        for (int e = 0; e < d[0].ntap; ++e) {
+                            const uint32_t ftap = (uint32_t)((d[2].ftap[a] * s->kh + d[1].ftap[b]) * s->kw + d[0].ftap[e]);
+                            p.taps[ntaps_all++] = (uint32_t)d[0].off[e] | ((uint32_t)d[1].off[b] << 8) | ((uint32_t)d[2].off[a] << 16) | (ftap << 24);
                         }
-                p.x3 = x3;
-                {
-                    const char* dbg = getenv("AVID_TC_DEBUG");
-                    p.debug = dbg ? atoi(dbg) : 0;
-                }
-                p.strided_out = dgrad && (ss[0] > 1 || ss[1] > 1 || ss[2] > 1);
-                p.Wd = dst[0];  p.Hd = dst[1];  p.Td = dst[2];
-                p.ow = d[0].ostride;  p.oh = d[1].ostride;  p.ot = d[2].ostride;
-                p.rw = d[0].r;  p.rh = d[1].r;  p.rt = d[2].r;
                 const int lower[3] = {d[0].base, d[1].base, d[2].base};
                 const int upper[3] = {d[0].upper, d[1].upper, d[2].upper};
                 const int stride[3] = {d[0].trav, d[1].trav, d[2].trav};
@@ -786,16 +882,21 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                     AVID_REQUIRE(lower[i] >= -16 && lower[i] <= 15 && upper[i] >= -16 && upper[i] <= 15 &&
                                      (src[i] + upper[i] - lower[i] - 1) / stride[i] + 1 == d[i].cnt,
                                  "conv_tc: geometry not expressible as an im2col box (dim %d: lower %d upper %d)", i, lower[i], upper[i]);
-                CUtensorMap maps[4];
-                if ((rc = encode_im2col(&maps[0], a_hi, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
-                maps[1] = maps[0];
-                if (x3 && (rc = encode_im2col(&maps[1], a_lo, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
-                maps[2] = map_b[0];
-                maps[3] = map_b[1];
-                rc = bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, stats, fuse, st) : launch_conv_tc<64>(maps, p, addend, out, stats, fuse, st);
-                if (rc) return rc;
+                if ((rc = encode_im2col(&maps.a[p.ncls][0], a_hi, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
+                maps.a[p.ncls][1] = maps.a[p.ncls][0];
+                if (x3 && (rc = encode_im2col(&maps.a[p.ncls][1], a_lo, s->n, src[2], src[1], src[0], cs, lower, upper, stride, kBM))) return rc;
+                const int mt = (c.M + kBM - 1) / kBM;
+                if (mt > p.mtiles) p.mtiles = mt;
+                ++p.ncls;
             }
-    return AVID_OK;
+    if (p.ncls == 0) return AVID_OK;
+    for (int c = p.ncls; c < kMaxCls; ++c) {      // unused slots: defined bytes in the parameter block
+        p.cls[c] = p.cls[0];
+        maps.a[c][0] = maps.a[0][0];
+        maps.a[c][1] = maps.a[0][1];
+    }
+    for (int t = ntaps_all; t < kMaxTaps; ++t) p.taps[t] = 0;
+    return bn == 128 ? launch_conv_tc<128>(maps, p, addend, out, stats, fuse, st) : launch_conv_tc<64>(maps, p, addend, out, stats, fuse, st);
 }
 
 template <int BN, int G>

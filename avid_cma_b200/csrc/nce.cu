@@ -103,7 +103,8 @@ __device__ __forceinline__ float dot16(const float4 (&a)[4], const float4 (&b)[4
 // (key constants folded per lane, (bank, ctx) pairs as template parameter, rcp / lg2 approximations behind a series for
 // log1p, packed item descriptors, coefficient by one shuffle), the Philox rounds of the first chunk run while y is in flight,
 // the last split CTA finalises a query with one warp per context and no block barrier: 36.9 -> 30.7 us at K = 1024 (same box,
-// A/B), 75.8 -> 73.7 us at K = 4096, 213.9 -> 228.2 us at K = 16384 (0.77 -> 0.72 of the measured HBM rate: not understood).
+// A/B), 75.8 -> 73.7 us at K = 4096, 213.9 -> 228.2 us at K = 16384 (0.77 -> 0.72 of the measured HBM rate: not understood;
+// four resident CTAs per SM under a 128-register cap -- 152 B of spills -- are slower still: 0.67, and 32.8 us at K = 1024).
 // Measured and dropped (round 2): landing the rows in a per-warp shared-memory ring instead of registers -- with per-row
 // cp.async.bulk copies (request-rate bound: ~35 cycles per 512-byte request and SM; K = 1024: 49 us vs 39 us) and with cp.async
 // 16 B per lane (58 us; K = 16384: 0.60 instead of 0.77 of the HBM peak).  Also dropped: a per-lane prefetch.global.L2 of the
