@@ -229,12 +229,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         int it = 0;
         for (int pr = cluster_id; pr < p.num_pairs; pr += num_clusters, ++it) {
             const int buf = it & 1;
-            const int g = pr / p.tiles_per_frame, i = pr - g * p.tiles_per_frame;
-            const int f = 2 * g + (int)rank;
-            const int s = 128 * i + q * 32 + lane;          // strip pixel of accumulator row q * 32 + lane
-            const int h = s / p.Wp, c = s - h * p.Wp;
-            const bool valid = f < p.frames && h < p.H && c >= 1 && c <= p.W;
-            const uint32_t my_row = valid ? (uint32_t)((f * p.H + h) * p.W + (c - 1)) : ~0u;       // output pixel (the host checks frames * H * W < 2^31)
+            // output pixel of accumulator row q * 32 + lane of pair tile `t` (the host checks frames * H * W < 2^31); ~0: none
+            auto row_of = [&](int t) -> uint32_t {
+                const int g = t / p.tiles_per_frame, i = t - g * p.tiles_per_frame;
+                const int f = 2 * g + (int)rank;
+                const int s = 128 * i + q * 32 + lane;      // strip pixel
+                const int h = s / p.Wp, c = s - h * p.Wp;
+                const bool valid = t < p.num_pairs && f < p.frames && h < p.H && c >= 1 && c <= p.W;
+                return valid ? (uint32_t)((f * p.H + h) * p.W + (c - 1)) : ~0u;
+            };
+            const uint32_t my_row = row_of(pr);
+            if (addend || fuse.z) {      // the rows of the NEXT tile on their way to L2 (this warp's 32 columns of a row are one 128-byte line)
+                const uint32_t nxt = row_of(pr + num_clusters);
+                if (nxt != ~0u) {
+                    if (addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + (size_t)nxt * kPairBN + hsel * 32));
+                    if (fuse.z) asm volatile("prefetch.global.L2 [%0];" ::"l"(fuse.z + (size_t)nxt * kPairBN + hsel * 32));
+                }
+            }
             uint32_t rows4[4];                              // this lane's rows: r8, r8 + 8, r8 + 16, r8 + 24 of the quarter
 #pragma unroll
             for (int j = 0; j < 4; ++j) rows4[j] = __shfl_sync(0xffffffffu, my_row, j * 8 + r8);
