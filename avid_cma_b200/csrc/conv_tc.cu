@@ -80,6 +80,9 @@ struct TcConvParams {
     int x3;                         // 1: hi/lo planes, 3 MMAs per k-step; 0: hi only
     int strided_out;                // destination rows are scattered to the pixels of their class
     int Td, Hd, Wd, ot, oh, ow;
+    // subsampled addend (add_w != 0): the addend tensor is [n, add_T, add_H, add_W, cd] and belongs to the destination pixels whose
+    // coordinates are multiples of (add_t, add_h, add_w) -- the input gradient of a strided 1x1x1 residual convolution, zero elsewhere
+    int add_t, add_h, add_w, add_T, add_H, add_W;
     int debug;                      // AVID_TC_DEBUG probe bits (scripts/probe_conv.py; 0 in production): 1 no global stores, 2 no
                                     // statistics, 4 epilogue only hands the accumulator back, 8 no MMAs, 64 no per-tile atomics
 };
@@ -287,42 +290,52 @@ conv_tc_kernel(const __grid_constant__ TcConvMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int t = 0; t < 4; ++t) run1[a][b][t] = run2[a][b][t] = 0.f;
         int it = 0;
-        // element offset of the destination row this lane reads from TMEM in `tile` (~0: none)
-        auto row_of = [&](int tile) -> unsigned long long {
-            if (tile >= num_tiles) return ~0ull;
+        // element offsets of the destination row this lane reads from TMEM in `tile` and of its addend row (~0: none)
+        struct RowPair { unsigned long long row, arow; };
+        auto row_of = [&](int tile) -> RowPair {
+            RowPair rp{~0ull, ~0ull};
+            if (tile >= num_tiles) return rp;
             const TcTile tl = decode_tile<BN>(p, tile, nblocks);
-            if (!tl.valid) return ~0ull;
+            if (!tl.valid) return rp;
             const TcClass& cl = p.cls[tl.cls];
             const int m = tl.m0 + q * 32 + lane;
+            if (m >= cl.M) return rp;
             size_t pix = (size_t)m;
-            if (p.strided_out) {        // a stride-parity class of a strided input gradient: scatter rows to their pixels
+            if (p.strided_out || p.add_w) {        // a stride-parity class of a strided input gradient: scatter rows to their pixels
                 int r = m;
                 const int w_o = r % cl.wq;  r /= cl.wq;
                 const int h_o = r % cl.hq;  r /= cl.hq;
                 const int t_o = r % cl.tq;
                 const int n_i = r / cl.tq;
-                pix = (((size_t)n_i * p.Td + t_o * p.ot + cl.rt) * p.Hd + h_o * p.oh + cl.rh) * p.Wd + w_o * p.ow + cl.rw;
+                const int td = t_o * p.ot + cl.rt, hd = h_o * p.oh + cl.rh, wd = w_o * p.ow + cl.rw;
+                pix = (((size_t)n_i * p.Td + td) * p.Hd + hd) * p.Wd + wd;
+                if (p.add_w && td % p.add_t == 0 && hd % p.add_h == 0 && wd % p.add_w == 0)
+                    rp.arow = ((((size_t)n_i * p.add_T + td / p.add_t) * p.add_H + hd / p.add_h) * p.add_W + wd / p.add_w) * p.cd + n0;
             }
-            return m < cl.M ? (unsigned long long)(pix * p.cd + n0) : ~0ull;
+            rp.row = (unsigned long long)(pix * p.cd + n0);
+            if (!p.add_w) rp.arow = rp.row;
+            return rp;
         };
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const unsigned long long my_row = row_of(tile);
+            const RowPair mine = row_of(tile);
+            const unsigned long long my_row = mine.row;
             if (!decode_tile<BN>(p, tile, nblocks).valid) continue;
             const int buf = it & 1;
             if (addend || fuse.z) {
                 // the rows of the CTA's NEXT tile on their way to L2 (a 32-column chunk of a row is one 128-byte line)
-                const unsigned long long nxt = row_of(tile + gridDim.x);
-                if (nxt != ~0ull) {
+                const RowPair nxt = row_of(tile + gridDim.x);
 #pragma unroll
-                    for (int jj = 0; jj < kChunks; ++jj) {
-                        if (addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + nxt + (hsel * kChunks + jj) * 32));
-                        if (fuse.z) asm volatile("prefetch.global.L2 [%0];" ::"l"(fuse.z + nxt + (hsel * kChunks + jj) * 32));
-                    }
+                for (int jj = 0; jj < kChunks; ++jj) {
+                    if (addend && nxt.arow != ~0ull) asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + nxt.arow + (hsel * kChunks + jj) * 32));
+                    if (fuse.z && nxt.row != ~0ull) asm volatile("prefetch.global.L2 [%0];" ::"l"(fuse.z + nxt.row + (hsel * kChunks + jj) * 32));
                 }
             }
-            unsigned long long rows4[4];            // element offsets of the rows this lane serves in the coalesced layout (~0: no row)
+            unsigned long long rows4[4], rows4a[4]; // element offsets of the rows this lane serves in the coalesced layout (~0: no row) / their addend rows
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rows4[i] = __shfl_sync(0xffffffffu, my_row, i * 8 + r8);
+            for (int i = 0; i < 4; ++i) {
+                rows4[i] = __shfl_sync(0xffffffffu, my_row, i * 8 + r8);
+                rows4a[i] = __shfl_sync(0xffffffffu, mine.arow, i * 8 + r8);
+            }
             // BN = 64 (two half-chunks per warp, registers to spare): the residual addend and the z tile of the fused BatchNorm
             // backward of the WHOLE tile are requested before the accumulator wait -- their addresses depend on the tile index
             // only.  Requested per half-chunk behind the wait, the strided conv3x-entry input gradient (both operands, 85 tiles per
@@ -335,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ TcConvMaps maps, const __grid_constant__ 
                     const int col = hsel * 32 + hh * 16;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        ad_pre[hh][i] = (addend && rows4[i] != ~0ull) ? __ldg(reinterpret_cast<const float4*>(addend + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        ad_pre[hh][i] = (addend && rows4a[i] != ~0ull) ? __ldg(reinterpret_cast<const float4*>(addend + rows4a[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         zz_pre[hh][i] = (fuse.z && rows4[i] != ~0ull) ? __ldg(reinterpret_cast<const float4*>(fuse.z + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
@@ -369,7 +382,7 @@ conv_tc_kernel(const __grid_constant__ TcConvMaps maps, const __grid_constant__ 
                     if (addend) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            ad[i] = rows4[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            ad[i] = rows4a[i] != ~0ull ? __ldg(reinterpret_cast<const float4*>(addend + rows4a[i] + col + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (fuse.z) {
 #pragma unroll
@@ -796,7 +809,7 @@ static DimPlan plan_dgrad(int dst, int src, int k, int s, int pad, int r) {
 //             input gradient is st * sh * sw stride-parity classes, each a stride-1 correlation with its own taps and im2col
 //             box; all classes run in ONE launch (tile -> class, see decode_tile).
 int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
-                const float* addend, float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
+                const float* addend, const int32_t* addend_stride, float* out, double* stats, const BnBwdFuse& fuse, cudaStream_t st) {
     AVID_REQUIRE(s && a_hi && b_hi && out, "conv_tc: NULL pointer");
     AVID_REQUIRE(!(stats && fuse.z), "conv_tc: forward statistics and the fused BatchNorm backward reduction are exclusive");
     AVID_REQUIRE(!fuse.z || (fuse.mean && fuse.invstd && fuse.gamma && fuse.beta && fuse.sums), "conv_tc: incomplete BatchNorm fusion arguments");
@@ -817,8 +830,13 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     const bool x3 = a_lo != nullptr;
     int rc;
     // the 64 -> 64 channel 1x3x3 stride-1 layers (forward and input gradient) run on CTA pairs with a halo tile and a resident filter
-    rc = conv_pair_run(s, dgrad, a_hi, a_lo, b_hi, b_lo, addend, out, stats, fuse, st);
-    if (rc != AVID_EUNSUPPORTED) return rc;
+    const bool sub_addend = addend && addend_stride && (addend_stride[0] > 1 || addend_stride[1] > 1 || addend_stride[2] > 1);
+    AVID_REQUIRE(!sub_addend || (dgrad && addend_stride[0] >= 1 && addend_stride[1] >= 1 && addend_stride[2] >= 1),
+                 "conv_tc: a subsampled addend belongs to an input gradient and needs positive strides");
+    if (!sub_addend) {
+        rc = conv_pair_run(s, dgrad, a_hi, a_lo, b_hi, b_lo, addend, out, stats, fuse, st);
+        if (rc != AVID_EUNSUPPORTED) return rc;
+    }
     TcConvMaps maps;
     if ((rc = encode_tiled_2d(&maps.b[0], b_hi, (uint64_t)taps_total * cd, cs, bn, kBK))) return rc;
     maps.b[1] = maps.b[0];
@@ -849,6 +867,12 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     p.Wd = dst[0];  p.Hd = dst[1];  p.Td = dst[2];
     p.ow = classes[0];  p.oh = classes[1];  p.ot = classes[2];
     p.sw = dgrad ? 1 : ss[0];  p.sh = dgrad ? 1 : ss[1];  p.st = dgrad ? 1 : ss[2];
+    p.add_t = p.add_h = p.add_w = 0;
+    p.add_T = p.add_H = p.add_W = 0;
+    if (sub_addend) {      // (t, h, w) order like the shape struct
+        p.add_t = addend_stride[0];  p.add_h = addend_stride[1];  p.add_w = addend_stride[2];
+        p.add_T = (dst[2] + p.add_t - 1) / p.add_t;  p.add_H = (dst[1] + p.add_h - 1) / p.add_h;  p.add_W = (dst[0] + p.add_w - 1) / p.add_w;
+    }
     int ntaps_all = 0;
     for (int rt = 0; rt < classes[2]; ++rt)
         for (int rh = 0; rh < classes[1]; ++rh)
@@ -992,11 +1016,11 @@ int avid_conv_tc_uses_cta_pairs(const avid_conv_shape_t* s, int32_t dgrad) {
 
 int avid_conv_forward_tc(const avid_conv_shape_t* s, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
                          const float* addend, float* out, double* bn_stats, void* stream) {
-    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, out, bn_stats, BnBwdFuse{}, static_cast<cudaStream_t>(stream));
+    return conv_tc_run(s, 0, in_hi, in_lo, filt_hi, filt_lo, addend, nullptr, out, bn_stats, BnBwdFuse{}, static_cast<cudaStream_t>(stream));
 }
 
-int avid_conv_dgrad_tc(const avid_conv_shape_t* s, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
-                       const float* addend, float* din, const avid_bn_backward_fuse_t* fuse, void* stream) {
+int avid_conv_dgrad_tc_sub(const avid_conv_shape_t* s, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
+                           const float* addend, const int32_t* addend_stride, float* din, const avid_bn_backward_fuse_t* fuse, void* stream) {
     BnBwdFuse f;
     if (fuse) {
         f.z = fuse->z;  f.mean = fuse->mean;  f.invstd = fuse->invstd;  f.gamma = fuse->gamma;  f.beta = fuse->beta;  f.sums = fuse->sums;
@@ -1004,7 +1028,12 @@ int avid_conv_dgrad_tc(const avid_conv_shape_t* s, const void* dout_hi, const vo
     }
     // a class no filter tap reaches is zero-filled, not computed: its rows would be missing from the fused sums
     AVID_REQUIRE(!fuse || (s && s->kt >= s->st && s->kh >= s->sh && s->kw >= s->sw), "conv_dgrad_tc: BatchNorm fusion needs filter >= stride");
-    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, din, nullptr, f, static_cast<cudaStream_t>(stream));
+    return conv_tc_run(s, 1, dout_hi, dout_lo, filt_hi, filt_lo, addend, addend_stride, din, nullptr, f, static_cast<cudaStream_t>(stream));
+}
+
+int avid_conv_dgrad_tc(const avid_conv_shape_t* s, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
+                       const float* addend, float* din, const avid_bn_backward_fuse_t* fuse, void* stream) {
+    return avid_conv_dgrad_tc_sub(s, dout_hi, dout_lo, filt_hi, filt_lo, addend, nullptr, din, fuse, stream);
 }
 
 }  // extern "C"

@@ -99,11 +99,21 @@ class ConvOp:
         k_total = self.conv.out_channels * self.k[0] * self.k[1] * self.k[2]
         return self.tc and all(k >= s for k, s in zip(self.k, self.s)) and k_total >= FUSE_MIN_K
 
-    def dgrad(self, dz, addend=None, bn_fuse=None):
+    def dgrad(self, dz, addend=None, bn_fuse=None, addend_stride=None):
         if self.tc:
-            return ops.conv_dgrad_tc(self.shape, dz.hi, dz.lo, self.wd_hi, self.wd_lo, addend=addend, bn_fuse=bn_fuse)
-        assert bn_fuse is None
+            return ops.conv_dgrad_tc(self.shape, dz.hi, dz.lo, self.wd_hi, self.wd_lo, addend=addend, bn_fuse=bn_fuse, addend_stride=addend_stride)
+        assert bn_fuse is None and addend_stride is None
         return ops.conv_dgrad(self.shape, dz.f32, self.w_tap_t, addend=addend)
+
+    def subsampled_dgrad(self, dz):
+        """Strided 1x1x1 convolution on the tensor cores: its input gradient at the pixels it reads, [n, to, ho, wo, ci] (a
+        stride-1 1x1x1 input gradient over the OUTPUT grid; every other input pixel receives zero) and the stride, for
+        ops.conv_dgrad_tc(addend_stride=...).  None when the layer is not such a convolution."""
+        if not (self.tc and self.k == (1, 1, 1) and self.p == (0, 0, 0) and self.s != (1, 1, 1)):
+            return None
+        sh = self.shape
+        dense = ops.conv_shape(sh.n, sh.to, sh.ho, sh.wo, sh.ci, sh.co, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+        return ops.conv_dgrad_tc(dense, dz.hi, dz.lo, self.wd_hi, self.wd_lo), self.s
 
 
 class StemOp:
@@ -169,7 +179,7 @@ class ConvBNReLU:
         return y, (op, x, z, st, bn)
 
     @staticmethod
-    def backward(dy, saved, grads, need_dx=True, dx_addend=None, dz_f32=False, sums=None, below=None):
+    def backward(dy, saved, grads, need_dx=True, dx_addend=None, dz_f32=False, sums=None, below=None, dx_addend_stride=None):
         """dy: fp32 gradient at the ReLU output.  Returns (dx fp32 or None, dz: Act at the conv output, i.e. after
         the residual sum, sums_below).
 
@@ -196,7 +206,10 @@ class ConvBNReLU:
                 _, _, z_b, st_b, bn_b = below
                 sums_below = ops.bn_backward_sums(z_b.shape[-1], z_b.device)
                 fuse = (z_b, st_b, bn_b.weight.detach(), bn_b.bias.detach(), sums_below)
-            dx = op.dgrad(dz, addend=dx_addend, bn_fuse=fuse) if fuse is not None else op.dgrad(dz, addend=dx_addend)
+            if dx_addend_stride is not None:
+                dx = op.dgrad(dz, addend=dx_addend, bn_fuse=fuse, addend_stride=dx_addend_stride)
+            else:
+                dx = op.dgrad(dz, addend=dx_addend, bn_fuse=fuse) if fuse is not None else op.dgrad(dz, addend=dx_addend)
         if side:
             # The filter gradient starts when the input gradient has DRAINED (event after it, AVID_WGRAD_STREAM=2: before it): two persistent
             # tensor-core grids cannot share the SMs anyway, and this way the wgrad CTAs and the BatchNorm-backward pass of the next layer
@@ -282,14 +295,24 @@ class BasicR2P1DBlock(nn.Module):
         d3, d_sum, sums3 = ConvBNReLU.backward(dy, s4, grads, dz_f32=(not self.res) or rop.needs_f32_dz(), sums=sums, below=s3)
         d2, _, sums2 = ConvBNReLU.backward(d3, s3, grads, sums=sums3, below=s2)
         d1, _, sums1 = ConvBNReLU.backward(d2, s2, grads, sums=sums2, below=s1)
+        res_stride = None
         if self.res:
             grads[self.res_conv.weight] = rop.wgrad(x, d_sum)
-            d_res = rop.dgrad(d_sum) if need_dx else None
+            d_res = None
+            if need_dx:
+                # a strided 1x1x1 residual branch: its input gradient stays on the output grid (no zero fill of the input grid, and
+                # spt_conv1's input gradient reads 1/8 of the addend bytes)
+                sub = rop.subsampled_dgrad(d_sum) if s1[0].tc and not isinstance(s1[0], StemOp) else None
+                if sub is not None:
+                    d_res, res_stride = sub
+                else:
+                    d_res = rop.dgrad(d_sum)
         else:
             d_res = d_sum.f32
         # the block's input gradient = spt_conv1's input gradient + the residual branch's (fused as the epilogue addend), so the
         # epilogue sees the complete gradient and can reduce the BatchNorm backward of the layer below
-        dx, _, sums_below = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx, dx_addend=d_res, sums=sums1, below=below)
+        dx, _, sums_below = ConvBNReLU.backward(d1, s1, grads, need_dx=need_dx, dx_addend=d_res, sums=sums1, below=below,
+                                                dx_addend_stride=res_stride)
         return dx, sums_below
 
     @staticmethod

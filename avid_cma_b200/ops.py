@@ -525,21 +525,29 @@ def bn_backward_sums(c, device):
     return _zeros((2, c), torch.float64, device)
 
 
-def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None, bn_fuse=None):
+def conv_dgrad_tc(s, d_hi, d_lo, w_hi, w_lo, addend=None, out=None, bn_fuse=None, addend_stride=None):
     """tcgen05 input gradient (any stride); d_* planes [n,to,ho,wo,co] bf16, w_* planes [taps,ci,co] bf16.
     bn_fuse = (z, BNState, gamma, beta, sums): also accumulate the BatchNorm-backward sums of the layer that produced this
-    convolution's input (z: its conv output) -- see avid_bn_backward_fuse_t."""
+    convolution's input (z: its conv output) -- see avid_bn_backward_fuse_t.
+    addend_stride = (at, ah, aw): `addend` is the subsampled tensor [n, ceil(ti/at), ceil(hi/ah), ceil(wi/aw), ci] of
+    avid_conv_dgrad_tc_sub (the input gradient of a strided 1x1x1 residual convolution, zero at every other pixel)."""
     if out is None:
         out = torch.empty(s.n, s.ti, s.hi, s.wi, s.ci, dtype=torch.float32, device=d_hi.device)
+    sub = None
+    if addend_stride is not None and addend is not None and tuple(addend_stride) != (1, 1, 1):
+        at, ah, aw = addend_stride
+        want = (s.n, -(-s.ti // at), -(-s.hi // ah), -(-s.wi // aw), s.ci)
+        assert tuple(addend.shape) == want, (tuple(addend.shape), want)
+        sub = (C.c_int32 * 3)(at, ah, aw)
     fuse = None
     if bn_fuse is not None:
         z, st, gamma, beta, sums = bn_fuse
         assert z.numel() == out.numel()
         fuse = _lib.BnBackwardFuse(_p(z), _p(st.mean), _p(st.invstd), _p(gamma), _p(beta), _p(sums, torch.float64))
     e0 = _t0()
-    check(_lib.lib().avid_conv_dgrad_tc(C.byref(s), _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
-                                        _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), _p(out),
-                                        C.byref(fuse) if fuse is not None else None, _stream()))
+    check(_lib.lib().avid_conv_dgrad_tc_sub(C.byref(s), _p(d_hi, torch.bfloat16), _p(d_lo, torch.bfloat16, optional=True), _p(w_hi, torch.bfloat16),
+                                            _p(w_lo, torch.bfloat16, optional=True), _p(addend, optional=True), sub, _p(out),
+                                            C.byref(fuse) if fuse is not None else None, _stream()))
     if e0 is not None:
         _t1(e0, "conv_pair_dgrad" if _lib.lib().avid_conv_tc_uses_cta_pairs(C.byref(s), 1) else "conv_dgrad_tc%d" % (128 if s.ci % 128 == 0 else 64), _conv_flops(s))
     return out

@@ -240,7 +240,7 @@ int avid_conv_wgrad(const avid_conv_shape_t* s_host, const float* in, const floa
  * Channel counts must be multiples of 64 (every layer of both towers except the two stems).
  *   forward: in planes [n,ti,hi,wi,ci], filter planes K-major [taps][co][ci] (the w_tap_t layout)
  *   dgrad  : dout planes [n,to,ho,wo,co], filter planes [taps][ci][co] (the w_tap layout); a strided gradient runs as one
- *            stride-1 correlation per stride-parity class of the input pixels (st*sh*sw launches)                      */
+ *            stride-1 correlation per stride-parity class of the input pixels (st*sh*sw classes, ONE launch)            */
 int avid_split_bf16(const float* x, void* hi, void* lo /* may be NULL */, int64_t n, void* stream);
 int avid_conv_forward_tc(const avid_conv_shape_t* s_host, const void* in_hi, const void* in_lo, const void* filt_hi, const void* filt_lo,
                          const float* addend, float* out, double* bn_stats, void* stream);
@@ -258,6 +258,14 @@ typedef struct avid_bn_backward_fuse {
 } avid_bn_backward_fuse_t;
 int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
                        const float* addend, float* din, const avid_bn_backward_fuse_t* fuse_host /* may be NULL */, void* stream);
+/* avid_conv_dgrad_tc with a SUBSAMPLED addend: `addend` is [n, ceil(ti/at), ceil(hi/ah), ceil(wi/aw), ci] and is added to the
+ * input pixels (t, h, w) with t % at == 0, h % ah == 0, w % aw == 0 only (addend_stride = {at, ah, aw}; NULL or all ones: the dense
+ * addend of avid_conv_dgrad_tc).  That is the input gradient of the strided 1x1x1 residual convolution of a stage entry
+ * (network_blocks.py:46-49, :58 of the reference: x_res = res_conv(x)), which is zero at every other pixel: it is computed as a
+ * stride-1 1x1x1 input gradient over the OUTPUT grid, never zero-filled to the input grid and never read back from there. */
+int avid_conv_dgrad_tc_sub(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
+                           const float* addend, const int32_t* addend_stride_host /* {at, ah, aw}, may be NULL */, float* din,
+                           const avid_bn_backward_fuse_t* fuse_host /* may be NULL */, void* stream);
 /* Host-only query: which kernel avid_conv_forward_tc (dgrad == 0) / avid_conv_dgrad_tc (dgrad != 0) launches for this geometry:
  * 1 = conv_pair_kernel (64 -> 64 channel 1x3x3 stride-1 layers: CTA pairs, tcgen05 cta_group::2, halo strip, resident filter;
  * network_blocks.py:35-37 / :14-16 at 64 channels), 0 = conv_tc_kernel (im2col TMA, every other layer).  bench.py labels its

@@ -183,3 +183,47 @@ def test_conv_tc_full_resolution_properties(case):
     assert abs(lhs - float((dw.double() * wt.to(DEV).double()).sum())) < 2e-5 * scale    # = <w, wgrad(x, d)>
     if not stem:
         assert abs(lhs - float((ops.nhwc_to_nchw(din).double() * x.to(DEV).double()).sum())) < 2e-5 * scale   # = <x, dgrad(d)>
+
+
+# (n, ci, co, (t,h,w) of the INPUT, kernel, stride, padding of the main convolution, stride of the 1x1x1 residual convolution)
+SUB_ADDEND_CASES = [
+    (2, 64, 128, (4, 10, 10), (1, 3, 3), (1, 2, 2), (0, 1, 1), (2, 2, 2)),    # stage entry of the video tower: spatial stride below a (2,2,2) residual
+    (2, 64, 64, (3, 9, 11), (1, 3, 3), (1, 2, 2), (0, 1, 1), (2, 2, 2)),      # odd extents: ragged classes, ceil-sized addend grid
+    (1, 128, 128, (5, 6, 6), (1, 3, 3), (1, 1, 1), (0, 1, 1), (2, 1, 1)),     # stride-1 main convolution (one class), temporal residual stride
+    (2, 64, 128, (3, 7, 9), (3, 3, 3), (2, 2, 2), (1, 1, 1), (1, 2, 2)),      # 8 parity classes
+]
+
+
+@pytest.mark.parametrize("case", SUB_ADDEND_CASES, ids=[f"a{i}" for i in range(len(SUB_ADDEND_CASES))])
+def test_conv_tc_dgrad_subsampled_addend_equals_scattered_dense_addend(case):
+    """avid_conv_dgrad_tc_sub: the input gradient of a strided 1x1x1 residual convolution stays on its output grid; adding it as a
+    subsampled addend must give bit for bit what the dense, zero-filled addend gives -- output AND fused BatchNorm-backward sums."""
+    from avid_cma_b200 import ops
+    n, ci, co, (t, h, w), k, s, p, rs = case
+    g = torch.Generator().manual_seed(hash(case) % 2 ** 31)
+    shape = ops.conv_shape(n, t, h, w, ci, co, k, s, p)
+    dout = torch.randn(n, shape.to, shape.ho, shape.wo, co, generator=g).to(DEV)
+    wt = (torch.randn(k[0] * k[1] * k[2], ci, co, generator=g) / (co * k[0] * k[1] * k[2]) ** 0.5).to(DEV)       # dgrad operand [taps, ci, co]
+    d_hi, d_lo = ops.split_bf16(dout, True)
+    w_hi, w_lo = ops.split_bf16(wt, True)
+    ta, ha, wa = -(-t // rs[0]), -(-h // rs[1]), -(-w // rs[2])
+    sub = torch.randn(n, ta, ha, wa, ci, generator=g).to(DEV)
+    dense = torch.zeros(n, t, h, w, ci, device=DEV)
+    dense[:, ::rs[0], ::rs[1], ::rs[2]] = sub
+    z = torch.randn(n, t, h, w, ci, generator=g).to(DEV)
+    st = ops.BNState(ci, DEV)
+    st.mean.copy_(torch.randn(ci, generator=g) * 0.1)
+    st.invstd.copy_(torch.rand(ci, generator=g) + 0.5)
+    gamma, beta = (torch.rand(ci, generator=g) + 0.5).to(DEV), (torch.randn(ci, generator=g) * 0.1).to(DEV)
+    fuse_ok = all(kk >= ss for kk, ss in zip(k, s))
+    outs = []
+    for addend, stride in ((dense, None), (sub, rs)):
+        sums = torch.zeros(2, ci, dtype=torch.float64, device=DEV)
+        out = ops.conv_dgrad_tc(shape, d_hi, d_lo, w_hi, w_lo, addend=addend, addend_stride=stride,
+                                bn_fuse=(z, st, gamma, beta, sums) if fuse_ok else None)
+        torch.cuda.synchronize()
+        outs.append((out, sums))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-12, atol=0)          # fp64 atomics: the order of the CTAs' contributions may differ
+    plain = ops.conv_dgrad_tc(shape, d_hi, d_lo, w_hi, w_lo)
+    assert torch.equal(outs[1][0] - plain, dense) or _rel(outs[1][0] - plain, dense) < 1e-6
