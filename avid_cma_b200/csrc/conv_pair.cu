@@ -41,6 +41,7 @@ constexpr int kPairStgBytes = 4 * 2 * kPairBN * 4;     // per-CTA reduction of t
 struct PairParams {
     int frames, T, H, W, Wp;          // N * T frames of H x W pixels; strip pitch Wp = W + 2
     int tiles_per_frame, num_pairs;   // 128-pixel strip tiles per frame; (frame pairs) x (tiles per frame)
+    FastDiv d_tpf, d_wp;              // divisions by tiles_per_frame / Wp in the epilogue's tile -> pixel decode (tc_common.cuh)
     int slots;                        // plane slots in the ring: 3, or 2 for wide frames
     int slot_bytes;                   // pitch of the plane slots: R rows x Wp pixels x 128 B rounded up to 1 KB
     int slot_bytes_tx;                // bytes one strip load delivers (R * Wp * 128)
@@ -231,10 +232,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const int buf = it & 1;
             // output pixel of accumulator row q * 32 + lane of pair tile `t` (the host checks frames * H * W < 2^31); ~0: none
             auto row_of = [&](int t) -> uint32_t {
-                const int g = t / p.tiles_per_frame, i = t - g * p.tiles_per_frame;
+                int i, c;
+                const int g = fdivmod(t, p.d_tpf, i);
                 const int f = 2 * g + (int)rank;
                 const int s = 128 * i + q * 32 + lane;      // strip pixel
-                const int h = s / p.Wp, c = s - h * p.Wp;
+                const int h = fdivmod(s, p.d_wp, c);
                 const bool valid = t < p.num_pairs && f < p.frames && h < p.H && c >= 1 && c <= p.W;
                 return valid ? (uint32_t)((f * p.H + h) * p.W + (c - 1)) : ~0u;
             };
@@ -388,6 +390,7 @@ static bool conv_pair_plan(const avid_conv_shape_t* s, PairParams& p) {
     p.slot_bytes_tx = slot_tx;
     p.tiles_per_frame = (p.H * p.Wp + 127) / 128;
     p.num_pairs = ((p.frames + 1) / 2) * p.tiles_per_frame;
+    p.d_tpf = make_fastdiv(p.tiles_per_frame);  p.d_wp = make_fastdiv(p.Wp);
     return true;
 }
 

@@ -64,6 +64,7 @@ constexpr int kMaxCls = 8;      // stride-parity classes of one launch (2 x 2 x 
 struct TcClass {
     int M;                          // destination pixels of the class, enumerated ((n * tq + t) * hq + h) * wq + w
     int tq, hq, wq;                 // extents of that enumeration
+    FastDiv dtq, dhq, dwq;
     int bt, bh, bw;                 // source coordinate read by tap offset 0 for destination pixel 0 (forward: -padding)
     int tap0, ntaps;                // its entries of TcConvParams::taps
     int rt, rh, rw;                 // residues: enumerated pixel (n, t, h, w) -> ((n * Td + t * ot + rt) * Hd + h * oh + rh) * Wd + w * ow + rw
@@ -73,6 +74,8 @@ struct TcConvParams {
     int ncls;
     TcClass cls[kMaxCls];
     int mtiles;                     // 128-pixel tiles of the largest class
+    FastDiv dncls, dnblocks;        // divisions of the tile index
+    FastDiv dadd_t, dadd_h, dadd_w;
     int cd;                         // destination channels (GEMM N total)
     int cs;                         // source channels (GEMM K per tap)
     int st, sh, sw;                 // source traversal strides (forward conv stride; 1 for dgrad)
@@ -102,11 +105,12 @@ struct TcTile {
 template <int BN>
 __device__ __forceinline__ TcTile decode_tile(const TcConvParams& p, int tile, int nblocks) {
     TcTile t;
-    t.n0 = (tile % nblocks) * BN;
-    const int rest = tile / nblocks;
-    t.cls = rest % p.ncls;
-    t.m0 = (rest / p.ncls) * kBM;
+    int nb;
+    const int rest = fdivmod(tile, p.dnblocks, nb);
+    t.n0 = nb * BN;
+    t.m0 = fdivmod(rest, p.dncls, t.cls) * kBM;
     t.valid = t.m0 < p.cls[t.cls].M;
+    (void)nblocks;
     return t;
 }
 
@@ -185,11 +189,8 @@ conv_tc_kernel(const __grid_constant__ TcConvMaps maps, const __grid_constant__ 
             const CUtensorMap* const map_a_hi = &maps.a[tl.cls][0];
             const CUtensorMap* const map_a_lo = &maps.a[tl.cls][1];
             const int n0 = tl.n0;
-            int m = tl.m0;
-            const int w_o = m % cl.wq;  m /= cl.wq;
-            const int h_o = m % cl.hq;  m /= cl.hq;
-            const int t_o = m % cl.tq;
-            const int n_i = m / cl.tq;
+            int w_o, h_o, t_o;
+            const int n_i = fdivmod(fdivmod(fdivmod(tl.m0, cl.dwq, w_o), cl.dhq, h_o), cl.dtq, t_o);
             const int bw = w_o * p.sw + cl.bw, bh = h_o * p.sh + cl.bh, bt = t_o * p.st + cl.bt;   // source pixel read by tap offset 0
             const int nkb = cl.ntaps * cblocks;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -302,15 +303,15 @@ conv_tc_kernel(const __grid_constant__ TcConvMaps maps, const __grid_constant__ 
             if (m >= cl.M) return rp;
             size_t pix = (size_t)m;
             if (p.strided_out || p.add_w) {        // a stride-parity class of a strided input gradient: scatter rows to their pixels
-                int r = m;
-                const int w_o = r % cl.wq;  r /= cl.wq;
-                const int h_o = r % cl.hq;  r /= cl.hq;
-                const int t_o = r % cl.tq;
-                const int n_i = r / cl.tq;
+                int w_o, h_o, t_o;
+                const int n_i = fdivmod(fdivmod(fdivmod(m, cl.dwq, w_o), cl.dhq, h_o), cl.dtq, t_o);
                 const int td = t_o * p.ot + cl.rt, hd = h_o * p.oh + cl.rh, wd = w_o * p.ow + cl.rw;
                 pix = (((size_t)n_i * p.Td + td) * p.Hd + hd) * p.Wd + wd;
-                if (p.add_w && td % p.add_t == 0 && hd % p.add_h == 0 && wd % p.add_w == 0)
-                    rp.arow = ((((size_t)n_i * p.add_T + td / p.add_t) * p.add_H + hd / p.add_h) * p.add_W + wd / p.add_w) * p.cd + n0;
+                if (p.add_w) {
+                    int rt_, rh_, rw_;
+                    const int ta = fdivmod(td, p.dadd_t, rt_), ha = fdivmod(hd, p.dadd_h, rh_), wa = fdivmod(wd, p.dadd_w, rw_);
+                    if ((rt_ | rh_ | rw_) == 0) rp.arow = ((((size_t)n_i * p.add_T + ta) * p.add_H + ha) * p.add_W + wa) * p.cd + n0;
+                }
             }
             rp.row = (unsigned long long)(pix * p.cd + n0);
             if (!p.add_w) rp.arow = rp.row;
@@ -869,9 +870,11 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
     p.sw = dgrad ? 1 : ss[0];  p.sh = dgrad ? 1 : ss[1];  p.st = dgrad ? 1 : ss[2];
     p.add_t = p.add_h = p.add_w = 0;
     p.add_T = p.add_H = p.add_W = 0;
+    p.dadd_t = p.dadd_h = p.dadd_w = make_fastdiv(1);
     if (sub_addend) {      // (t, h, w) order like the shape struct
         p.add_t = addend_stride[0];  p.add_h = addend_stride[1];  p.add_w = addend_stride[2];
         p.add_T = (dst[2] + p.add_t - 1) / p.add_t;  p.add_H = (dst[1] + p.add_h - 1) / p.add_h;  p.add_W = (dst[0] + p.add_w - 1) / p.add_w;
+        p.dadd_t = make_fastdiv(p.add_t);  p.dadd_h = make_fastdiv(p.add_h);  p.dadd_w = make_fastdiv(p.add_w);
     }
     int ntaps_all = 0;
     for (int rt = 0; rt < classes[2]; ++rt)
@@ -888,6 +891,7 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                 TcClass& c = p.cls[p.ncls];
                 c.wq = d[0].cnt;  c.hq = d[1].cnt;  c.tq = d[2].cnt;
                 c.M = s->n * c.tq * c.hq * c.wq;
+                c.dwq = make_fastdiv(c.wq);  c.dhq = make_fastdiv(c.hq);  c.dtq = make_fastdiv(c.tq);
                 c.bw = d[0].base;  c.bh = d[1].base;  c.bt = d[2].base;
                 c.rw = d[0].r;  c.rh = d[1].r;  c.rt = d[2].r;
                 c.tap0 = ntaps_all;
@@ -914,6 +918,8 @@ int conv_tc_run(const avid_conv_shape_t* s, int dgrad, const void* a_hi, const v
                 ++p.ncls;
             }
     if (p.ncls == 0) return AVID_OK;
+    p.dncls = make_fastdiv(p.ncls);
+    p.dnblocks = make_fastdiv(cd / bn);
     for (int c = p.ncls; c < kMaxCls; ++c) {      // unused slots: defined bytes in the parameter block
         p.cls[c] = p.cls[0];
         maps.a[c][0] = maps.a[0][0];

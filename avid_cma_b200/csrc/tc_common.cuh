@@ -202,6 +202,31 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
 // Optional fusion of the NEXT BatchNorm backward's reduction into an input-gradient launch: the tensor this launch writes is
 // the gradient dy at the ReLU output of the previous layer, whose BatchNorm backward needs sum(g) and sum(g * xhat) per
 // channel with g = dy * relu'(bn(z)), xhat = (z - mean) * invstd (z = that layer's conv output, same shape as dy).
+// Division of a 31-bit index by a launch constant as multiply-high + shift (magic = ceil(2^(31 + s) / d), s = ceil(log2 d): exact for
+// every n < 2^31): the tile -> pixel decode runs per tile in every epilogue lane, and six 32-bit divisions were a third of the
+// epilogue's instructions on the short-K layers.
+struct FastDiv {
+    uint32_t magic;
+    int shift;
+    int d;
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d < 1 ? 1 : d;
+    int s = 0;
+    while (((int64_t)1 << s) < f.d) ++s;
+    f.shift = 31 + s;
+    f.magic = (uint32_t)((((uint64_t)1 << f.shift) + (uint64_t)f.d - 1) / (uint64_t)f.d);
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return (int)(((uint64_t)(uint32_t)n * f.magic) >> f.shift); }
+// n -> (n / d, n % d)
+__device__ __forceinline__ int fdivmod(int n, const FastDiv& f, int& rem) {
+    const int q = fdiv(n, f);
+    rem = n - q * f.d;
+    return q;
+}
+
 struct BnBwdFuse {
     const float* z = nullptr;
     const float* mean = nullptr;
