@@ -960,8 +960,12 @@ int wgrad_tc_run(const avid_conv_shape_t* s, const void* x_hi, const void* x_lo,
     const int taps = s->kt * s->kh * s->kw;
     p.groups = taps * (s->ci / 64);
     const int bn = s->co % 256 == 0 ? 256 : (s->co % 128 == 0 ? 128 : 64);
-    const bool three = p.groups == 3 && bn == 64;          // one CTA takes all three groups (see TcWgSmem)
-    const int tiles = three ? 1 : ((p.groups + 1) / 2) * (s->co / bn);
+    // 64 output channels and a multiple of three (tap, 64-channel) groups -- the 64-channel temporal layers (3 groups) and the 64 -> 64
+    // channel 3x3 layers (9 groups: conv2x spatial, audio block1): a CTA takes THREE groups in two accumulators (see TcWgSmem).  With
+    // two groups per CTA the 3x3 layers ran 5 CTAs per pixel range (the fifth with a dummy group), each loading its own dZ tile:
+    // 5 x 48 KB of operands per 64 pixels against 3 x 64 KB, on a launch that is bound by the L2 -> shared-memory stream.
+    const bool three = p.groups % 3 == 0 && bn == 64;
+    const int tiles = three ? p.groups / 3 : ((p.groups + 1) / 2) * (s->co / bn);
     const int total_kb = (p.M + kWgKB - 1) / kWgKB;
     // one CTA per SM (the stages fill shared memory): pick the pixel split that minimises waves x (k-blocks per CTA + the fixed
     // prologue / atomic-epilogue cost, ~8 k-blocks) -- a grid of 300 CTAs on 148 SMs would run a third wave for 4 CTAs.
