@@ -93,6 +93,7 @@ _SIGNATURES = {
     "avid_conv_tc_uses_cta_pairs": (C.c_int, [C.POINTER(ConvShape), C.c_int32]),
     "avid_conv_forward_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, _P, _P]),
     "avid_conv_dgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P, C.POINTER(BnBackwardFuse), _P]),
+    "avid_conv_tc_plan": (C.c_int, [C.POINTER(ConvShape), c_int32, C.POINTER(c_int64)]),
     "avid_conv_dgrad_tc_sub": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, C.POINTER(C.c_int32), _P, C.POINTER(BnBackwardFuse), _P]),
     "avid_conv_wgrad_tc": (C.c_int, [C.POINTER(ConvShape), _P, _P, _P, _P, _P, _P]),
     "avid_stem_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

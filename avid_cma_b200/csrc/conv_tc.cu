@@ -1019,6 +1019,44 @@ int avid_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream)
     return check_launch("split_bf16_kernel");
 }
 
+int avid_conv_tc_plan(const avid_conv_shape_t* s, int32_t dgrad, int64_t* out) {
+    AVID_REQUIRE(s && out, "conv_tc_plan: NULL pointer");
+    AVID_REQUIRE(s->st >= 1 && s->sh >= 1 && s->sw >= 1 && s->kt >= 1 && s->kh >= 1 && s->kw >= 1, "conv_tc_plan: bad filter / stride");
+    const int src[3] = {dgrad ? s->wo : s->wi, dgrad ? s->ho : s->hi, dgrad ? s->to : s->ti};
+    const int dst[3] = {dgrad ? s->wi : s->wo, dgrad ? s->hi : s->ho, dgrad ? s->ti : s->to};
+    const int kk[3] = {s->kw, s->kh, s->kt}, ss[3] = {s->sw, s->sh, s->st}, pp[3] = {s->pw, s->ph, s->pt};
+    const int classes[3] = {dgrad ? ss[0] : 1, dgrad ? ss[1] : 1, dgrad ? ss[2] : 1};
+    int64_t ncls = 0, mtiles = 0, taps = 0, pixels = 0, div_ok = 1;
+    for (int rt = 0; rt < classes[2]; ++rt)
+        for (int rh = 0; rh < classes[1]; ++rh)
+            for (int rw = 0; rw < classes[0]; ++rw) {
+                const int rr[3] = {rw, rh, rt};
+                DimPlan d[3];
+                bool empty = false;
+                for (int i = 0; i < 3; ++i) {
+                    d[i] = dgrad ? plan_dgrad(dst[i], src[i], kk[i], ss[i], pp[i], rr[i]) : plan_forward(dst[i], kk[i], ss[i], pp[i]);
+                    empty |= d[i].ntap == 0 || d[i].cnt == 0;
+                }
+                if (empty) continue;
+                const int64_t M = (int64_t)s->n * d[2].cnt * d[1].cnt * d[0].cnt;
+                ++ncls;
+                taps += (int64_t)d[2].ntap * d[1].ntap * d[0].ntap;
+                pixels += M;
+                if ((M + kBM - 1) / kBM > mtiles) mtiles = (M + kBM - 1) / kBM;
+                // the multiply-high divisions of the tile -> pixel decode on the class extents: first / last indices and a stride through the range
+                for (int i = 0; i < 3; ++i) {
+                    const FastDiv f = make_fastdiv(d[i].cnt);
+                    const int64_t step = M / 997 + 1;
+                    for (int64_t n = 0; n < M; n += step)
+                        div_ok &= (int64_t)(((uint64_t)(uint32_t)n * f.magic) >> f.shift) == n / d[i].cnt;
+                    const int64_t last = M - 1;
+                    div_ok &= (int64_t)(((uint64_t)(uint32_t)last * f.magic) >> f.shift) == last / d[i].cnt;
+                }
+            }
+    out[0] = ncls;  out[1] = mtiles;  out[2] = taps;  out[3] = pixels;  out[4] = div_ok;
+    return AVID_OK;
+}
+
 int avid_conv_tc_uses_cta_pairs(const avid_conv_shape_t* s, int32_t dgrad) {
     (void)dgrad;      // the pair kernel takes both directions of the layers it takes
     return s && s->ci % 64 == 0 && s->co % 64 == 0 && conv_pair_supported(s) ? 1 : 0;

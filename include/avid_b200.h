@@ -266,6 +266,12 @@ int avid_conv_dgrad_tc(const avid_conv_shape_t* s_host, const void* dout_hi, con
 int avid_conv_dgrad_tc_sub(const avid_conv_shape_t* s_host, const void* dout_hi, const void* dout_lo, const void* filt_hi, const void* filt_lo,
                            const float* addend, const int32_t* addend_stride_host /* {at, ah, aw}, may be NULL */, float* din,
                            const avid_bn_backward_fuse_t* fuse_host /* may be NULL */, void* stream);
+/* Host-only query: the launch plan of avid_conv_forward_tc (dgrad == 0) / avid_conv_dgrad_tc (dgrad != 0) for a geometry
+ * (network_blocks.py:35-49: the strided stage entries are the interesting cases).  out[0] = stride-parity classes that have work (all
+ * run in ONE launch), out[1] = 128-pixel tiles of the largest class, out[2] = filter taps covered by the classes (each tap belongs
+ * to exactly one class: kt*kh*kw), out[3] = destination pixels covered (every pixel a tap reaches, exactly once), out[4] = 1 when the
+ * multiply-high divisions of the tile -> pixel decode reproduce integer division on a sample of indices of every class. */
+int avid_conv_tc_plan(const avid_conv_shape_t* s_host, int32_t dgrad, int64_t* out_host /* [5] */);
 /* Host-only query: which kernel avid_conv_forward_tc (dgrad == 0) / avid_conv_dgrad_tc (dgrad != 0) launches for this geometry:
  * 1 = conv_pair_kernel (64 -> 64 channel 1x3x3 stride-1 layers: CTA pairs, tcgen05 cta_group::2, halo strip, resident filter;
  * network_blocks.py:35-37 / :14-16 at 64 channels), 0 = conv_tc_kernel (im2col TMA, every other layer).  bench.py labels its

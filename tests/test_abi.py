@@ -149,3 +149,35 @@ def test_video_prep_planning_is_host_only(lib):
     bad.op_factor[1] = 0.75                       # hue_factor outside [-0.5, 0.5]: the reference raises too
     assert lib.avid_video_prep_workspace_bytes(C.byref(bad)) == 0 and b"hue_factor" in lib.avid_last_error()
     assert lib.avid_video_prep(None, C.byref(p), None, None, 0, None) == 1      # AVID_EINVAL
+
+
+def test_conv_tc_launch_plan_is_host_only(lib):
+    """avid_conv_tc_plan: the stride-parity classes of a strided input gradient partition the filter taps and the input pixels, and
+    the multiply-high divisions of the tile -> pixel decode are exact on every class (no GPU involved)."""
+    from avid_cma_b200 import ops
+    cases = [
+        # n, (t,h,w), ci, co, kernel, stride, padding
+        (64, (8, 56, 56), 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # conv3x entry of the video tower at config 2
+        (64, (8, 28, 28), 128, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),     # its temporal stride
+        (64, (1, 100, 129), 64, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1)),     # audio block entry: odd extents, ragged classes
+        (2, (3, 7, 9), 64, 128, (3, 3, 3), (2, 2, 2), (1, 1, 1)),         # 8 classes
+        (2, (4, 10, 10), 64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0)),       # 1x1x1 stride 2: 7 of 8 classes receive nothing
+        (4, (8, 28, 28), 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),        # stride 1
+    ]
+    for n, (t, h, w), ci, co, k, s, p in cases:
+        shape = ops.conv_shape(n, t, h, w, ci, co, k, s, p)
+        out = (C.c_int64 * 5)()
+        assert lib.avid_conv_tc_plan(C.byref(shape), 1, out) == 0
+        ncls, mtiles, taps, pixels, div_ok = list(out)
+        assert div_ok == 1
+        assert taps == k[0] * k[1] * k[2]
+        reached = all(kk >= ss for kk, ss in zip(k, s))
+        if reached:
+            assert ncls == s[0] * s[1] * s[2]
+            assert pixels == n * t * h * w
+        else:
+            assert ncls == 1 and pixels == n * shape.to * shape.ho * shape.wo
+        assert mtiles >= -(-pixels // ncls // 128)
+        assert lib.avid_conv_tc_plan(C.byref(shape), 0, out) == 0
+        assert list(out)[:4] == [1, -(-(n * shape.to * shape.ho * shape.wo) // 128), k[0] * k[1] * k[2], n * shape.to * shape.ho * shape.wo] and out[4] == 1
+    assert lib.avid_conv_tc_plan(None, 1, None) != 0
